@@ -1,0 +1,73 @@
+/* b200_dit.h — C ABI of libb200dit.so: the sm_100a kernels behind LightX2V's DiT operator surface.
+ *
+ * Conventions:
+ *   - plain device pointers + int64 shapes + a cudaStream_t; no torch types, no allocation, no implicit sync;
+ *   - every kernel is launched on the stream passed in (the caller passes torch.cuda.current_stream(), because
+ *     the reference runs blocks under `torch.cuda.stream(compute_stream)`, transformer_infer.py:92);
+ *   - return 0 on success, a negative code otherwise; b200_last_error() returns a thread-local message
+ *     (the reference's native ABI raises through TORCH_CHECK, lightx2v_kernel/csrc/gemm/nvfp4_scaled_mm_kernels_sm120.cu:253-273;
+ *     the Python shim turns a non-zero return into RuntimeError);
+ *   - bf16 tensors are row-major with an explicit leading dimension in ELEMENTS; pointers 16-byte aligned.
+ *
+ * Each entry point cites the reference interface it replaces (paths relative to the LightX2V tree).
+ */
+#ifndef B200_DIT_H_
+#define B200_DIT_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct CUstream_st* b200_stream_t; /* == cudaStream_t */
+
+#define B200_OK 0
+#define B200_ERR_INVALID (-1)
+#define B200_ERR_CUDA (-2)
+#define B200_ERR_UNSUPPORTED (-3)
+
+/* Library / device introspection. */
+const char* b200_last_error(void);
+int b200_version(void);
+int b200_num_sms(void);
+
+/* GEMM epilogues (fusions of the elementwise passes that follow each linear in WanTransformerInfer). */
+#define B200_EPI_BIAS 0          /* C = bf16(A B^T + bias)                         mm_weight.py:81-88            */
+#define B200_EPI_BIAS_GELU 1     /* C = gelu_tanh(bf16(A B^T + bias))              + transformer_infer.py:492     */
+#define B200_EPI_GATE_RESIDUAL 2 /* C = C + bf16(bf16(A B^T + bias) * gate[n])     + transformer_infer.py:402,503 */
+#define B200_EPI_RESIDUAL 3      /* C = C + bf16(A B^T + bias)                     + transformer_infer.py:468     */
+
+/* C[M,N] = epilogue(A[M,K] * B[N,K]^T + bias[N]).  A, B, C bf16 row-major (B is the checkpoint's [N,K] weight, the
+ * storage MMWeight.load keeps as a transposed view, lightx2v/common/ops/mm/mm_weight.py:76).  bias / gate may be NULL
+ * (gate required for B200_EPI_GATE_RESIDUAL).  K, N multiples of 8.  block_n: 0 = auto, 128 or 256.  max_ctas: 0 = one
+ * per SM.  Replaces MMWeight.apply (mm_weight.py:81-88). */
+int b200_gemm_bf16(const void* A, int64_t lda, const void* B, int64_t ldb, void* C, int64_t ldc, const void* bias,
+                   const void* gate, int64_t M, int64_t N, int64_t K, int epilogue, int block_n, int max_ctas,
+                   b200_stream_t stream);
+
+/* y = LayerNorm(x; eps) [* ln_w + ln_b]  then optionally  y = bf16(bf16(y * bf16(1 + scale)) + shift).
+ * ln_w/ln_b NULL -> no affine (norm1/norm2); scale/shift NULL -> no modulation (norm3).
+ * Replaces LNWeight.apply (lightx2v/common/ops/norm/layer_norm_weight.py:100-111) + the in-place
+ * `norm_out.mul_(1+scale).add_(shift)` (lightx2v/models/networks/wan/infer/transformer_infer.py:326-334,478-484). */
+int b200_ln_modulate(const void* x, int64_t ldx, void* y, int64_t ldy, const void* ln_w, const void* ln_b,
+                     const void* scale, const void* shift, int64_t rows, int D, float eps, b200_stream_t stream);
+
+/* In-place RMSNorm over the full row (D) of x0 (and x1 if non-NULL, e.g. q and k inside one fused QKV buffer),
+ * bf16 arithmetic as RMSWeightSgl.apply's torch fallback (lightx2v/common/ops/norm/rms_norm_weight.py:102-118), then,
+ * if cos_sin != NULL, RoPE on adjacent pairs per 128-wide head with table cos_sin[(row + pos_offset), 64] float2
+ * (apply_rotary_emb, lightx2v/models/networks/wan/infer/utils.py:107-115) for rows < rope_rows. */
+int b200_rms_rope(void* x0, int64_t ld0, const void* w0, void* x1, int64_t ld1, const void* w1, int64_t rows, int D,
+                  float eps, const void* cos_sin, int64_t rope_rows, int64_t pos_offset, b200_stream_t stream);
+
+/* out[sq, H, 128] = softmax(q k^T * softmax_scale) v for one varlen segment, non-causal, head_dim 128.
+ * q/k/v/out are [rows, H, 128] bf16 with row strides in elements (heads contiguous).
+ * Replaces FlashAttn2Weight.apply / flash_attn_varlen_func (lightx2v/common/ops/attn/attn_weight.py:71-97). */
+int b200_fmha_fwd_d128(const void* q, int64_t q_stride_s, const void* k, int64_t k_stride_s, const void* v,
+                       int64_t v_stride_s, void* out, int64_t o_stride_s, int64_t sq, int64_t sk, int heads,
+                       float softmax_scale, b200_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200_DIT_H_ */

@@ -1,0 +1,370 @@
+// Fused multi-head attention forward, head_dim 128, non-causal, one varlen segment per launch.
+//
+// Replaces FlashAttn2Weight.apply = flash_attn_varlen_func(q, k, v, cu_q, cu_k, max_q, max_k)
+// (reference: lightx2v/common/ops/attn/attn_weight.py:71-97; softmax scale d^-0.5, no dropout, non-causal,
+// SURVEY appendix A.8) for Wan self-attention (Sq = Sk = 75 600), Wan cross-attention (Sk = 512 / 257) and the
+// Hunyuan joint attention segments.
+//
+// sm_100a design (one CTA per SM, 2 x 128 query rows of one head per CTA, ping-pong):
+//   warp 0        TMA producer: Q (once), then K_0 V_0 K_1 V_1 ... through a 4-deep 32 KB ring
+//   warp 1        MMA issuer:   S_t = Q_t K_j^T   (tcgen05.mma SS, fp32 S in TMEM)
+//                               O_t += P_t V_j    (tcgen05.mma TS: P read from TMEM, V MN-major from smem)
+//   warp 2        TMEM allocator (512 columns: S0 | S1 | O0 | O1; P_t aliases the first 64 columns of S_t as bf16)
+//   warps 4..7    softmax for query tile 0: tcgen05.ld S row -> online max/sum with lazy rescale -> exp2 ->
+//   warps 8..11   softmax for query tile 1:   bf16 P -> tcgen05.st; O rescale in TMEM when the max moved by > 2^8;
+//                                             final O / l -> bf16 -> global.
+// While the softmax warpgroup of one tile works on S_{j+1}, the tensor pipe runs PV_j and QK_{j+1} of the other tile.
+#include "host_util.cuh"
+#include "ptx.cuh"
+
+namespace b200 {
+
+constexpr int FMHA_D = 128;
+constexpr int FMHA_BLOCK_Q = 128;   // rows per query tile; two tiles per CTA
+constexpr int FMHA_BLOCK_KV = 128;
+constexpr int FMHA_THREADS = 384;
+constexpr int FMHA_KV_STAGES = 4;
+constexpr int FMHA_TILE_BYTES = 128 * 128 * 2;   // 32 KB: [128 rows][128 d] bf16 as two [128][64] swizzled panels
+constexpr int FMHA_PANEL_BYTES = 128 * 64 * 2;   // 16 KB
+constexpr int FMHA_SMEM_BYTES = 2 * FMHA_TILE_BYTES + FMHA_KV_STAGES * FMHA_TILE_BYTES + 1024 + 256;
+
+struct FmhaParams {
+  int sq, sk;               // rows of this segment
+  int num_kv_tiles;
+  float scale_log2;         // softmax_scale * log2(e)
+  __nv_bfloat16* out;       // [sq, H, 128] (+ stride)
+  long long o_stride_s;     // elements between consecutive rows of out
+};
+
+__device__ __forceinline__ float ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+__global__ void __launch_bounds__(FMHA_THREADS, 1)
+fmha_fwd_d128_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                     const __grid_constant__ CUtensorMap tmV, const FmhaParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;                             // 2 x 32 KB
+  uint8_t* sKV = smem + 2 * FMHA_TILE_BYTES;      // 4 x 32 KB ring
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sKV + FMHA_KV_STAGES * FMHA_TILE_BYTES);
+  uint64_t* q_full = bars;               // [1]
+  uint64_t* kv_full = bars + 1;          // [4]
+  uint64_t* kv_empty = bars + 5;         // [4]
+  uint64_t* s_full = bars + 9;           // [2]
+  uint64_t* p_full = bars + 11;          // [2]
+  uint64_t* o_full = bars + 13;          // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 15);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int head = blockIdx.y;
+  const int q0 = blockIdx.x * (2 * FMHA_BLOCK_Q);
+  const int n_kv = p.num_kv_tiles;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmQ);
+    prefetch_tmap(&tmK);
+    prefetch_tmap(&tmV);
+  }
+  if (warp == 1 && lane == 0) {
+    mbar_init(q_full, 1);
+    for (int i = 0; i < FMHA_KV_STAGES; ++i) {
+      mbar_init(&kv_full[i], 1);
+      mbar_init(&kv_empty[i], 1);
+    }
+    for (int t = 0; t < 2; ++t) {
+      mbar_init(&s_full[t], 1);
+      mbar_init(&p_full[t], 128);
+      mbar_init(&o_full[t], 1);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  // column offsets
+  constexpr uint32_t COL_S0 = 0, COL_S1 = 128, COL_O0 = 256, COL_O1 = 384;
+
+  if (warp < 4) {
+   // warpgroup 0 (load / mma / alloc / idle) donates registers to the softmax warps
+   reg_dealloc<80>();
+   if (warp == 0) {
+    // ============================== TMA producer ==============================
+    if (lane == 0) {
+      mbar_arrive_expect_tx(q_full, 2 * FMHA_TILE_BYTES);
+      for (int t = 0; t < 2; ++t)
+        for (int h = 0; h < 2; ++h)
+          tma_load_3d(sQ + t * FMHA_TILE_BYTES + h * FMHA_PANEL_BYTES, &tmQ, q_full, h * 64, head,
+                      q0 + t * FMHA_BLOCK_Q);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int it = 0; it < 2 * n_kv; ++it) {   // K_0, V_0, K_1, V_1, ...
+        const int j = it >> 1;
+        const CUtensorMap* tm = (it & 1) ? &tmV : &tmK;
+        mbar_wait(&kv_empty[stage], phase ^ 1);
+        mbar_arrive_expect_tx(&kv_full[stage], FMHA_TILE_BYTES);
+        for (int h = 0; h < 2; ++h)
+          tma_load_3d(sKV + stage * FMHA_TILE_BYTES + h * FMHA_PANEL_BYTES, tm, &kv_full[stage], h * 64, head,
+                      j * FMHA_BLOCK_KV);
+        if (++stage == FMHA_KV_STAGES) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ============================== MMA issuer ==============================
+    if (lane == 0) {
+      constexpr uint32_t idesc_qk = make_idesc(FMT_BF16, FMT_BF16, 128, 128, 0, 0);  // A=Q K-major, B=K K-major
+      constexpr uint32_t idesc_pv = make_idesc(FMT_BF16, FMT_BF16, 128, 128, 0, 1);  // A=P (TMEM), B=V MN-major
+      const uint32_t tS[2] = {tmem_base + COL_S0, tmem_base + COL_S1};
+      const uint32_t tO[2] = {tmem_base + COL_O0, tmem_base + COL_O1};
+
+      auto issue_qk = [&](int t, int kstage) {
+        const uint32_t qa = smem_u32(sQ + t * FMHA_TILE_BYTES);
+        const uint32_t kb = smem_u32(sKV + kstage * FMHA_TILE_BYTES);
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks) {  // d = 128 in steps of 16; 4 steps per 64-wide panel
+          const uint32_t off = (ks >> 2) * FMHA_PANEL_BYTES + (ks & 3) * 32;
+          mma_f16_ss(tS[t], make_desc_kmajor_sw128(qa + off), make_desc_kmajor_sw128(kb + off), idesc_qk,
+                     ks != 0 ? 1u : 0u);
+        }
+      };
+      auto issue_pv = [&](int t, int vstage, bool accumulate) {
+        const uint32_t vb = smem_u32(sKV + vstage * FMHA_TILE_BYTES);
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks) {  // kv = 128 in steps of 16 rows (16 x 128 B = 2048 B); P: 8 columns per step
+          mma_f16_ts(tO[t], tS[t] + ks * 8, make_desc_mnmajor_sw128(vb + ks * 2048, FMHA_PANEL_BYTES), idesc_pv,
+                     (accumulate || ks != 0) ? 1u : 0u);
+        }
+      };
+
+      int stage = 0;        // ring position of the next tile to consume
+      uint32_t phase = 0;
+      auto advance = [&]() {
+        if (++stage == FMHA_KV_STAGES) {
+          stage = 0;
+          phase ^= 1;
+        }
+      };
+
+      mbar_wait(q_full, 0);
+      // K_0
+      mbar_wait(&kv_full[stage], phase);
+      tc_fence_after();
+      issue_qk(0, stage);
+      tc_commit(&s_full[0]);
+      issue_qk(1, stage);
+      tc_commit(&s_full[1]);
+      tc_commit(&kv_empty[stage]);
+      advance();
+
+      for (int j = 0; j < n_kv; ++j) {
+        const bool has_next = (j + 1) < n_kv;
+        // V_j
+        const int vstage = stage;
+        mbar_wait(&kv_full[stage], phase);
+        advance();
+        // K_{j+1}
+        const int kstage = stage;
+        if (has_next) {
+          mbar_wait(&kv_full[stage], phase);
+          advance();
+        }
+        const uint32_t pj = j & 1;
+        // ---- tile 0
+        mbar_wait(&p_full[0], pj);
+        tc_fence_after();
+        issue_pv(0, vstage, j > 0);
+        if (has_next) {
+          issue_qk(0, kstage);
+          tc_commit(&s_full[0]);
+        } else {
+          tc_commit(&o_full[0]);
+        }
+        // ---- tile 1
+        mbar_wait(&p_full[1], pj);
+        tc_fence_after();
+        issue_pv(1, vstage, j > 0);
+        tc_commit(&kv_empty[vstage]);
+        if (has_next) {
+          issue_qk(1, kstage);
+          tc_commit(&s_full[1]);
+          tc_commit(&kv_empty[kstage]);
+        } else {
+          tc_commit(&o_full[1]);
+        }
+      }
+    }
+   }
+  } else {
+    // ============================== softmax / correction / epilogue ==============================
+    reg_alloc<216>();
+    const int t = (warp - 4) >> 2;             // query tile 0 / 1
+    const int lg = warp & 3;                   // TMEM lane group of this warp
+    const int row = lg * 32 + lane;            // row inside the query tile
+    const uint32_t lane_off = uint32_t(lg * 32) << 16;
+    const uint32_t tS = tmem_base + (t ? COL_S1 : COL_S0) + lane_off;
+    const uint32_t tO = tmem_base + (t ? COL_O1 : COL_O0) + lane_off;
+    const float sl2 = p.scale_log2;
+
+    float m_used = -INFINITY;   // max the accumulated O / l are expressed against (raw score units)
+    float l_sum = 0.f;
+
+    for (int j = 0; j < n_kv; ++j) {
+      mbar_wait(&s_full[t], j & 1);
+      tc_fence_after();
+      uint32_t s[128];
+      tmem_ld_x32(tS + 0, s + 0);
+      tmem_ld_x32(tS + 32, s + 32);
+      tmem_ld_x32(tS + 64, s + 64);
+      tmem_ld_x32(tS + 96, s + 96);
+      tmem_ld_wait();
+
+      const int kv_valid = p.sk - j * FMHA_BLOCK_KV;   // >= 1
+      if (kv_valid < FMHA_BLOCK_KV) {
+#pragma unroll
+        for (int i = 0; i < 128; ++i)
+          if (i >= kv_valid) s[i] = 0xff800000u;  // -inf
+      }
+      float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+#pragma unroll
+      for (int i = 0; i < 128; i += 4) {
+        mx0 = fmaxf(mx0, __uint_as_float(s[i]));
+        mx1 = fmaxf(mx1, __uint_as_float(s[i + 1]));
+        mx2 = fmaxf(mx2, __uint_as_float(s[i + 2]));
+        mx3 = fmaxf(mx3, __uint_as_float(s[i + 3]));
+      }
+      const float m_new = fmaxf(fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)), m_used);
+
+      if (j == 0) {
+        m_used = m_new;
+      } else {
+        // lazy rescale: only when the running max moved by more than 2^8 in the exp2 domain
+        const bool need = (m_new - m_used) * sl2 > 8.0f;
+        if (__any_sync(0xffffffffu, need)) {
+          float alpha = 1.0f;
+          if (need) {
+            alpha = ex2((m_used - m_new) * sl2);
+            m_used = m_new;
+          }
+          l_sum *= alpha;
+#pragma unroll 1
+          for (int c = 0; c < 128; c += 32) {
+            uint32_t o[32];
+            tmem_ld_x32(tO + c, o);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+            tmem_st_x32(tO + c, o);
+          }
+          tmem_st_wait();
+        }
+      }
+
+      const float neg_m = -m_used * sl2;
+      float sum0 = 0.f, sum1 = 0.f;
+      uint32_t pk[64];
+#pragma unroll
+      for (int i = 0; i < 64; ++i) {
+        const float p0 = ex2(fmaf(__uint_as_float(s[2 * i]), sl2, neg_m));
+        const float p1 = ex2(fmaf(__uint_as_float(s[2 * i + 1]), sl2, neg_m));
+        sum0 += p0;
+        sum1 += p1;
+        pk[i] = pack_bf16(p0, p1);
+      }
+      l_sum += sum0 + sum1;
+      tmem_st_x32(tS + 0, pk + 0);    // P (bf16 pairs) overwrites the first 64 columns of S
+      tmem_st_x32(tS + 32, pk + 32);
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive(&p_full[t]);
+    }
+
+    // ---- epilogue: O / l -> bf16 -> global
+    mbar_wait(&o_full[t], 0);
+    tc_fence_after();
+    const float inv_l = 1.0f / l_sum;
+    const int q_row = q0 + t * FMHA_BLOCK_Q + row;
+    __nv_bfloat16* orow = p.out + (long long)q_row * p.o_stride_s + (long long)head * FMHA_D;
+#pragma unroll 1
+    for (int c = 0; c < 128; c += 32) {
+      uint32_t o[32];
+      tmem_ld_x32(tO + c, o);
+      tmem_ld_wait();
+      if (q_row < p.sq) {
+#pragma unroll
+        for (int v = 0; v < 4; ++v) {
+          uint4 w;
+          w.x = pack_bf16(__uint_as_float(o[v * 8 + 0]) * inv_l, __uint_as_float(o[v * 8 + 1]) * inv_l);
+          w.y = pack_bf16(__uint_as_float(o[v * 8 + 2]) * inv_l, __uint_as_float(o[v * 8 + 3]) * inv_l);
+          w.z = pack_bf16(__uint_as_float(o[v * 8 + 4]) * inv_l, __uint_as_float(o[v * 8 + 5]) * inv_l);
+          w.w = pack_bf16(__uint_as_float(o[v * 8 + 6]) * inv_l, __uint_as_float(o[v * 8 + 7]) * inv_l);
+          *reinterpret_cast<uint4*>(orow + c + v * 8) = w;
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// q/k/v: [rows, H, 128] bf16 with arbitrary row stride (elements), heads contiguous (stride 128).
+static int encode_qkv_map(CUtensorMap* tm, const void* base, long long rows, int heads, long long stride_s) {
+  uint64_t dims[3] = {128, (uint64_t)heads, (uint64_t)rows};
+  uint64_t strides[2] = {128 * 2, (uint64_t)stride_s * 2};
+  uint32_t box[3] = {64, 1, 128};
+  return encode_tmap(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, base, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
+}
+
+int fmha_fwd_d128(const void* q, long long q_stride_s, const void* k, long long k_stride_s, const void* v,
+                  long long v_stride_s, void* out, long long o_stride_s, long long sq, long long sk, int heads,
+                  float softmax_scale, cudaStream_t stream) {
+  B200_CHECK_ARG(q && k && v && out, "b200_fmha_fwd_d128: null pointer");
+  B200_CHECK_ARG(sq > 0 && sk > 0 && heads > 0, "b200_fmha_fwd_d128: empty problem sq=%lld sk=%lld heads=%d", sq, sk,
+                 heads);
+  B200_CHECK_ARG(q_stride_s % 8 == 0 && k_stride_s % 8 == 0 && v_stride_s % 8 == 0 && o_stride_s % 8 == 0,
+                 "b200_fmha_fwd_d128: row strides must be multiples of 8 elements");
+  B200_CHECK_ARG(q_stride_s >= heads * 128LL && k_stride_s >= heads * 128LL && v_stride_s >= heads * 128LL &&
+                     o_stride_s >= heads * 128LL,
+                 "b200_fmha_fwd_d128: row stride smaller than heads*128");
+  B200_CHECK_ARG(((uintptr_t)q % 16 == 0) && ((uintptr_t)k % 16 == 0) && ((uintptr_t)v % 16 == 0) &&
+                     ((uintptr_t)out % 16 == 0),
+                 "b200_fmha_fwd_d128: pointers must be 16-byte aligned");
+  CUtensorMap tmQ, tmK, tmV;
+  int rc;
+  if ((rc = encode_qkv_map(&tmQ, q, sq, heads, q_stride_s))) return rc;
+  if ((rc = encode_qkv_map(&tmK, k, sk, heads, k_stride_s))) return rc;
+  if ((rc = encode_qkv_map(&tmV, v, sk, heads, v_stride_s))) return rc;
+
+  FmhaParams p;
+  p.sq = (int)sq;
+  p.sk = (int)sk;
+  p.num_kv_tiles = (int)((sk + FMHA_BLOCK_KV - 1) / FMHA_BLOCK_KV);
+  p.scale_log2 = softmax_scale * 1.4426950408889634f;
+  p.out = reinterpret_cast<__nv_bfloat16*>(out);
+  p.o_stride_s = o_stride_s;
+
+  static bool attr_set = false;
+  if (!attr_set) {
+    B200_CHECK_CUDA(cudaFuncSetAttribute(fmha_fwd_d128_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         FMHA_SMEM_BYTES));
+    attr_set = true;
+  }
+  dim3 grid((unsigned)((sq + 2 * FMHA_BLOCK_Q - 1) / (2 * FMHA_BLOCK_Q)), (unsigned)heads, 1);
+  fmha_fwd_d128_kernel<<<grid, FMHA_THREADS, FMHA_SMEM_BYTES, stream>>>(tmQ, tmK, tmV, p);
+  B200_CHECK_CUDA(cudaGetLastError());
+  return B200_OK;
+}
+
+}  // namespace b200

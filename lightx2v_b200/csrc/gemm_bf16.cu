@@ -1,0 +1,348 @@
+// bf16 NT GEMM for the DiT linears:  C[M,N] = epilogue(A[M,K] * B[N,K]^T + bias)
+//
+// Replaces MMWeight.apply = torch.addmm(bias, x, W.t())  (reference: lightx2v/common/ops/mm/mm_weight.py:81-88;
+// B is the checkpoint's [N,K] row-major weight, i.e. an NT GEMM) and absorbs the
+// elementwise passes that follow it in WanTransformerInfer (transformer_infer.py:402,468,492,503).
+//
+// sm_100a design: persistent warp-specialised kernel, one CTA per SM.
+//   warp 0      : TMA producer  (cp.async.bulk.tensor, 128B-swizzled K-major tiles, kStages-deep mbarrier ring)
+//   warp 1      : MMA issuer    (tcgen05.mma cta_group::1 kind::f16, M=128, N=BLOCK_N, K=16; fp32 accumulators in TMEM,
+//                                two accumulator stages so the epilogue of tile i overlaps the mainloop of tile i+1)
+//   warp 2      : TMEM allocator
+//   warps 4..7  : epilogue      (tcgen05.ld -> registers -> bias / GELU / gate*y+residual -> swizzled smem -> TMA store)
+#include "host_util.cuh"
+#include "ptx.cuh"
+
+namespace b200 {
+
+enum GemmEpilogue : int {
+  EPI_BIAS = 0,           // C = bf16(acc + bias)
+  EPI_BIAS_GELU = 1,      // C = bf16(gelu_tanh(bf16(acc + bias)))
+  EPI_GATE_RESIDUAL = 2,  // C = bf16(C + bf16(bf16(acc + bias) * gate[n]))      (in place on C)
+  EPI_RESIDUAL = 3,       // C = bf16(C + bf16(acc + bias))                        (in place on C)
+};
+
+constexpr int GEMM_BLOCK_M = 128;
+constexpr int GEMM_BLOCK_K = 64;   // 64 bf16 = 128 bytes = one swizzle-128B row
+constexpr int GEMM_UMMA_K = 16;
+constexpr int GEMM_THREADS = 256;
+constexpr int GEMM_EPI_THREADS = 128;
+constexpr int GEMM_EPI_CHUNK = 64;  // columns per epilogue store chunk (128 bytes of bf16)
+
+template <int BLOCK_N>
+struct GemmCfg {
+  static constexpr int kStages = (BLOCK_N == 256) ? 4 : 6;
+  static constexpr int kABytes = GEMM_BLOCK_M * GEMM_BLOCK_K * 2;       // 16 KB
+  static constexpr int kBBytes = BLOCK_N * GEMM_BLOCK_K * 2;            // 32 / 16 KB
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kStagingBytes = GEMM_BLOCK_M * GEMM_EPI_CHUNK * 2;  // 16 KB, x2 buffers
+  static constexpr int kTmemCols = 2 * BLOCK_N;                         // two accumulator stages
+  static constexpr int kSmemBytes = kStages * kStageBytes + 2 * kStagingBytes + 1024 /*align*/ + 256 /*barriers*/;
+};
+
+struct GemmParams {
+  int M, N, K;
+  int num_m_blocks, num_n_blocks, num_k_blocks;
+  const __nv_bfloat16* bias;   // [N] or null
+  const __nv_bfloat16* gate;   // [N] (EPI_GATE_RESIDUAL)
+  __nv_bfloat16* C;            // residual source (in-place epilogues)
+  long long ldc;
+};
+
+// Tile rasterisation: groups of kGroupM m-blocks, n fastest inside a group-row sweep, so the ~148 tiles in flight
+// touch ~16 A panels and ~10 B panels (L2-resident) instead of 148 A panels.
+__device__ __forceinline__ void tile_coords(int tile, const GemmParams& p, int& m_blk, int& n_blk) {
+  constexpr int kGroupM = 16;
+  const int tiles_per_group = kGroupM * p.num_n_blocks;
+  const int group = tile / tiles_per_group;
+  const int first_m = group * kGroupM;
+  const int group_m = min(kGroupM, p.num_m_blocks - first_m);
+  const int in_group = tile - group * tiles_per_group;
+  m_blk = first_m + in_group % group_m;
+  n_blk = in_group / group_m;
+}
+
+__device__ __forceinline__ float gelu_tanh_f(float x) {
+  // torch.nn.functional.gelu(approximate="tanh")
+  const float k0 = 0.7978845608028654f, k1 = 0.044715f;
+  float inner = k0 * (x + k1 * x * x * x);
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(inner));
+  return 0.5f * x * (1.0f + t);
+}
+
+template <int BLOCK_N, int EPI>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                 const __grid_constant__ CUtensorMap tmC, const GemmParams p) {
+  using Cfg = GemmCfg<BLOCK_N>;
+  constexpr int kStages = Cfg::kStages;
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sA = smem;                                   // kStages x 16 KB
+  uint8_t* sB = smem + kStages * Cfg::kABytes;          // kStages x kBBytes
+  uint8_t* sStage = smem + kStages * Cfg::kStageBytes;  // 2 x 16 KB epilogue staging
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sStage + 2 * Cfg::kStagingBytes);
+  uint64_t* full_bar = bars;                  // [kStages]
+  uint64_t* empty_bar = bars + kStages;       // [kStages]
+  uint64_t* tmem_full_bar = bars + 2 * kStages;       // [2]
+  uint64_t* tmem_empty_bar = bars + 2 * kStages + 2;  // [2]
+  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int num_tiles = p.num_m_blocks * p.num_n_blocks;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmA);
+    prefetch_tmap(&tmB);
+    prefetch_tmap(&tmC);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < kStages; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tmem_full_bar[i], 1);
+      mbar_init(&tmem_empty_bar[i], GEMM_EPI_THREADS);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_base_slot, Cfg::kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_base_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        int m_blk, n_blk;
+        tile_coords(tile, p, m_blk, n_blk);
+        for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+          tma_load_2d(sA + stage * Cfg::kABytes, &tmA, &full_bar[stage], kb * GEMM_BLOCK_K, m_blk * GEMM_BLOCK_M);
+          tma_load_2d(sB + stage * Cfg::kBBytes, &tmB, &full_bar[stage], kb * GEMM_BLOCK_K, n_blk * BLOCK_N);
+          if (++stage == kStages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(FMT_BF16, FMT_BF16, GEMM_BLOCK_M, BLOCK_N, 0, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
+        for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint64_t a_desc = make_desc_kmajor_sw128(smem_u32(sA + stage * Cfg::kABytes));
+          const uint64_t b_desc = make_desc_kmajor_sw128(smem_u32(sB + stage * Cfg::kBBytes));
+#pragma unroll
+          for (int k = 0; k < GEMM_BLOCK_K / GEMM_UMMA_K; ++k) {
+            // +32 bytes along K inside the 128B swizzle row = +2 in the (addr >> 4) field
+            mma_f16_ss(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          tc_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs have read it
+          if (++stage == kStages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        tc_commit(&tmem_full_bar[acc]);  // accumulator complete -> epilogue
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue =====================
+    const int ewarp = warp - 4;               // == warp % 4 -> TMEM lane group
+    const int row = ewarp * 32 + lane;        // row inside the 128-row tile
+    const int et = threadIdx.x - 128;         // 0..127
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    int sbuf = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      int m_blk, n_blk;
+      tile_coords(tile, p, m_blk, n_blk);
+      const int m0 = m_blk * GEMM_BLOCK_M;
+      const int n0 = n_blk * BLOCK_N;
+      mbar_wait(&tmem_full_bar[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t t_row = tmem_base + acc * BLOCK_N + (uint32_t(ewarp * 32) << 16);
+      const bool row_ok = (m0 + row) < p.M;
+
+#pragma unroll 1
+      for (int c = 0; c < BLOCK_N / GEMM_EPI_CHUNK; ++c) {
+        const int ncol0 = n0 + c * GEMM_EPI_CHUNK;
+        if (ncol0 >= p.N) break;  // uniform across the CTA
+        uint32_t v[64];
+        tmem_ld_x32(t_row + c * GEMM_EPI_CHUNK, v);
+        tmem_ld_x32(t_row + c * GEMM_EPI_CHUNK + 32, v + 32);
+
+        // staging buffer `sbuf` must have been drained by the TMA store issued two chunks ago
+        if (et == 0) tma_store_wait_read<1>();
+        named_bar_sync(1, GEMM_EPI_THREADS);
+        tmem_ld_wait();
+
+        uint8_t* stg = sStage + sbuf * Cfg::kStagingBytes;
+        const __nv_bfloat16* res_row = p.C + (long long)(m0 + row) * p.ldc + ncol0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {  // 8 columns (one 16-byte chunk) at a time
+          const int col = ncol0 + j * 8;
+          float f[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(v[j * 8 + e]);
+          if (p.bias != nullptr && col < p.N) {
+            uint4 bv = __ldg(reinterpret_cast<const uint4*>(p.bias + col));
+            const uint32_t bw[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              f[2 * e] += bf16_lo(bw[e]);
+              f[2 * e + 1] += bf16_hi(bw[e]);
+            }
+          }
+          if constexpr (EPI == EPI_BIAS_GELU) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) f[e] = gelu_tanh_f(bf16_round(f[e]));
+          }
+          if constexpr (EPI == EPI_GATE_RESIDUAL || EPI == EPI_RESIDUAL) {
+            uint4 rv = make_uint4(0, 0, 0, 0);
+            if (row_ok && col < p.N) rv = *reinterpret_cast<const uint4*>(res_row + j * 8);
+            const uint32_t rw[4] = {rv.x, rv.y, rv.z, rv.w};
+            if constexpr (EPI == EPI_GATE_RESIDUAL) {
+              uint4 gv = make_uint4(0, 0, 0, 0);
+              if (col < p.N) gv = __ldg(reinterpret_cast<const uint4*>(p.gate + col));
+              const uint32_t gw[4] = {gv.x, gv.y, gv.z, gv.w};
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                // reference rounding points: y -> bf16, y*gate -> bf16, x + (.) -> bf16
+                f[2 * e] = bf16_lo(rw[e]) + bf16_round(bf16_round(f[2 * e]) * bf16_lo(gw[e]));
+                f[2 * e + 1] = bf16_hi(rw[e]) + bf16_round(bf16_round(f[2 * e + 1]) * bf16_hi(gw[e]));
+              }
+            } else {
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                f[2 * e] = bf16_lo(rw[e]) + bf16_round(f[2 * e]);
+                f[2 * e + 1] = bf16_hi(rw[e]) + bf16_round(f[2 * e + 1]);
+              }
+            }
+          }
+          uint4 o;
+          o.x = pack_bf16(f[0], f[1]);
+          o.y = pack_bf16(f[2], f[3]);
+          o.z = pack_bf16(f[4], f[5]);
+          o.w = pack_bf16(f[6], f[7]);
+          // 128B-swizzled staging row: 16-byte chunk j of row r lives at chunk (j ^ (r & 7))
+          *reinterpret_cast<uint4*>(stg + row * 128 + ((j ^ (row & 7)) << 4)) = o;
+        }
+        fence_async_smem();
+        named_bar_sync(1, GEMM_EPI_THREADS);
+        if (et == 0) {
+          tma_store_2d(&tmC, stg, ncol0, m0);
+          tma_store_commit();
+        }
+        sbuf ^= 1;
+      }
+      // accumulator stage fully read -> hand it back to the MMA warp
+      tc_fence_before();
+      mbar_arrive(&tmem_empty_bar[acc]);
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+    if (et == 0) tma_store_wait_all<0>();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::kTmemCols);
+  }
+}
+
+template <int BLOCK_N, int EPI>
+static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const GemmParams& p,
+                       int max_ctas, cudaStream_t stream) {
+  using Cfg = GemmCfg<BLOCK_N>;
+  auto kern = gemm_bf16_kernel<BLOCK_N, EPI>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    B200_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    attr_set = true;
+  }
+  const int num_tiles = p.num_m_blocks * p.num_n_blocks;
+  int grid = num_tiles < max_ctas ? num_tiles : max_ctas;
+  kern<<<grid, GEMM_THREADS, Cfg::kSmemBytes, stream>>>(tmA, tmB, tmC, p);
+  B200_CHECK_CUDA(cudaGetLastError());
+  return B200_OK;
+}
+
+template <int BLOCK_N>
+static int dispatch_epi(int epi, const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC,
+                        const GemmParams& p, int max_ctas, cudaStream_t stream) {
+  switch (epi) {
+    case EPI_BIAS: return launch_gemm<BLOCK_N, EPI_BIAS>(tmA, tmB, tmC, p, max_ctas, stream);
+    case EPI_BIAS_GELU: return launch_gemm<BLOCK_N, EPI_BIAS_GELU>(tmA, tmB, tmC, p, max_ctas, stream);
+    case EPI_GATE_RESIDUAL: return launch_gemm<BLOCK_N, EPI_GATE_RESIDUAL>(tmA, tmB, tmC, p, max_ctas, stream);
+    case EPI_RESIDUAL: return launch_gemm<BLOCK_N, EPI_RESIDUAL>(tmA, tmB, tmC, p, max_ctas, stream);
+  }
+  set_last_error("b200_gemm_bf16: unknown epilogue %d", epi);
+  return B200_ERR_INVALID;
+}
+
+int gemm_bf16(const void* A, long long lda, const void* B, long long ldb, void* C, long long ldc, const void* bias,
+              const void* gate, long long M, long long N, long long K, int epilogue, int block_n, int max_ctas,
+              cudaStream_t stream) {
+  B200_CHECK_ARG(A && B && C, "b200_gemm_bf16: null operand pointer");
+  B200_CHECK_ARG(M > 0 && N > 0 && K > 0, "b200_gemm_bf16: non-positive shape M=%lld N=%lld K=%lld", M, N, K);
+  B200_CHECK_ARG(K % 8 == 0 && N % 8 == 0, "b200_gemm_bf16: K (%lld) and N (%lld) must be multiples of 8", K, N);
+  B200_CHECK_ARG(lda % 8 == 0 && ldb % 8 == 0 && ldc % 8 == 0 && lda >= K && ldb >= K && ldc >= N,
+                 "b200_gemm_bf16: leading dimensions must be multiples of 8 and cover the row (lda=%lld ldb=%lld ldc=%lld)",
+                 lda, ldb, ldc);
+  B200_CHECK_ARG(((uintptr_t)A % 16 == 0) && ((uintptr_t)B % 16 == 0) && ((uintptr_t)C % 16 == 0),
+                 "b200_gemm_bf16: operands must be 16-byte aligned");
+  B200_CHECK_ARG(epilogue != EPI_GATE_RESIDUAL || gate != nullptr, "b200_gemm_bf16: gate epilogue needs a gate vector");
+  B200_CHECK_ARG((bias == nullptr || (uintptr_t)bias % 16 == 0) && (gate == nullptr || (uintptr_t)gate % 16 == 0),
+                 "b200_gemm_bf16: bias / gate must be 16-byte aligned");
+  if (block_n == 0) block_n = (N >= 256) ? 256 : 128;
+  B200_CHECK_ARG(block_n == 128 || block_n == 256, "b200_gemm_bf16: block_n must be 128 or 256");
+  if (max_ctas <= 0) max_ctas = num_sms();
+
+  CUtensorMap tmA, tmB, tmC;
+  int rc;
+  if ((rc = encode_tmap_2d_bf16(&tmA, A, M, K, lda, GEMM_BLOCK_M, GEMM_BLOCK_K))) return rc;
+  if ((rc = encode_tmap_2d_bf16(&tmB, B, N, K, ldb, block_n, GEMM_BLOCK_K))) return rc;
+  if ((rc = encode_tmap_2d_bf16(&tmC, C, M, N, ldc, GEMM_BLOCK_M, GEMM_EPI_CHUNK))) return rc;
+
+  GemmParams p;
+  p.M = (int)M;
+  p.N = (int)N;
+  p.K = (int)K;
+  p.num_m_blocks = (int)((M + GEMM_BLOCK_M - 1) / GEMM_BLOCK_M);
+  p.num_n_blocks = (int)((N + block_n - 1) / block_n);
+  p.num_k_blocks = (int)((K + GEMM_BLOCK_K - 1) / GEMM_BLOCK_K);
+  p.bias = reinterpret_cast<const __nv_bfloat16*>(bias);
+  p.gate = reinterpret_cast<const __nv_bfloat16*>(gate);
+  p.C = reinterpret_cast<__nv_bfloat16*>(C);
+  p.ldc = ldc;
+  if (block_n == 256) return dispatch_epi<256>(epilogue, tmA, tmB, tmC, p, max_ctas, stream);
+  return dispatch_epi<128>(epilogue, tmA, tmB, tmC, p, max_ctas, stream);
+}
+
+}  // namespace b200

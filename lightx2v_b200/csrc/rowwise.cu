@@ -1,0 +1,233 @@
+// HBM-bound row-wise kernels of the DiT block: LayerNorm (+AdaLN modulation), full-width q/k RMSNorm (+3-axis RoPE).
+// One CTA of 128 threads per token row; the row lives in registers between the statistics pass and the
+// normalise/rotate pass, so every element is read once and written once (algorithmic bytes = 4 B per element).
+//
+// Rounding points mirror the reference's bf16 torch path exactly:
+//   LayerNorm  : F.layer_norm(bf16) -> bf16, then .mul_(1+scale) -> bf16, .add_(shift) -> bf16
+//                (lightx2v/models/networks/wan/infer/transformer_infer.py:326-334,478-484; layer_norm_weight.py:100-111)
+//   RMSNorm    : x * rsqrt(x.pow(2).mean(-1) + eps) * w, every intermediate a bf16 tensor
+//                (lightx2v/common/ops/norm/rms_norm_weight.py:111-113 — the fallback taken when sgl_kernel is absent)
+//   RoPE       : complex multiply of adjacent pairs (2i, 2i+1) by freqs[pos, i], one rounding to bf16
+//                (lightx2v/models/networks/wan/infer/utils.py:107-115); the reference does it in complex128,
+//                here fp32 on a cos/sin table prepared in fp64 on the host.
+#include "host_util.cuh"
+#include "ptx.cuh"
+
+namespace b200 {
+
+constexpr int ROW_THREADS = 128;
+constexpr int ROW_MAX_VEC = 8;  // up to 8 x 8 elements per thread -> D <= 8192
+
+__device__ __forceinline__ float block_sum_128(float v, float* red) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  const int w = threadIdx.x >> 5;
+  if ((threadIdx.x & 31) == 0) red[w] = v;
+  __syncthreads();
+  float t = red[0] + red[1] + red[2] + red[3];
+  __syncthreads();
+  return t;
+}
+
+__device__ __forceinline__ void unpack8(const uint4& v, float* f) {
+  f[0] = bf16_lo(v.x); f[1] = bf16_hi(v.x);
+  f[2] = bf16_lo(v.y); f[3] = bf16_hi(v.y);
+  f[4] = bf16_lo(v.z); f[5] = bf16_hi(v.z);
+  f[6] = bf16_lo(v.w); f[7] = bf16_hi(v.w);
+}
+__device__ __forceinline__ uint4 pack8(const float* f) {
+  uint4 o;
+  o.x = pack_bf16(f[0], f[1]);
+  o.y = pack_bf16(f[2], f[3]);
+  o.z = pack_bf16(f[4], f[5]);
+  o.w = pack_bf16(f[6], f[7]);
+  return o;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// LayerNorm (eps, optional affine weight/bias) followed by optional AdaLN modulation  y = bf16(bf16(n * w1) + shift)
+// with w1 = bf16(1 + scale).  `scale` / `shift` are [D] bf16 vectors (one per block and pass).
+// ---------------------------------------------------------------------------------------------------------
+template <bool kAffine, bool kModulate>
+__global__ void __launch_bounds__(ROW_THREADS)
+ln_modulate_kernel(const __nv_bfloat16* __restrict__ x, long long ldx, __nv_bfloat16* __restrict__ y, long long ldy,
+                   const __nv_bfloat16* __restrict__ ln_w, const __nv_bfloat16* __restrict__ ln_b,
+                   const __nv_bfloat16* __restrict__ scale, const __nv_bfloat16* __restrict__ shift, int D,
+                   float eps) {
+  __shared__ float red[4];
+  const long long row = blockIdx.x;
+  const int nvec = D >> 3;
+  const uint4* xr = reinterpret_cast<const uint4*>(x + row * ldx);
+  uint4 raw[ROW_MAX_VEC];
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < ROW_MAX_VEC; ++i) {
+    const int v = threadIdx.x + i * ROW_THREADS;
+    if (v < nvec) {
+      raw[i] = xr[v];
+      float f[8];
+      unpack8(raw[i], f);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) sum += f[e];
+    }
+  }
+  const float mean = block_sum_128(sum, red) / (float)D;
+  float sq = 0.f;
+#pragma unroll
+  for (int i = 0; i < ROW_MAX_VEC; ++i) {
+    const int v = threadIdx.x + i * ROW_THREADS;
+    if (v < nvec) {
+      float f[8];
+      unpack8(raw[i], f);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const float d = f[e] - mean;
+        sq += d * d;
+      }
+    }
+  }
+  const float rstd = rsqrtf(block_sum_128(sq, red) / (float)D + eps);
+  uint4* yr = reinterpret_cast<uint4*>(y + row * ldy);
+#pragma unroll
+  for (int i = 0; i < ROW_MAX_VEC; ++i) {
+    const int v = threadIdx.x + i * ROW_THREADS;
+    if (v < nvec) {
+      float f[8];
+      unpack8(raw[i], f);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) f[e] = (f[e] - mean) * rstd;
+      if constexpr (kAffine) {
+        float w[8], b[8];
+        unpack8(__ldg(reinterpret_cast<const uint4*>(ln_w) + v), w);
+        unpack8(__ldg(reinterpret_cast<const uint4*>(ln_b) + v), b);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) f[e] = fmaf(f[e], w[e], b[e]);
+      }
+      if constexpr (kModulate) {
+        float sc[8], sh[8];
+        unpack8(__ldg(reinterpret_cast<const uint4*>(scale) + v), sc);
+        unpack8(__ldg(reinterpret_cast<const uint4*>(shift) + v), sh);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const float w1 = bf16_round(1.0f + sc[e]);
+          f[e] = bf16_round(bf16_round(f[e]) * w1) + sh[e];
+        }
+      }
+      yr[v] = pack8(f);
+    }
+  }
+}
+
+int ln_modulate(const void* x, long long ldx, void* y, long long ldy, const void* ln_w, const void* ln_b,
+                const void* scale, const void* shift, long long rows, int D, float eps, cudaStream_t stream) {
+  B200_CHECK_ARG(x && y, "b200_ln_modulate: null pointer");
+  B200_CHECK_ARG(rows > 0 && D > 0 && D % 8 == 0 && D <= ROW_THREADS * ROW_MAX_VEC * 8,
+                 "b200_ln_modulate: D=%d must be a multiple of 8 and <= %d", D, ROW_THREADS * ROW_MAX_VEC * 8);
+  B200_CHECK_ARG(ldx % 8 == 0 && ldy % 8 == 0 && ldx >= D && ldy >= D, "b200_ln_modulate: bad leading dimension");
+  B200_CHECK_ARG((ln_w == nullptr) == (ln_b == nullptr), "b200_ln_modulate: affine weight and bias go together");
+  B200_CHECK_ARG((scale == nullptr) == (shift == nullptr), "b200_ln_modulate: scale and shift go together");
+  const auto* xp = reinterpret_cast<const __nv_bfloat16*>(x);
+  auto* yp = reinterpret_cast<__nv_bfloat16*>(y);
+  const auto* w = reinterpret_cast<const __nv_bfloat16*>(ln_w);
+  const auto* b = reinterpret_cast<const __nv_bfloat16*>(ln_b);
+  const auto* sc = reinterpret_cast<const __nv_bfloat16*>(scale);
+  const auto* sh = reinterpret_cast<const __nv_bfloat16*>(shift);
+  dim3 grid((unsigned)rows);
+  if (w && sc) ln_modulate_kernel<true, true><<<grid, ROW_THREADS, 0, stream>>>(xp, ldx, yp, ldy, w, b, sc, sh, D, eps);
+  else if (w) ln_modulate_kernel<true, false><<<grid, ROW_THREADS, 0, stream>>>(xp, ldx, yp, ldy, w, b, sc, sh, D, eps);
+  else if (sc) ln_modulate_kernel<false, true><<<grid, ROW_THREADS, 0, stream>>>(xp, ldx, yp, ldy, w, b, sc, sh, D, eps);
+  else ln_modulate_kernel<false, false><<<grid, ROW_THREADS, 0, stream>>>(xp, ldx, yp, ldy, w, b, sc, sh, D, eps);
+  B200_CHECK_CUDA(cudaGetLastError());
+  return B200_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// RMSNorm over `norm_dim` contiguous elements (Wan: the whole row, D; Hunyuan: one head, 128), bf16 arithmetic as in
+// the reference fallback, then optional RoPE on adjacent pairs with a [rows, 64] (cos, sin) fp32 table.
+// In place on up to two tensors at once (q and k of one fused QKV buffer): blockIdx.y selects the tensor.
+// Rows >= rope_rows are normalised but not rotated (apply_rotary_emb keeps x[seq_len:] as is, utils.py:114).
+// ---------------------------------------------------------------------------------------------------------
+struct RmsRopeArgs {
+  __nv_bfloat16* x[2];
+  const __nv_bfloat16* w[2];
+  long long ld[2];
+};
+
+template <bool kRope>
+__global__ void __launch_bounds__(ROW_THREADS)
+rms_rope_kernel(RmsRopeArgs a, int D, float eps, const float2* __restrict__ cs, long long rope_rows,
+                long long pos_offset) {
+  __shared__ float red[4];
+  const long long row = blockIdx.x;
+  const int which = blockIdx.y;
+  const int nvec = D >> 3;
+  uint4* xr = reinterpret_cast<uint4*>(a.x[which] + row * a.ld[which]);
+  const uint4* wr = reinterpret_cast<const uint4*>(a.w[which]);
+  uint4 raw[ROW_MAX_VEC];
+  float ssq = 0.f;
+#pragma unroll
+  for (int i = 0; i < ROW_MAX_VEC; ++i) {
+    const int v = threadIdx.x + i * ROW_THREADS;
+    if (v < nvec) {
+      raw[i] = xr[v];
+      float f[8];
+      unpack8(raw[i], f);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) ssq += bf16_round(f[e] * f[e]);   // x.pow(2) is a bf16 tensor
+    }
+  }
+  // mean(-1) accumulates in fp32 and rounds to bf16; + eps and rsqrt are bf16 tensor ops
+  float ms = bf16_round(block_sum_128(ssq, red) / (float)D);
+  ms = bf16_round(ms + eps);
+  const float rinv = bf16_round(rsqrtf(ms));
+  const bool rotate = kRope && row < rope_rows;
+  const float2* csr = cs + (row + pos_offset) * 64;
+#pragma unroll
+  for (int i = 0; i < ROW_MAX_VEC; ++i) {
+    const int v = threadIdx.x + i * ROW_THREADS;
+    if (v < nvec) {
+      float f[8], w[8];
+      unpack8(raw[i], f);
+      unpack8(__ldg(wr + v), w);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) f[e] = bf16_round(bf16_round(f[e] * rinv) * w[e]);
+      if (rotate) {
+        const int pair0 = ((v * 8) & 127) >> 1;  // pair index inside the head (head_dim 128 -> 64 pairs)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float2 c = __ldg(csr + pair0 + e);
+          const float re = f[2 * e], im = f[2 * e + 1];
+          f[2 * e] = re * c.x - im * c.y;
+          f[2 * e + 1] = re * c.y + im * c.x;
+        }
+      }
+      xr[v] = pack8(f);
+    }
+  }
+}
+
+int rms_rope(void* x0, long long ld0, const void* w0, void* x1, long long ld1, const void* w1, long long rows, int D,
+             float eps, const void* cos_sin, long long rope_rows, long long pos_offset, cudaStream_t stream) {
+  B200_CHECK_ARG(x0 && w0, "b200_rms_rope: null pointer");
+  B200_CHECK_ARG(rows > 0 && D > 0 && D % 128 == 0 && D <= ROW_THREADS * ROW_MAX_VEC * 8,
+                 "b200_rms_rope: D=%d must be a multiple of 128 and <= %d", D, ROW_THREADS * ROW_MAX_VEC * 8);
+  B200_CHECK_ARG(ld0 % 8 == 0 && ld0 >= D && (x1 == nullptr || (ld1 % 8 == 0 && ld1 >= D && w1)),
+                 "b200_rms_rope: bad leading dimension / missing weight");
+  RmsRopeArgs a;
+  a.x[0] = reinterpret_cast<__nv_bfloat16*>(x0);
+  a.w[0] = reinterpret_cast<const __nv_bfloat16*>(w0);
+  a.ld[0] = ld0;
+  a.x[1] = reinterpret_cast<__nv_bfloat16*>(x1);
+  a.w[1] = reinterpret_cast<const __nv_bfloat16*>(w1);
+  a.ld[1] = ld1;
+  dim3 grid((unsigned)rows, x1 ? 2 : 1);
+  if (cos_sin)
+    rms_rope_kernel<true><<<grid, ROW_THREADS, 0, stream>>>(a, D, eps, reinterpret_cast<const float2*>(cos_sin),
+                                                            rope_rows, pos_offset);
+  else
+    rms_rope_kernel<false><<<grid, ROW_THREADS, 0, stream>>>(a, D, eps, nullptr, 0, 0);
+  B200_CHECK_CUDA(cudaGetLastError());
+  return B200_OK;
+}
+
+}  // namespace b200

@@ -1,0 +1,145 @@
+"""ctypes binding of ``libb200dit.so`` (C ABI declared in ``include/b200_dit.h``).
+
+There is no fallback: if the library is missing or a call returns non-zero the caller gets an exception.
+All wrappers take torch CUDA tensors, pass raw device pointers + the *current* torch stream, allocate nothing
+inside the native code and never synchronise.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from typing import Optional
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "libb200dit.so")
+
+# symbol -> (restype, argtypes); mirrors include/b200_dit.h one to one (tests check the header against this table)
+_i64, _i32, _f32, _ptr = ctypes.c_int64, ctypes.c_int, ctypes.c_float, ctypes.c_void_p
+SIGNATURES = {
+    "b200_last_error": (ctypes.c_char_p, []),
+    "b200_version": (_i32, []),
+    "b200_num_sms": (_i32, []),
+    "b200_gemm_bf16": (_i32, [_ptr, _i64, _ptr, _i64, _ptr, _i64, _ptr, _ptr, _i64, _i64, _i64, _i32, _i32, _i32, _ptr]),
+    "b200_ln_modulate": (_i32, [_ptr, _i64, _ptr, _i64, _ptr, _ptr, _ptr, _ptr, _i64, _i32, _f32, _ptr]),
+    "b200_rms_rope": (_i32, [_ptr, _i64, _ptr, _ptr, _i64, _ptr, _i64, _i32, _f32, _ptr, _i64, _i64, _ptr]),
+    "b200_fmha_fwd_d128": (_i32, [_ptr, _i64, _ptr, _i64, _ptr, _i64, _ptr, _i64, _i64, _i64, _i32, _f32, _ptr]),
+}
+
+EPI_BIAS, EPI_BIAS_GELU, EPI_GATE_RESIDUAL, EPI_RESIDUAL = 0, 1, 2, 3
+
+_lib: Optional[ctypes.CDLL] = None
+
+
+class B200Error(RuntimeError):
+    pass
+
+
+def load() -> ctypes.CDLL:
+    """Load the shared library (once). Raises if it has not been built — there is no CPU/torch fallback."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise B200Error(
+            f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(nvcc, sm_100a). lightx2v_b200 has no fallback path."
+        )
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def _check(rc: int, what: str) -> None:
+    if rc != 0:
+        msg = load().b200_last_error()
+        raise B200Error(f"{what} failed (code {rc}): {msg.decode() if msg else '?'}")
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _p(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _req(t: torch.Tensor, name: str, dtype=torch.bfloat16) -> None:
+    if not t.is_cuda:
+        raise B200Error(f"{name}: expected a CUDA tensor (lightx2v_b200 has no CPU path)")
+    if t.dtype != dtype:
+        raise B200Error(f"{name}: expected {dtype}, got {t.dtype}")
+    if t.stride(-1) != 1:
+        raise B200Error(f"{name}: innermost dimension must be contiguous")
+
+
+def gemm_bf16(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, *, out: Optional[torch.Tensor] = None,
+              epilogue: int = EPI_BIAS, gate: Optional[torch.Tensor] = None, block_n: int = 0, max_ctas: int = 0) -> torch.Tensor:
+    """out[M,N] = epilogue(a[M,K] @ w[N,K]^T + bias).  For the residual epilogues `out` is the in/out residual stream."""
+    _req(a, "a"); _req(w, "w")
+    M, K = a.shape
+    N, K2 = w.shape
+    if K != K2:
+        raise B200Error(f"gemm_bf16: K mismatch {K} vs {K2}")
+    if out is None:
+        if epilogue in (EPI_GATE_RESIDUAL, EPI_RESIDUAL):
+            raise B200Error("gemm_bf16: residual epilogues need out= (the residual stream, updated in place)")
+        out = torch.empty((M, N), dtype=torch.bfloat16, device=a.device)
+    _req(out, "out")
+    rc = load().b200_gemm_bf16(a.data_ptr(), a.stride(0), w.data_ptr(), w.stride(0), out.data_ptr(), out.stride(0),
+                               _p(bias), _p(gate), M, N, K, epilogue, block_n, max_ctas, _stream())
+    _check(rc, "b200_gemm_bf16")
+    return out
+
+
+def ln_modulate(x: torch.Tensor, *, weight=None, bias=None, scale=None, shift=None, eps: float = 1e-6,
+                out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    _req(x, "x")
+    rows, D = x.shape
+    if out is None:
+        out = torch.empty((rows, D), dtype=torch.bfloat16, device=x.device)
+    rc = load().b200_ln_modulate(x.data_ptr(), x.stride(0), out.data_ptr(), out.stride(0), _p(weight), _p(bias),
+                                 _p(scale), _p(shift), rows, D, eps, _stream())
+    _check(rc, "b200_ln_modulate")
+    return out
+
+
+def rms_rope_(x0: torch.Tensor, w0: torch.Tensor, x1: Optional[torch.Tensor] = None, w1: Optional[torch.Tensor] = None, *,
+              eps: float = 1e-6, cos_sin: Optional[torch.Tensor] = None, rope_rows: Optional[int] = None,
+              pos_offset: int = 0) -> None:
+    """In-place full-width RMSNorm (+ optional RoPE) on x0 (and x1)."""
+    _req(x0, "x0")
+    rows, D = x0.shape
+    if x1 is not None:
+        _req(x1, "x1")
+        assert x1.shape == x0.shape
+    if cos_sin is not None:
+        _req(cos_sin, "cos_sin", torch.float32)
+        assert cos_sin.is_contiguous() and cos_sin.shape[-2:] == (64, 2)
+    rr = rows if rope_rows is None else rope_rows
+    rc = load().b200_rms_rope(x0.data_ptr(), x0.stride(0), w0.data_ptr(), _p(x1), 0 if x1 is None else x1.stride(0),
+                              _p(w1), rows, D, eps, _p(cos_sin), rr, pos_offset, _stream())
+    _check(rc, "b200_rms_rope")
+
+
+def fmha(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, *, softmax_scale: Optional[float] = None,
+         out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """q [Sq,H,128], k/v [Sk,H,128] (row-strided views allowed) -> out [Sq,H,128]; one segment, non-causal."""
+    for n, t in (("q", q), ("k", k), ("v", v)):
+        _req(t, n)
+        if t.dim() != 3 or t.shape[2] != 128 or t.stride(1) != 128:
+            raise B200Error(f"fmha: {n} must be [S,H,128] with contiguous heads, got {tuple(t.shape)} / {t.stride()}")
+    sq, H, _ = q.shape
+    sk = k.shape[0]
+    if out is None:
+        out = torch.empty((sq, H, 128), dtype=torch.bfloat16, device=q.device)
+    scale = 128 ** -0.5 if softmax_scale is None else softmax_scale
+    rc = load().b200_fmha_fwd_d128(q.data_ptr(), q.stride(0), k.data_ptr(), k.stride(0), v.data_ptr(), v.stride(0),
+                                   out.data_ptr(), out.stride(0), sq, sk, H, scale, _stream())
+    _check(rc, "b200_fmha_fwd_d128")
+    return out
