@@ -92,7 +92,7 @@ fmha_fwd_d128_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
 
   if (warp < 4) {
    // warpgroup 0 (load / mma / alloc / idle) donates registers to the softmax warps
-   reg_dealloc<80>();
+   reg_dealloc<88>();
    if (warp == 0) {
     // ============================== TMA producer ==============================
     if (lane == 0) {
@@ -204,7 +204,7 @@ fmha_fwd_d128_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
    }
   } else {
     // ============================== softmax / correction / epilogue ==============================
-    reg_alloc<216>();
+    reg_alloc<208>();   // 128*88 + 256*208 == 384*168: the pool is what the CTA launched with
     const int t = (warp - 4) >> 2;             // query tile 0 / 1
     const int lg = warp & 3;                   // TMEM lane group of this warp
     const int row = lg * 32 + lane;            // row inside the query tile

@@ -1,0 +1,240 @@
+"""Weight-holding op objects with LightX2V's operator interface (`load / apply / to_cuda / to_cpu / state_dict /
+set_config / clear / _calculate_size`), backed by the sm_100a kernels of libb200dit.so.
+
+Reference classes mirrored (same constructor arguments, same `apply` signatures, same state_dict keys):
+  MMWeightB200    <- MMWeight         lightx2v/common/ops/mm/mm_weight.py:29-96
+  RMSWeightB200   <- RMSWeightSgl     lightx2v/common/ops/norm/rms_norm_weight.py:12-118
+  LNWeightB200    <- LNWeight         lightx2v/common/ops/norm/layer_norm_weight.py:7-111
+  FmhaWeightB200  <- FlashAttn2Weight lightx2v/common/ops/attn/attn_weight.py:43-97
+  DefaultTensor   <- DefaultTensor    lightx2v/common/ops/tensor/tensor.py:6-47
+`apply` raises if the tensor is not on a CUDA device: there is no CPU / torch fallback on this path.
+"""
+from __future__ import annotations
+
+from typing import Dict, Optional
+
+import torch
+
+from .. import lib
+from .registry import ATTN_KEY, ATTN_WEIGHT_REGISTER, LN_WEIGHT_REGISTER, MM_KEY, MM_WEIGHT_REGISTER, RMS_WEIGHT_REGISTER, TENSOR_REGISTER
+
+
+class _WeightOp:
+    """to_cuda / to_cpu / clear plumbing shared by the weight holders (attribute names listed in `_attrs`)."""
+
+    _attrs = ()
+
+    def set_config(self, config=None):
+        if config is not None:
+            self.config = config
+
+    def to_cuda(self, non_blocking=False):
+        for a in self._attrs:
+            t = getattr(self, a, None)
+            if t is not None:
+                setattr(self, a, t.cuda(non_blocking=non_blocking))
+
+    def to_cpu(self, non_blocking=False):
+        for a in self._attrs:
+            t = getattr(self, a, None)
+            if t is not None:
+                setattr(self, a, t.to("cpu", non_blocking=non_blocking))
+
+    def clear(self):
+        for a in self._attrs:
+            if hasattr(self, a):
+                setattr(self, a, None)
+
+    def _calculate_size(self):
+        return sum(t.numel() * t.element_size() for t in (getattr(self, a, None) for a in self._attrs) if t is not None)
+
+
+@MM_WEIGHT_REGISTER(MM_KEY)
+class MMWeightB200(_WeightOp):
+    """y = x @ W^T + b through the tcgen05 GEMM.  `self.weight` keeps the reference's convention — the transposed VIEW
+    `[K, N]` of the checkpoint's `[N, K]` tensor (mm_weight.py:76) — so code that reads `.weight` sees the same thing;
+    the kernel consumes the underlying `[N, K]` row-major storage (an NT GEMM)."""
+
+    _attrs = ("weight", "bias")
+
+    def __init__(self, weight_name, bias_name, lazy_load=False, lazy_load_file=None):
+        self.weight_name = weight_name
+        self.bias_name = bias_name
+        self.lazy_load = lazy_load
+        self.lazy_load_file = lazy_load_file
+        self.config = {}
+        self.weight = None
+        self.bias = None
+
+    def load(self, weight_dict: Dict[str, torch.Tensor]):
+        w = weight_dict[self.weight_name]
+        if w.dtype != torch.bfloat16:
+            raise lib.B200Error(f"{self.weight_name}: B200-bf16 expects a bf16 checkpoint tensor, got {w.dtype}")
+        self.weight = w.contiguous().t()
+        self.bias = weight_dict[self.bias_name] if self.bias_name is not None else None
+
+    def to_cuda(self, non_blocking=False):
+        # .cuda() of a transposed view stays a transposed view of a contiguous [N,K] buffer
+        self.weight = self.weight.t().cuda(non_blocking=non_blocking).t()
+        if self.bias is not None:
+            self.bias = self.bias.cuda(non_blocking=non_blocking)
+
+    def to_cpu(self, non_blocking=False):
+        self.weight = self.weight.t().to("cpu", non_blocking=non_blocking).t()
+        if self.bias is not None:
+            self.bias = self.bias.to("cpu", non_blocking=non_blocking)
+
+    @property
+    def weight_nk(self) -> torch.Tensor:
+        return self.weight.t()
+
+    def apply(self, input_tensor: torch.Tensor, *, out=None, epilogue: int = lib.EPI_BIAS, gate=None) -> torch.Tensor:
+        return lib.gemm_bf16(input_tensor, self.weight.t(), self.bias, out=out, epilogue=epilogue, gate=gate)
+
+    def state_dict(self, destination=None):
+        if destination is None:
+            destination = {}
+        destination[self.weight_name] = self.weight.cpu().detach().clone().t().contiguous()
+        if self.bias is not None:
+            destination[self.bias_name] = self.bias.cpu().detach().clone()
+        return destination
+
+
+class RMSWeightB200(_WeightOp):
+    """Full-row RMSNorm with the reference's bf16 rounding points (rms_norm_weight.py:111-113)."""
+
+    _attrs = ("weight",)
+
+    def __init__(self, weight_name, lazy_load=False, lazy_load_file=None, eps=1e-6):
+        self.weight_name = weight_name
+        self.eps = eps
+        self.lazy_load = lazy_load
+        self.lazy_load_file = lazy_load_file
+        self.config = {}
+        self.weight = None
+
+    def load(self, weight_dict):
+        if not self.lazy_load:
+            self.weight = weight_dict[self.weight_name]
+
+    def load_from_disk(self):
+        self.weight = self.lazy_load_file.get_tensor(self.weight_name).to(torch.bfloat16)
+
+    def apply(self, input_tensor: torch.Tensor) -> torch.Tensor:
+        shape = input_tensor.shape
+        x = input_tensor.reshape(-1, shape[-1]).clone()      # the reference returns a new tensor
+        lib.rms_rope_(x, self.weight, eps=self.eps)
+        return x.view(shape)
+
+    def state_dict(self, destination=None):
+        if destination is None:
+            destination = {}
+        destination[self.weight_name] = self.weight.cpu().detach().clone()
+        return destination
+
+
+RMS_WEIGHT_REGISTER["Default"] = RMSWeightB200
+RMS_WEIGHT_REGISTER["sgl-kernel"] = RMSWeightB200
+
+
+class LNWeightB200(_WeightOp):
+    """LayerNorm, optional affine (layer_norm_weight.py:100-111)."""
+
+    _attrs = ("weight", "bias")
+
+    def __init__(self, weight_name=None, bias_name=None, lazy_load=False, lazy_load_file=None, eps=1e-6):
+        self.weight_name = weight_name
+        self.bias_name = bias_name
+        self.eps = eps
+        self.lazy_load = lazy_load
+        self.lazy_load_file = lazy_load_file
+        self.config = {}
+        self.weight = None
+        self.bias = None
+
+    def load(self, weight_dict):
+        if not self.lazy_load:
+            self.weight = weight_dict[self.weight_name] if self.weight_name is not None else None
+            self.bias = weight_dict[self.bias_name] if self.bias_name is not None else None
+
+    def apply(self, input_tensor: torch.Tensor, *, scale=None, shift=None, out=None) -> torch.Tensor:
+        return lib.ln_modulate(input_tensor, weight=self.weight, bias=self.bias, scale=scale, shift=shift, eps=self.eps, out=out)
+
+    def state_dict(self, destination=None):
+        if destination is None:
+            destination = {}
+        if self.weight is not None:
+            destination[self.weight_name] = self.weight.cpu().detach().clone()
+        if self.bias is not None:
+            destination[self.bias_name] = self.bias.cpu().detach().clone()
+        return destination
+
+
+LN_WEIGHT_REGISTER["Default"] = LNWeightB200
+
+
+@ATTN_WEIGHT_REGISTER(ATTN_KEY)
+class FmhaWeightB200:
+    """Varlen non-causal attention, same call signature as FlashAttn2Weight.apply (attn_weight.py:76-97).
+    cu_seqlens are HOST-visible sequences or tensors; each segment is one kernel launch (Wan: one segment; Hunyuan: two)."""
+
+    def __init__(self):
+        self.config = {}
+
+    def load(self, weight_dict):
+        pass
+
+    def set_config(self, config=None):
+        if config is not None:
+            self.config = config
+
+    def to_cpu(self, non_blocking=False):
+        pass
+
+    def to_cuda(self, non_blocking=False):
+        pass
+
+    def state_dict(self, destination=None):
+        return {} if destination is None else destination
+
+    @staticmethod
+    def _bounds(cu, total):
+        if cu is None:
+            return [0, total]
+        if isinstance(cu, torch.Tensor):
+            return [int(v) for v in cu.tolist()]
+        return [int(v) for v in cu]
+
+    def apply(self, q, k, v, cu_seqlens_q=None, cu_seqlens_kv=None, max_seqlen_q=None, max_seqlen_kv=None,
+              model_cls=None, mask_map=None):
+        bq = self._bounds(cu_seqlens_q, q.shape[0])
+        bk = self._bounds(cu_seqlens_kv, k.shape[0])
+        if len(bq) != len(bk):
+            raise lib.B200Error("b200_fmha: cu_seqlens_q and cu_seqlens_kv must have the same number of segments")
+        out = torch.empty((q.shape[0], q.shape[1], q.shape[2]), dtype=torch.bfloat16, device=q.device)
+        for i in range(len(bq) - 1):
+            if bq[i + 1] > bq[i] and bk[i + 1] > bk[i]:
+                lib.fmha(q[bq[i]:bq[i + 1]], k[bk[i]:bk[i + 1]], v[bk[i]:bk[i + 1]], out=out[bq[i]:bq[i + 1]])
+        rows = q.shape[0] if max_seqlen_q is None else max_seqlen_q
+        return out.reshape(rows, -1)
+
+
+@TENSOR_REGISTER("Default")
+class DefaultTensor(_WeightOp):
+    _attrs = ("tensor",)
+
+    def __init__(self, tensor_name, lazy_load=False, lazy_load_file=None):
+        self.tensor_name = tensor_name
+        self.lazy_load = lazy_load
+        self.lazy_load_file = lazy_load_file
+        self.tensor = None
+
+    def load(self, weight_dict):
+        if not self.lazy_load:
+            self.tensor = weight_dict[self.tensor_name]
+
+    def state_dict(self, destination=None):
+        if destination is None:
+            destination = {}
+        destination[self.tensor_name] = self.tensor.cpu().detach().clone()
+        return destination

@@ -1,0 +1,240 @@
+"""WanTransformerInfer with the reference's method surface, running each block as a short chain of fused sm_100a kernels.
+
+Mirrors lightx2v/models/networks/wan/infer/transformer_infer.py (class WanTransformerInfer):
+  infer(weights, grid_sizes, embed, x, embed0, seq_lens, freqs, context, audio_dit_blocks=None)   :80-81
+  infer_block / infer_modulation / infer_self_attn / infer_cross_attn / infer_ffn / post_process     :289-508
+and accepts either this package's weights tree (host/wan_weights.py) or the reference's own WanTransformerWeights
+(the infer class only reads `.weight`, `.bias`, `.tensor`, `.eps` of the op objects).
+
+Fusions per block (~50 launches / ~14 passes over [S,D] in the reference):
+  LN + AdaLN modulate        -> b200_ln_modulate                       (1 read + 1 write of [S,D])
+  q,k,v linears              -> ONE [S,D]x[D,3D] tcgen05 GEMM on the concatenated weight
+  q/k RMSNorm + 3-axis RoPE  -> b200_rms_rope, in place on the fused QKV buffer (fp32 cos/sin table, no fp64 round trip)
+  attention                  -> b200_fmha_fwd_d128 reading q/k/v as strided views of the QKV buffer
+  o-proj + gate*y + residual -> GEMM epilogue (in place on x);  cross o-proj + residual -> GEMM epilogue
+  ffn_0 + GELU(tanh)         -> GEMM epilogue;  ffn_2 + gate*y + residual -> GEMM epilogue
+Text K/V of the cross-attention are step-invariant; they are cached per (block, context tensor).
+"""
+from __future__ import annotations
+
+from typing import Dict, Optional, Tuple
+
+import torch
+
+from .. import lib
+
+
+def rope_cos_sin(grid_sizes, freqs: torch.Tensor, head_dim: int, rows: Optional[int] = None, row_offset: int = 0) -> torch.Tensor:
+    """[rows, 64, 2] fp32 (cos, sin) table for the (f, h, w) token grid — the content of compute_freqs
+    (lightx2v/models/networks/wan/infer/utils.py:7-20), or of compute_freqs_dist (:86-104) when rows/row_offset select a
+    rank's shard (rows past f*h*w get the identity rotation, like pad_freqs' ones)."""
+    c = head_dim // 2
+    fs = freqs.split([c - 2 * (c // 3), c // 3, c // 3], dim=1)
+    f, h, w = [int(v) for v in grid_sizes]
+    fi = torch.cat(
+        [
+            fs[0][:f].view(f, 1, 1, -1).expand(f, h, w, -1),
+            fs[1][:h].view(1, h, 1, -1).expand(f, h, w, -1),
+            fs[2][:w].view(1, 1, w, -1).expand(f, h, w, -1),
+        ],
+        dim=-1,
+    ).reshape(f * h * w, c)
+    if rows is not None:
+        total = row_offset + rows
+        if total > fi.shape[0]:
+            fi = torch.cat([fi, torch.ones(total - fi.shape[0], c, dtype=fi.dtype, device=fi.device)], dim=0)
+        fi = fi[row_offset:total]
+    return torch.stack([fi.real, fi.imag], dim=-1).to(torch.float32).contiguous()
+
+
+class _BlockCache:
+    """Per-block derived tensors: concatenated QKV weight/bias, cached cross-attention text K/V."""
+
+    __slots__ = ("wqkv", "bqkv", "ctx_key", "ck", "cv", "ck_img", "cv_img")
+
+    def __init__(self):
+        self.wqkv = None
+        self.bqkv = None
+        self.ctx_key = None
+        self.ck = self.cv = self.ck_img = self.cv_img = None
+
+
+class WanTransformerInfer:
+    def __init__(self, config):
+        self.config = config
+        self.task = config["task"]
+        self.attention_type = config.get("attention_type", "b200_fmha")
+        self.blocks_num = config["num_layers"]
+        self.phases_num = 4
+        self.num_heads = config["num_heads"]
+        self.head_dim = config["dim"] // config["num_heads"]
+        if self.head_dim != 128:
+            raise lib.B200Error(f"WanTransformerInfer(B200): head_dim must be 128, got {self.head_dim}")
+        self.parallel_attention = None          # set by parallel.ulysses.parallelize_wan
+        self.sp_rank, self.sp_world = 0, 1
+        self.infer_conditional = True
+        self.mask_map = None
+        self.cache_cross_kv = bool(config.get("b200_cache_cross_kv", True))
+        self._caches: Dict[int, _BlockCache] = {}
+        self._rope: Dict[Tuple, torch.Tensor] = {}
+        self._bufs: Dict[Tuple, torch.Tensor] = {}
+        self.infer_func = self._infer_without_offload
+
+    # ------------------------------------------------------------------ reference surface
+    def switch_status(self):
+        self.infer_conditional = not self.infer_conditional
+
+    def infer(self, weights, grid_sizes, embed, x, embed0, seq_lens, freqs, context, audio_dit_blocks=None):
+        return self.infer_func(weights, grid_sizes, embed, x, embed0, seq_lens, freqs, context, audio_dit_blocks)
+
+    def _infer_without_offload(self, weights, grid_sizes, embed, x, embed0, seq_lens, freqs, context, audio_dit_blocks=None):
+        for block_idx in range(self.blocks_num):
+            x = self.infer_block(weights.blocks[block_idx], grid_sizes, embed, x, embed0, seq_lens, freqs, context)
+        return x
+
+    def infer_block(self, weights, grid_sizes, embed, x, embed0, seq_lens, freqs, context):
+        shift_msa, scale_msa, gate_msa, c_shift_msa, c_scale_msa, c_gate_msa = self.infer_modulation(weights.compute_phases[0], embed0)
+        x = self.infer_self_attn(weights.compute_phases[1], grid_sizes, x, seq_lens, freqs, shift_msa, scale_msa, gate_msa=gate_msa)
+        x, attn_out = self.infer_cross_attn(weights.compute_phases[2], x, context, None, None)
+        y = self.infer_ffn(weights.compute_phases[3], x, attn_out, c_shift_msa, c_scale_msa, c_gate_msa=c_gate_msa)
+        return self.post_process(x, y, c_gate_msa)
+
+    def infer_modulation(self, weights, embed0):
+        """transformer_infer.py:308-319 (embed0 [6, D]); returns six contiguous [D] vectors."""
+        if embed0.dim() != 2:
+            raise lib.B200Error("WanTransformerInfer(B200): per-token (diffusion-forcing) embed0 is out of scope")
+        mod = (weights.modulation.tensor + embed0).reshape(6, -1)
+        return tuple(mod[i] for i in range(6))
+
+    # ------------------------------------------------------------------ helpers
+    def _buf(self, name, shape, device):
+        key = (name, tuple(shape), str(device))
+        b = self._bufs.get(key)
+        if b is None:
+            b = torch.empty(shape, dtype=torch.bfloat16, device=device)
+            self._bufs[key] = b
+        return b
+
+    def _cache(self, weights) -> _BlockCache:
+        c = self._caches.get(id(weights))
+        if c is None:
+            c = _BlockCache()
+            self._caches[id(weights)] = c
+        return c
+
+    def _rope_table(self, grid_sizes, freqs, rows, device):
+        gs = grid_sizes[0].tolist() if isinstance(grid_sizes, torch.Tensor) else list(grid_sizes[0])
+        key = (tuple(gs), rows, self.sp_rank, self.sp_world, str(device))
+        t = self._rope.get(key)
+        if t is None:
+            if self.sp_world > 1:
+                t = rope_cos_sin(gs, freqs.cpu(), self.head_dim, rows=rows, row_offset=self.sp_rank * rows)
+            else:
+                t = rope_cos_sin(gs, freqs.cpu(), self.head_dim)
+            t = t.to(device)
+            self._rope[key] = t
+        return t
+
+    @staticmethod
+    def _nk(mm) -> torch.Tensor:
+        """[N,K] row-major storage behind an MM op (ours or the reference's `weight = ckpt.t()` view)."""
+        w = mm.weight.t()
+        return w if w.is_contiguous() else w.contiguous()
+
+    # ------------------------------------------------------------------ phases
+    def infer_self_attn(self, weights, grid_sizes, x, seq_lens, freqs, shift_msa, scale_msa, gate_msa=None):
+        """transformer_infer.py:321-396 (+ the gated residual of :402 when gate_msa is given: returns the updated x;
+        with gate_msa=None returns y like the reference)."""
+        S, D = x.shape
+        dev = x.device
+        c = self._cache(weights)
+        if c.wqkv is None:
+            c.wqkv = torch.cat([self._nk(weights.self_attn_q), self._nk(weights.self_attn_k), self._nk(weights.self_attn_v)], dim=0).contiguous()
+            c.bqkv = torch.cat([weights.self_attn_q.bias, weights.self_attn_k.bias, weights.self_attn_v.bias]).contiguous()
+        n1 = self._buf("a", (S, D), dev)
+        lib.ln_modulate(x, scale=scale_msa, shift=shift_msa, eps=weights.norm1.eps, out=n1)
+        qkv = self._buf("qkv", (S, 3 * D), dev)
+        lib.gemm_bf16(n1, c.wqkv, c.bqkv, out=qkv)
+        q, k, v = qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:]
+        cs = self._rope_table(grid_sizes, freqs, S, dev)
+        lib.rms_rope_(q, weights.self_attn_norm_q.weight, k, weights.self_attn_norm_k.weight, eps=weights.self_attn_norm_q.eps,
+                      cos_sin=cs, rope_rows=min(S, cs.shape[0]))
+        H, d = self.num_heads, self.head_dim
+        q3, k3, v3 = (t.unflatten(1, (H, d)) for t in (q, k, v))
+        attn = n1.view(S, H, d)          # n1 is dead after the QKV GEMM: reuse it for the attention output
+        if self.parallel_attention is None:
+            lib.fmha(q3, k3, v3, out=attn)
+        else:
+            attn = self.parallel_attention(q=q3, k=k3, v=v3, out=attn)
+        attn2 = attn.reshape(S, D)
+        if gate_msa is None:
+            return lib.gemm_bf16(attn2, self._nk(weights.self_attn_o), weights.self_attn_o.bias)
+        lib.gemm_bf16(attn2, self._nk(weights.self_attn_o), weights.self_attn_o.bias, out=x,
+                      epilogue=lib.EPI_GATE_RESIDUAL, gate=gate_msa)
+        return x
+
+    def _context_kv(self, weights, context, c: _BlockCache):
+        key = (context.data_ptr(), context._version, tuple(context.shape))
+        if self.cache_cross_kv and c.ctx_key == key:
+            return
+        H, d = self.num_heads, self.head_dim
+        if self.task == "i2v":
+            context_img, ctx = context[:257], context[257:]
+        else:
+            context_img, ctx = None, context
+        ck = lib.gemm_bf16(ctx, self._nk(weights.cross_attn_k), weights.cross_attn_k.bias)
+        lib.rms_rope_(ck, weights.cross_attn_norm_k.weight, eps=weights.cross_attn_norm_k.eps)
+        cv = lib.gemm_bf16(ctx, self._nk(weights.cross_attn_v), weights.cross_attn_v.bias)
+        c.ck, c.cv = ck.view(-1, H, d), cv.view(-1, H, d)
+        if context_img is not None:
+            ki = lib.gemm_bf16(context_img, self._nk(weights.cross_attn_k_img), weights.cross_attn_k_img.bias)
+            lib.rms_rope_(ki, weights.cross_attn_norm_k_img.weight, eps=weights.cross_attn_norm_k_img.eps)
+            vi = lib.gemm_bf16(context_img, self._nk(weights.cross_attn_v_img), weights.cross_attn_v_img.bias)
+            c.ck_img, c.cv_img = ki.view(-1, H, d), vi.view(-1, H, d)
+        c.ctx_key = key
+
+    def infer_cross_attn(self, weights, x, context, y_out, gate_msa):
+        """transformer_infer.py:398-465.  If y_out is given the gated residual `x += y_out * gate_msa` (:402) is applied
+        here like the reference; the fused path passes None because the self-attention o-proj epilogue already did it.
+        Returns (x, attn_out) where attn_out is None when the cross o-proj epilogue already accumulated into x."""
+        S, D = x.shape
+        dev = x.device
+        H, d = self.num_heads, self.head_dim
+        if y_out is not None:
+            x.add_(y_out * gate_msa)
+        c = self._cache(weights)
+        n3 = self._buf("a", (S, D), dev)
+        lib.ln_modulate(x, weight=weights.norm3.weight, bias=weights.norm3.bias, eps=weights.norm3.eps, out=n3)
+        cq = self._buf("b", (S, D), dev)
+        lib.gemm_bf16(n3, self._nk(weights.cross_attn_q), weights.cross_attn_q.bias, out=cq)
+        lib.rms_rope_(cq, weights.cross_attn_norm_q.weight, eps=weights.cross_attn_norm_q.eps)
+        self._context_kv(weights, context, c)
+        attn = n3.view(S, H, d)
+        lib.fmha(cq.view(S, H, d), c.ck, c.cv, out=attn)
+        if self.task == "i2v":
+            img = lib.fmha(cq.view(S, H, d), c.ck_img, c.cv_img, out=self._buf("c", (S, H, d), dev))
+            attn.add_(img)                                                      # :454 (two softmaxes, summed in bf16)
+        lib.gemm_bf16(attn.reshape(S, D), self._nk(weights.cross_attn_o), weights.cross_attn_o.bias, out=x, epilogue=lib.EPI_RESIDUAL)
+        return x, None
+
+    def infer_ffn(self, weights, x, attn_out, c_shift_msa, c_scale_msa, c_gate_msa=None):
+        """transformer_infer.py:467-497 (+ :503 when c_gate_msa is given: the ffn_2 epilogue updates x and None is returned)."""
+        S, D = x.shape
+        dev = x.device
+        if attn_out is not None:
+            x.add_(attn_out)
+        n2 = self._buf("a", (S, D), dev)
+        lib.ln_modulate(x, scale=c_scale_msa, shift=c_shift_msa, eps=weights.norm2.eps, out=n2)
+        w0 = self._nk(weights.ffn_0)
+        hidden = self._buf("h", (S, w0.shape[0]), dev)
+        lib.gemm_bf16(n2, w0, weights.ffn_0.bias, out=hidden, epilogue=lib.EPI_BIAS_GELU)
+        if c_gate_msa is None:
+            return lib.gemm_bf16(hidden, self._nk(weights.ffn_2), weights.ffn_2.bias)
+        lib.gemm_bf16(hidden, self._nk(weights.ffn_2), weights.ffn_2.bias, out=x, epilogue=lib.EPI_GATE_RESIDUAL, gate=c_gate_msa)
+        return None
+
+    def post_process(self, x, y, c_gate_msa):
+        """transformer_infer.py:499-508."""
+        if y is not None:
+            x.add_(y * c_gate_msa)
+        return x

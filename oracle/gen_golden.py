@@ -1,0 +1,127 @@
+#!/usr/bin/env python
+"""Generate golden fixtures from the REAL LightX2V reference (runs only in the build container).
+
+Imports `/root/reference/lightx2v` under the two shims of SURVEY.md §8c (patch torch.cuda.get_device_capability; drop
+pin_memory), builds the reference's own weight tree (`WanTransformerAttentionBlock`) + infer class
+(`WanTransformerInfer`) on seeded synthetic weights, runs them on CPU in DTYPE=BF16 mode with `torch_sdpa`
+attention, and stores inputs and outputs as safetensors under tests/golden/.  The fixtures pin oracle/wan_oracle.py
+(tests/test_oracle_golden.py) and are also compared with the CUDA path on the GPU box (tests/test_gpu_block.py).
+
+    python oracle/gen_golden.py            # writes tests/golden/*.safetensors
+"""
+import os
+import sys
+import types
+
+os.environ["DTYPE"] = "BF16"
+os.environ.setdefault("ENABLE_GRAPH_MODE", "false")
+
+import torch  # noqa: E402
+
+REF = os.environ.get("LIGHTX2V_REFERENCE", "/root/reference")
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLD = os.path.join(ROOT, "tests", "golden")
+sys.path.insert(0, ROOT)
+
+
+def install_shims():
+    """Shim 1: attn_weight.py:26 / sage_attn2.py:3 call torch.cuda.get_device_capability(0) at import.
+    Shim 2: every op's load() allocates torch.empty(..., pin_memory=True) (mm_weight.py:77, rms_norm_weight.py:23...)."""
+    torch.cuda.get_device_capability = lambda *a, **k: (10, 0)
+    _empty = torch.empty
+
+    def empty_nopin(*a, **k):
+        k.pop("pin_memory", None)
+        return _empty(*a, **k)
+
+    torch.empty = empty_nopin
+    sys.path.insert(0, REF)
+
+
+class Cfg(dict):
+    """EasyDict stand-in (easydict is not installed): dict with attribute access."""
+
+    __getattr__ = dict.__getitem__
+
+
+def ref_config(dim, num_heads, ffn_dim, num_layers, task="t2v"):
+    return Cfg(
+        task=task, num_layers=num_layers, num_heads=num_heads, dim=dim, ffn_dim=ffn_dim, cpu_offload=False,
+        mm_config={}, do_mm_calib=False, self_attn_1_type="torch_sdpa", cross_attn_1_type="torch_sdpa",
+        cross_attn_2_type="torch_sdpa", model_cls="wan2.1", freq_dim=256, text_len=512, in_dim=16, out_dim=16,
+        enable_cfg=True, attention_type="torch_sdpa",
+    )
+
+
+def run_reference_blocks(W, cfg, x, embed0, grid_sizes, freqs, context):
+    from lightx2v.models.networks.wan.infer.transformer_infer import WanTransformerInfer
+    from lightx2v.models.networks.wan.weights.transformer_weights import WanTransformerWeights
+
+    weights = WanTransformerWeights(cfg)
+    weights.load(W)
+    infer = WanTransformerInfer(cfg)
+    seq_lens = torch.tensor([x.shape[0]], dtype=torch.long)
+    gs = torch.tensor([list(grid_sizes)], dtype=torch.long)
+    return infer.infer(weights, gs, None, x, embed0, seq_lens, freqs, context)
+
+
+def main():
+    install_shims()
+    from safetensors.torch import save_file
+
+    import lightx2v.common.ops  # noqa: F401  registers MM/ATTN/RMS/LN/TENSOR op classes (common/ops/__init__.py)
+    from lightx2v.common.ops import mm, attn, norm, tensor, conv  # noqa: F401
+
+    from oracle import wan_oracle as O
+
+    os.makedirs(GOLD, exist_ok=True)
+    torch.manual_seed(0)
+    torch.set_num_threads(8)
+
+    # ---- fixture 1: two Wan-1.3B-shaped blocks (D 1536, 12 heads, F 8960), grid 3x8x10 -> 240 tokens, t2v
+    # ---- fixture 2: one block, i2v (257 CLIP rows + 512 text rows), grid 2x6x9 -> 108 tokens
+    for name, task, L, grid in (("wan13b_t2v_2blocks", "t2v", 2, (3, 8, 10)), ("wan13b_i2v_1block", "i2v", 1, (2, 6, 9))):
+        dim, heads, ffn = 1536, 12, 8960
+        S = grid[0] * grid[1] * grid[2]
+        cfg = ref_config(dim, heads, ffn, L, task)
+        W = O.synth_block_weights(L, dim, ffn, task=task, seed=42)
+        x, embed0, context = O.synth_block_inputs(S, dim, task=task, seed=7)
+        freqs = O.wan_freqs_table(dim // heads)
+        x_in = x.clone()
+        out = run_reference_blocks(W, cfg, x, embed0, grid, freqs, context)
+        # per-function probes from the reference's own methods on block 0 (fresh x)
+        from lightx2v.models.networks.wan.infer.transformer_infer import WanTransformerInfer
+        from lightx2v.models.networks.wan.infer.utils import apply_rotary_emb, compute_freqs
+        from lightx2v.models.networks.wan.weights.transformer_weights import WanTransformerWeights
+
+        weights = WanTransformerWeights(cfg)
+        weights.load(W)
+        infer = WanTransformerInfer(cfg)
+        blk = weights.blocks[0]
+        xs = x_in.clone()
+        gs = torch.tensor([list(grid)], dtype=torch.long)
+        seq_lens = torch.tensor([S], dtype=torch.long)
+        sh, sc, ga, csh, csc, cga = infer.infer_modulation(blk.compute_phases[0], embed0)
+        y_out = infer.infer_self_attn(blk.compute_phases[1], gs, xs, seq_lens, freqs, sh, sc)
+        xs2, attn_out = infer.infer_cross_attn(blk.compute_phases[2], xs, context, y_out, ga)
+        x_after_cross = xs2.clone()
+        y_ffn = infer.infer_ffn(blk.compute_phases[3], xs2, attn_out, csh, csc)
+        freqs_i = compute_freqs(dim // heads // 2, gs, freqs)
+        qprobe = torch.randn(S, heads, dim // heads, generator=torch.Generator().manual_seed(3)).to(torch.bfloat16)
+        rope_out = apply_rotary_emb(qprobe, freqs_i)
+        tensors = {
+            "x_in": x_in, "embed0": embed0, "context": context, "x_out": out,
+            "probe.self_attn_y": y_out, "probe.x_after_cross": x_after_cross, "probe.cross_attn_out": attn_out,
+            "probe.ffn_y": y_ffn, "probe.rope_in": qprobe, "probe.rope_out": rope_out,
+            "grid": torch.tensor(grid, dtype=torch.int64),
+        }
+        meta = {"dim": str(dim), "heads": str(heads), "ffn": str(ffn), "layers": str(L), "task": task, "weights_seed": "42",
+                "inputs_seed": "7", "generator": "oracle/gen_golden.py", "reference": "ModelTC/lightx2v@0591c35e",
+                "attn": "torch_sdpa", "dtype_mode": "BF16"}
+        save_file({k: v.contiguous() for k, v in tensors.items()}, os.path.join(GOLD, name + ".safetensors"), metadata=meta)
+        print(name, "x_out absmax", float(out.float().abs().max()), "bytes",
+              os.path.getsize(os.path.join(GOLD, name + ".safetensors")))
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,251 @@
+"""ORACLE (test infrastructure, NOT product code).
+
+A plain-torch restatement of LightX2V's Wan DiT hot path in its `DTYPE=BF16` mode, function by function, each citing
+the reference lines it follows (paths relative to the LightX2V tree at 0591c35e).  It runs on CPU (attention through
+torch SDPA, like the reference's `torch_sdpa` op) or on a GPU (`device="cuda"`, attention through flash_attn when
+`attn="flash_attn2"`, like the reference's `flash_attn2` op) and is the checker for every CUDA kernel in
+`lightx2v_b200/csrc`.
+
+Only `tests/`, `__graft_entry__.smoke()` and `bench.py`'s cpu_baseline / `--impl reference` legs may import this file.
+
+Pinning: `oracle/gen_golden.py` imports the REAL reference classes (under the two shims of SURVEY.md §8c) in the build
+container, runs them on seeded synthetic weights and stores inputs + outputs under `tests/golden/`;
+`tests/test_oracle_golden.py` checks this restatement against those fixtures bit for bit.
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, Optional
+
+import torch
+import torch.nn.functional as F
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# operator surface (lightx2v/common/ops/*)
+# ---------------------------------------------------------------------------------------------------------------
+def mm_apply(x: torch.Tensor, weight_nk: torch.Tensor, bias: Optional[torch.Tensor]) -> torch.Tensor:
+    """MMWeight.apply: torch.addmm(bias, x, W.t())  — common/ops/mm/mm_weight.py:81-88 (weight kept as [N,K].t() view, :76)."""
+    if bias is None:
+        return torch.mm(x, weight_nk.t())
+    return torch.addmm(bias, x, weight_nk.t())
+
+
+def rms_apply(x: torch.Tensor, weight: torch.Tensor, eps: float = 1e-6) -> torch.Tensor:
+    """RMSWeightSgl.apply, bf16 fallback taken when sgl_kernel is absent — common/ops/norm/rms_norm_weight.py:109-113."""
+    x = x * torch.rsqrt(x.pow(2).mean(-1, keepdim=True) + eps)
+    return x * weight
+
+
+def ln_apply(x: torch.Tensor, weight=None, bias=None, eps: float = 1e-6) -> torch.Tensor:
+    """LNWeight.apply in BF16 mode — common/ops/norm/layer_norm_weight.py:110."""
+    return F.layer_norm(x, (x.shape[-1],), weight, bias, eps)
+
+
+def attn_apply(q, k, v, impl: str = "torch_sdpa") -> torch.Tensor:
+    """ATTN op `.apply` for one segment, non-causal, scale d^-0.5 -> [Sq, H*d].
+    torch_sdpa: common/ops/attn/attn_weight.py:209-239;  flash_attn2: :71-97."""
+    sq = q.shape[0]
+    if impl == "flash_attn2":
+        from flash_attn import flash_attn_varlen_func
+
+        cu_q = torch.tensor([0, sq], dtype=torch.int32, device=q.device)
+        cu_k = torch.tensor([0, k.shape[0]], dtype=torch.int32, device=q.device)
+        return flash_attn_varlen_func(q, k, v, cu_q, cu_k, sq, k.shape[0]).reshape(sq, -1)
+    qq, kk, vv = (t.unsqueeze(0).transpose(1, 2) for t in (q, k, v))
+    x = F.scaled_dot_product_attention(qq, kk, vv, attn_mask=None, dropout_p=0, is_causal=False)
+    return x.transpose(1, 2).reshape(1, sq, -1).squeeze(0)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# RoPE (models/networks/wan/infer/utils.py)
+# ---------------------------------------------------------------------------------------------------------------
+def rope_params(max_seq_len: int, dim: int, theta: float = 10000.0) -> torch.Tensor:
+    """utils.py:151-158 — complex128 table [max_seq_len, dim/2]."""
+    freqs = torch.outer(torch.arange(max_seq_len), 1.0 / torch.pow(theta, torch.arange(0, dim, 2).to(torch.float64).div(dim)))
+    return torch.polar(torch.ones_like(freqs), freqs)
+
+
+def wan_freqs_table(head_dim: int = 128) -> torch.Tensor:
+    """WanModel / WanPreInfer build: cat of three rope_params tables (pre_infer.py:16-25) -> [1024, head_dim/2] complex128."""
+    d = head_dim
+    return torch.cat([rope_params(1024, d - 4 * (d // 6)), rope_params(1024, 2 * (d // 6)), rope_params(1024, 2 * (d // 6))], dim=1)
+
+
+def compute_freqs(c: int, grid_sizes, freqs: torch.Tensor) -> torch.Tensor:
+    """utils.py:7-20 — [f*h*w, 1, c] complex table for the (t, h, w) grid."""
+    fs = freqs.split([c - 2 * (c // 3), c // 3, c // 3], dim=1)
+    f, h, w = [int(v) for v in grid_sizes]
+    return torch.cat(
+        [
+            fs[0][:f].view(f, 1, 1, -1).expand(f, h, w, -1),
+            fs[1][:h].view(1, h, 1, -1).expand(f, h, w, -1),
+            fs[2][:w].view(1, 1, w, -1).expand(f, h, w, -1),
+        ],
+        dim=-1,
+    ).reshape(f * h * w, 1, -1)
+
+
+def compute_freqs_dist(s: int, c: int, grid_sizes, freqs: torch.Tensor, world_size: int, rank: int) -> torch.Tensor:
+    """utils.py:86-104 — pad with ones (identity rotation) to s*world_size rows and slice this rank's rows."""
+    fi = compute_freqs(c, grid_sizes, freqs)
+    pad = s * world_size - fi.shape[0]
+    if pad > 0:
+        fi = torch.cat([fi, torch.ones(pad, 1, fi.shape[2], dtype=fi.dtype, device=fi.device)], dim=0)
+    return fi[rank * s : (rank + 1) * s]
+
+
+def apply_rotary_emb(x: torch.Tensor, freqs_i: torch.Tensor) -> torch.Tensor:
+    """utils.py:107-115 — complex128 multiply of adjacent pairs, single rounding to bf16."""
+    n = x.size(1)
+    seq_len = freqs_i.size(0)
+    x_i = torch.view_as_complex(x[:seq_len].to(torch.float64).reshape(seq_len, n, -1, 2))
+    x_i = torch.view_as_real(x_i * freqs_i).flatten(2)
+    x_i = torch.cat([x_i, x[seq_len:]])
+    return x_i.to(torch.bfloat16)
+
+
+def cos_sin_table(freqs_i: torch.Tensor) -> torch.Tensor:
+    """Host-side product helper input format: [S, 64, 2] fp32 (cos, sin) from the complex128 table (rounded once)."""
+    f = freqs_i.reshape(freqs_i.shape[0], -1)
+    return torch.stack([f.real, f.imag], dim=-1).to(torch.float32).contiguous()
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# one DiT block  (models/networks/wan/infer/transformer_infer.py:289-508), weights = checkpoint-named dict
+# ---------------------------------------------------------------------------------------------------------------
+def infer_modulation(W: Dict[str, torch.Tensor], pre: str, embed0: torch.Tensor):
+    """transformer_infer.py:308-319 (embed0.dim()==2 branch: [6, D]; modulation [1, 6, D])."""
+    return (W[pre + "modulation"] + embed0).chunk(6, dim=1)
+
+
+def infer_self_attn(W, pre, x, freqs_i, shift_msa, scale_msa, num_heads, attn="torch_sdpa", parallel_attention=None):
+    """transformer_infer.py:321-396."""
+    norm1_weight = 1 + scale_msa.squeeze(0)
+    norm1_bias = shift_msa.squeeze(0)
+    norm1_out = ln_apply(x)                                              # :329 (norm1: LN without affine)
+    norm1_out.mul_(norm1_weight).add_(norm1_bias)                        # :334
+    s, n = norm1_out.shape[0], num_heads
+    d = norm1_out.shape[1] // n
+    sa = pre + "self_attn."
+    q = rms_apply(mm_apply(norm1_out, W[sa + "q.weight"], W[sa + "q.bias"]), W[sa + "norm_q.weight"]).view(s, n, d)   # :341
+    k = rms_apply(mm_apply(norm1_out, W[sa + "k.weight"], W[sa + "k.bias"]), W[sa + "norm_k.weight"]).view(s, n, d)   # :342
+    v = mm_apply(norm1_out, W[sa + "v.weight"], W[sa + "v.bias"]).view(s, n, d)                                       # :343
+    q = apply_rotary_emb(q, freqs_i)                                     # :358
+    k = apply_rotary_emb(k, freqs_i)                                     # :359
+    if parallel_attention is None:
+        attn_out = attn_apply(q, k, v, attn)                             # :369-379
+    else:
+        attn_out = parallel_attention(q, k, v)                           # :381-388
+    return mm_apply(attn_out, W[sa + "o.weight"], W[sa + "o.bias"])      # :390
+
+
+def infer_cross_attn(W, pre, x, context, y_out, gate_msa, num_heads, task="t2v", attn="torch_sdpa"):
+    """transformer_infer.py:398-465."""
+    x.add_(y_out * gate_msa.squeeze(0))                                  # :402
+    ca = pre + "cross_attn."
+    norm3_out = ln_apply(x, W[pre + "norm3.weight"], W[pre + "norm3.bias"])   # :404
+    if task == "i2v":
+        context_img, context = context[:257], context[257:]             # :405-407
+    n = num_heads
+    d = x.shape[1] // n
+    q = rms_apply(mm_apply(norm3_out, W[ca + "q.weight"], W[ca + "q.bias"]), W[ca + "norm_q.weight"]).view(-1, n, d)  # :418
+    k = rms_apply(mm_apply(context, W[ca + "k.weight"], W[ca + "k.bias"]), W[ca + "norm_k.weight"]).view(-1, n, d)    # :419
+    v = mm_apply(context, W[ca + "v.weight"], W[ca + "v.bias"]).view(-1, n, d)                                        # :420
+    attn_out = attn_apply(q, k, v, attn)                                 # :425-434
+    if task == "i2v":
+        k_img = rms_apply(mm_apply(context_img, W[ca + "k_img.weight"], W[ca + "k_img.bias"]), W[ca + "norm_k_img.weight"]).view(-1, n, d)
+        v_img = mm_apply(context_img, W[ca + "v_img.weight"], W[ca + "v_img.bias"]).view(-1, n, d)
+        attn_out = attn_out.clone() if not attn_out.is_contiguous() else attn_out
+        attn_out.add_(attn_apply(q, k_img, v_img, attn))                 # :436-454
+    attn_out = mm_apply(attn_out, W[ca + "o.weight"], W[ca + "o.bias"])  # :460
+    return x, attn_out
+
+
+def infer_ffn(W, pre, x, attn_out, c_shift_msa, c_scale_msa):
+    """transformer_infer.py:467-497."""
+    x.add_(attn_out)                                                     # :468
+    norm2_weight = 1 + c_scale_msa.squeeze(0)
+    norm2_bias = c_shift_msa.squeeze(0)
+    norm2_out = ln_apply(x)                                              # :481
+    norm2_out.mul_(norm2_weight).add_(norm2_bias)                        # :484
+    y = mm_apply(norm2_out, W[pre + "ffn.0.weight"], W[pre + "ffn.0.bias"])   # :488
+    y = F.gelu(y, approximate="tanh")                                    # :492
+    return mm_apply(y, W[pre + "ffn.2.weight"], W[pre + "ffn.2.bias"])   # :495
+
+
+def post_process(x, y, c_gate_msa):
+    """transformer_infer.py:499-508."""
+    x.add_(y * c_gate_msa.squeeze(0))                                    # :503
+    return x
+
+
+def infer_block(W, block_idx, x, embed0, freqs_i, context, num_heads, task="t2v", attn="torch_sdpa", parallel_attention=None):
+    """WanTransformerInfer.infer_block — transformer_infer.py:289-306.  Mutates x in place like the reference."""
+    pre = f"blocks.{block_idx}."
+    shift_msa, scale_msa, gate_msa, c_shift_msa, c_scale_msa, c_gate_msa = infer_modulation(W, pre, embed0)
+    y_out = infer_self_attn(W, pre, x, freqs_i, shift_msa, scale_msa, num_heads, attn, parallel_attention)
+    x, attn_out = infer_cross_attn(W, pre, x, context, y_out, gate_msa, num_heads, task, attn)
+    y = infer_ffn(W, pre, x, attn_out, c_shift_msa, c_scale_msa)
+    return post_process(x, y, c_gate_msa)
+
+
+def infer_blocks(W, num_layers, x, embed0, grid_sizes, freqs, context, num_heads, task="t2v", attn="torch_sdpa"):
+    """_infer_without_offload — transformer_infer.py:269-287 (freqs_i recomputed per block in the reference, :349)."""
+    d = x.shape[1] // num_heads
+    for i in range(num_layers):
+        freqs_i = compute_freqs(d // 2, grid_sizes, freqs)
+        x = infer_block(W, i, x, embed0, freqs_i, context, num_heads, task, attn)
+    return x
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# synthetic weights at checkpoint key names (SURVEY.md §8d recipe)
+# ---------------------------------------------------------------------------------------------------------------
+def synth_block_weights(num_layers: int, dim: int, ffn_dim: int, task: str = "t2v", seed: int = 42, device="cpu") -> Dict[str, torch.Tensor]:
+    g = torch.Generator().manual_seed(seed)
+    W: Dict[str, torch.Tensor] = {}
+
+    def lin(name, n, k):
+        W[name + ".weight"] = (torch.randn(n, k, generator=g) * 0.02).to(torch.bfloat16).to(device)
+        W[name + ".bias"] = (torch.randn(n, generator=g) * 0.02).to(torch.bfloat16).to(device)
+
+    def norm_w(name, n):
+        W[name] = (1.0 + torch.randn(n, generator=g) * 0.05).to(torch.bfloat16).to(device)
+
+    for i in range(num_layers):
+        p = f"blocks.{i}."
+        W[p + "modulation"] = (torch.randn(1, 6, dim, generator=g) * 0.1).to(torch.bfloat16).to(device)
+        for nm in ("q", "k", "v", "o"):
+            lin(p + "self_attn." + nm, dim, dim)
+            lin(p + "cross_attn." + nm, dim, dim)
+        norm_w(p + "self_attn.norm_q.weight", dim)
+        norm_w(p + "self_attn.norm_k.weight", dim)
+        norm_w(p + "cross_attn.norm_q.weight", dim)
+        norm_w(p + "cross_attn.norm_k.weight", dim)
+        norm_w(p + "norm3.weight", dim)
+        W[p + "norm3.bias"] = (torch.randn(dim, generator=g) * 0.02).to(torch.bfloat16).to(device)
+        if task == "i2v":
+            lin(p + "cross_attn.k_img", dim, dim)
+            lin(p + "cross_attn.v_img", dim, dim)
+            norm_w(p + "cross_attn.norm_k_img.weight", dim)
+        lin(p + "ffn.0", ffn_dim, dim)
+        lin(p + "ffn.2", dim, ffn_dim)
+    return W
+
+
+def synth_block_inputs(S: int, dim: int, text_len: int = 512, task: str = "t2v", seed: int = 7, device="cpu"):
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(S, dim, generator=g).to(torch.bfloat16).to(device)
+    embed0 = (torch.randn(6, dim, generator=g) * 0.2).to(torch.bfloat16).to(device)
+    ctx_rows = text_len + (257 if task == "i2v" else 0)
+    context = torch.randn(ctx_rows, dim, generator=g).to(torch.bfloat16).to(device)
+    return x, embed0, context
+
+
+def block_flops(S: int, D: int, F_: int, Lt: int = 512, i2v: bool = False) -> float:
+    """FLOPs of one block."""
+    fl = 8 * S * D * D + 4 * S * S * D + 4 * S * D * D + 4 * Lt * D * D + 4 * S * Lt * D + 4 * S * D * F_
+    if i2v:
+        fl += 4 * 257 * D * D + 4 * S * 257 * D
+    return float(fl)

@@ -1,0 +1,58 @@
+"""Pins oracle/wan_oracle.py against fixtures produced by the REAL reference classes (oracle/gen_golden.py)."""
+import os
+
+import pytest
+import torch
+from safetensors import safe_open
+
+from oracle import wan_oracle as O
+
+
+def _load(path):
+    with safe_open(path, framework="pt") as f:
+        return {k: f.get_tensor(k) for k in f.keys()}, f.metadata()
+
+
+@pytest.mark.parametrize("name", ["wan13b_t2v_2blocks", "wan13b_i2v_1block"])
+def test_oracle_matches_reference_fixture(golden_dir, name):
+    torch.set_num_threads(8)
+    T, meta = _load(os.path.join(golden_dir, name + ".safetensors"))
+    dim, heads, ffn, L, task = int(meta["dim"]), int(meta["heads"]), int(meta["ffn"]), int(meta["layers"]), meta["task"]
+    W = O.synth_block_weights(L, dim, ffn, task=task, seed=int(meta["weights_seed"]))
+    grid = T["grid"].tolist()
+    freqs = O.wan_freqs_table(dim // heads)
+
+    # RoPE probe: bit exact
+    fi = O.compute_freqs(dim // heads // 2, grid, freqs)
+    assert torch.equal(O.apply_rotary_emb(T["probe.rope_in"], fi), T["probe.rope_out"])
+
+    # per-function probes on block 0, bit exact (same torch CPU kernels, same op order as the reference)
+    x = T["x_in"].clone()
+    pre = "blocks.0."
+    sh, sc, ga, csh, csc, cga = O.infer_modulation(W, pre, T["embed0"])
+    y = O.infer_self_attn(W, pre, x, fi, sh, sc, heads)
+    assert torch.equal(y, T["probe.self_attn_y"])
+    x2, attn_out = O.infer_cross_attn(W, pre, x, T["context"], y, ga, heads, task)
+    assert torch.equal(x2, T["probe.x_after_cross"])
+    assert torch.equal(attn_out, T["probe.cross_attn_out"])
+    y_ffn = O.infer_ffn(W, pre, x2, attn_out, csh, csc)
+    assert torch.equal(y_ffn, T["probe.ffn_y"])
+
+    # whole stack
+    out = O.infer_blocks(W, L, T["x_in"].clone(), T["embed0"], grid, freqs, T["context"], heads, task)
+    assert torch.equal(out, T["x_out"])
+
+
+def test_freqs_dist_padding_is_identity():
+    freqs = O.wan_freqs_table(128)
+    fi = O.compute_freqs_dist(10, 64, (1, 3, 5), freqs, world_size=2, rank=1)   # 15 tokens padded to 20
+    assert fi.shape == (10, 1, 64)
+    assert torch.all(fi[5:] == 1)
+    full = O.compute_freqs(64, (1, 3, 5), freqs)
+    assert torch.equal(fi[:5], full[10:15])
+
+
+def test_block_flops_matches_survey():
+    # 163.1 TFLOP per block at 14B / 720p
+    fl = O.block_flops(75600, 5120, 13824)
+    assert abs(fl / 1e12 - 163.1) < 0.2
