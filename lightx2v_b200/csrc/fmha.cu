@@ -17,6 +17,8 @@
 #include "host_util.cuh"
 #include "ptx.cuh"
 
+#include <stdlib.h>
+
 namespace b200 {
 
 constexpr int FMHA_D = 128;
@@ -42,6 +44,26 @@ __device__ __forceinline__ float ex2(float x) {
   return y;
 }
 
+// 2^x for x <= ~8 on the FMA pipe: n = round(x) by the 1.5*2^23 trick, f = x - n in [-0.5, 0.5], degree-3 minimax
+// polynomial for 2^f (max relative error 7.5e-5, far below the 2^-9 of the bf16 P it feeds), exponent add in integer.
+__device__ __forceinline__ float2 exp2_poly2(float2 x) {
+  x.x = fmaxf(x.x, -126.f);
+  x.y = fmaxf(x.y, -126.f);
+  const float2 magic = make_float2(12582912.f, 12582912.f);
+  const float2 fi = __fadd2_rn(x, magic);
+  const float2 n = __fadd2_rn(fi, make_float2(-12582912.f, -12582912.f));
+  const float2 f = __ffma2_rn(n, make_float2(-1.f, -1.f), x);
+  float2 p = __ffma2_rn(f, make_float2(0.055171649903059006f, 0.055171649903059006f),
+                        make_float2(0.2426111251115799f, 0.2426111251115799f));
+  p = __ffma2_rn(p, f, make_float2(0.6932609677314758f, 0.6932609677314758f));
+  p = __ffma2_rn(p, f, make_float2(0.9999280571937561f, 0.9999280571937561f));
+  float2 r;
+  r.x = __int_as_float(__float_as_int(p.x) + (__float_as_int(fi.x) << 23));
+  r.y = __int_as_float(__float_as_int(p.y) + (__float_as_int(fi.y) << 23));
+  return r;
+}
+
+template <int kPolyPairs>
 __global__ void __launch_bounds__(FMHA_THREADS, 1)
 fmha_fwd_d128_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                      const __grid_constant__ CUtensorMap tmV, const FmhaParams p) {
@@ -267,18 +289,33 @@ fmha_fwd_d128_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         }
       }
 
+      // exp2(s * scale_log2 - m * scale_log2) on packed f32x2 lanes (FFMA2 / FADD2 halve the fma-pipe instruction count);
+      // kPolyPairs of every 4 pairs take the FMA-pipe polynomial instead of MUFU.EX2, which is the co-critical unit
+      // (16 ex2/clk/SM vs 8192 tensor FLOP/clk/SM: a 128x128 tile costs 1024 MUFU cycles and 1024 MMA cycles).
+      const float2 sl2v = make_float2(sl2, sl2);
       const float neg_m = -m_used * sl2;
-      float sum0 = 0.f, sum1 = 0.f;
+      const float2 negm = make_float2(neg_m, neg_m);
+      float2 acc[4] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
       uint32_t pk[64];
 #pragma unroll
-      for (int i = 0; i < 64; ++i) {
-        const float p0 = ex2(fmaf(__uint_as_float(s[2 * i]), sl2, neg_m));
-        const float p1 = ex2(fmaf(__uint_as_float(s[2 * i + 1]), sl2, neg_m));
-        sum0 += p0;
-        sum1 += p1;
-        pk[i] = pack_bf16(p0, p1);
+      for (int g = 0; g < 16; ++g) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int i = g * 4 + j;
+          const float2 x = __ffma2_rn(make_float2(__uint_as_float(s[2 * i]), __uint_as_float(s[2 * i + 1])), sl2v, negm);
+          float2 e;
+          if (j < kPolyPairs) {
+            e = exp2_poly2(x);
+          } else {
+            e.x = ex2(x.x);
+            e.y = ex2(x.y);
+          }
+          acc[j] = __fadd2_rn(acc[j], e);
+          pk[i] = pack_bf16(e.x, e.y);
+        }
       }
-      l_sum += sum0 + sum1;
+      const float2 a01 = __fadd2_rn(acc[0], acc[1]), a23 = __fadd2_rn(acc[2], acc[3]);
+      l_sum += (a01.x + a01.y) + (a23.x + a23.y);
       tmem_st_x32(tS + 0, pk + 0);    // P (bf16 pairs) overwrites the first 64 columns of S
       tmem_st_x32(tS + 32, pk + 32);
       tmem_st_wait();
@@ -355,14 +392,27 @@ int fmha_fwd_d128(const void* q, long long q_stride_s, const void* k, long long 
   p.out = reinterpret_cast<__nv_bfloat16*>(out);
   p.o_stride_s = o_stride_s;
 
-  static bool attr_set = false;
-  if (!attr_set) {
-    B200_CHECK_CUDA(cudaFuncSetAttribute(fmha_fwd_d128_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         FMHA_SMEM_BYTES));
-    attr_set = true;
+  // fraction of exp2 evaluated by the FMA-pipe polynomial: B200_FMHA_POLY = 0..3 pairs out of every 4 (default 1)
+  static int poly = -1;
+  if (poly < 0) {
+    const char* e = getenv("B200_FMHA_POLY");
+    poly = e ? atoi(e) : 1;
+    if (poly < 0 || poly > 3) poly = 1;
   }
   dim3 grid((unsigned)((sq + 2 * FMHA_BLOCK_Q - 1) / (2 * FMHA_BLOCK_Q)), (unsigned)heads, 1);
-  fmha_fwd_d128_kernel<<<grid, FMHA_THREADS, FMHA_SMEM_BYTES, stream>>>(tmQ, tmK, tmV, p);
+  auto launch = [&](auto kern) -> int {
+    B200_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, FMHA_SMEM_BYTES));
+    kern<<<grid, FMHA_THREADS, FMHA_SMEM_BYTES, stream>>>(tmQ, tmK, tmV, p);
+    return B200_OK;
+  };
+  int rc2;
+  switch (poly) {
+    case 0: rc2 = launch(fmha_fwd_d128_kernel<0>); break;
+    case 2: rc2 = launch(fmha_fwd_d128_kernel<2>); break;
+    case 3: rc2 = launch(fmha_fwd_d128_kernel<3>); break;
+    default: rc2 = launch(fmha_fwd_d128_kernel<1>); break;
+  }
+  if (rc2) return rc2;
   B200_CHECK_CUDA(cudaGetLastError());
   return B200_OK;
 }

@@ -1,0 +1,114 @@
+"""Ulysses sequence parallelism for the Wan block stack: token axis sharded across P ranks for every per-token op,
+head-scatter / sequence-gather all-to-all around self-attention only.
+
+Reference behaviour mirrored:
+  pre_process / post_process  lightx2v/attentions/distributed/utils/wan/processor.py:9-37  (pad to a multiple of P, chunk, all_gather)
+  ulysses_attn                lightx2v/attentions/distributed/ulysses/attn.py:7-91          (3 a2a in, attention on H/P heads, 1 a2a out)
+  all2all_seq2head/head2seq   lightx2v/attentions/distributed/comm/all2all.py:7-89
+  parallelize_wan             lightx2v/attentions/distributed/ulysses/wrap.py:53-71
+
+B200 changes: q, k, v travel in ONE packed all-to-all ([P, S/P, 3, H/P, d], 290 MB per rank at 14B/720p/P=8)
+instead of three; the received buffer is consumed in place by the FMHA as strided [S, H/P, d] views (no .contiguous()
+transposes); no host synchronisation (the reference calls torch.cuda.synchronize() twice per block, attn.py:48,85);
+padded key rows are masked out by passing the true sequence length to the FMHA (the reference lets zero-input pad
+rows act as keys, SURVEY.md §5 "Long-context").
+"""
+from __future__ import annotations
+
+from typing import Callable, Optional
+
+import torch
+import torch.distributed as dist
+
+
+def shard_rows(total: int, world: int) -> int:
+    """Rows per rank after padding to a multiple of `world` (processor.py:13-19)."""
+    return (total + world - 1) // world
+
+
+def pre_process(x: torch.Tensor, rank: int, world: int) -> torch.Tensor:
+    """processor.py:9-21: zero-pad the token axis to a multiple of P and keep this rank's contiguous chunk."""
+    s = shard_rows(x.shape[0], world)
+    pad = s * world - x.shape[0]
+    if pad > 0:
+        x = torch.cat([x, x.new_zeros(pad, x.shape[1])], dim=0)
+    return x[rank * s:(rank + 1) * s].contiguous()
+
+
+def post_process(x: torch.Tensor, total: int, group=None) -> torch.Tensor:
+    """processor.py:24-37: all_gather the shards along the token axis (padding rows dropped here rather than in unpatchify)."""
+    world = dist.get_world_size(group)
+    out = torch.empty((world * x.shape[0], x.shape[1]), dtype=x.dtype, device=x.device)
+    dist.all_gather_into_tensor(out, x.contiguous(), group=group)
+    return out[:total]
+
+
+def pack_qkv_for_a2a(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, world: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """[s, H, d] x3 (any row stride) -> send buffer [P, s, 3, H/P, d]: block p holds heads [p*H/P, (p+1)*H/P) of q, k, v."""
+    s, H, d = q.shape
+    hp = H // world
+    if out is None:
+        out = torch.empty((world, s, 3, hp, d), dtype=q.dtype, device=q.device)
+    for i, t in enumerate((q, k, v)):
+        out[:, :, i].copy_(t.reshape(s, world, hp, d).permute(1, 0, 2, 3))
+    return out
+
+
+def unpack_out_from_a2a(recv: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """recv [P(src = head group), s, H/P, d] -> [s, H, d] with heads in global order (all2all.py:84-87)."""
+    world, s, hp, d = recv.shape
+    if out is None:
+        out = torch.empty((s, world * hp, d), dtype=recv.dtype, device=recv.device)
+    out.view(s, world, hp, d).copy_(recv.permute(1, 0, 2, 3))
+    return out
+
+
+class UlyssesAttention:
+    """parallel_attention hook for WanTransformerInfer: q, k, v [S/P, H, d] -> out [S/P, H, d]."""
+
+    def __init__(self, attention_fn: Callable, total_rows: int, group=None):
+        self.attn = attention_fn            # (q[S,h,d], k, v, out=[S,h,d]) -> out   (lib.fmha on the GPU)
+        self.group = group
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        self.total_rows = total_rows        # true (unpadded) sequence length: padded keys are excluded
+        self._bufs = {}
+
+    def _buf(self, name, shape, like):
+        key = (name, tuple(shape), like.dtype, str(like.device))
+        b = self._bufs.get(key)
+        if b is None:
+            b = torch.empty(shape, dtype=like.dtype, device=like.device)
+            self._bufs[key] = b
+        return b
+
+    def __call__(self, q, k, v, out=None, **_):
+        P = self.world
+        s, H, d = q.shape
+        if H % P != 0:
+            raise ValueError(f"Ulysses needs num_heads ({H}) divisible by world size ({P})")   # attn.py:37
+        hp = H // P
+        send = pack_qkv_for_a2a(q, k, v, P, self._buf("send", (P, s, 3, hp, d), q))
+        recv = self._buf("recv", (P, s, 3, hp, d), q)
+        dist.all_to_all_single(recv, send, group=self.group)
+        full = recv.view(P * s, 3, hp, d)[: self.total_rows]              # rank-major == token order; drop pad rows
+        osend = self._buf("osend", (P, s, hp, d), q)
+        oview = osend.view(P * s, hp, d)
+        if self.total_rows < P * s:
+            oview[self.total_rows:].zero_()
+        # [S, H/P, d] for all tokens, this rank's heads, written straight into the send buffer of the return exchange
+        self.attn(full[:, 0], full[:, 1], full[:, 2], out=oview[: self.total_rows])
+        orecv = self._buf("orecv", (P, s, hp, d), q)
+        dist.all_to_all_single(orecv, osend, group=self.group)
+        return unpack_out_from_a2a(orecv, out)
+
+
+def parallelize_wan(model, total_rows: int, attention_fn: Callable, group=None):
+    """Install the SP hooks on a host.wan_model.WanModel (wrap.py:53-71 does this by monkey-patching)."""
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    ti = model.transformer_infer
+    ti.parallel_attention = UlyssesAttention(attention_fn, total_rows, group)
+    ti.sp_rank, ti.sp_world = rank, world
+    model.pre_process = lambda x: pre_process(x, rank, world)
+    model.post_process = lambda x: post_process(x, total_rows, group)
+    return model

@@ -1,0 +1,151 @@
+"""Wan DiT forward = pre_infer -> block stack -> post_infer, cond/uncond + CFG combine, with the reference's call order
+(lightx2v/models/networks/wan/model.py:197-226) and the reference's pre/post math on the B200 kernels:
+
+  WanPreInfer.infer   lightx2v/models/networks/wan/infer/pre_infer.py:29-120
+      patch-embed conv3d k = s = (1,2,2)  == a [S, C*4] x [C*4, D] GEMM on the unfolded patches  (conv3d.py:40-50)
+      sinusoidal t-embedding in fp64 -> bf16 (utils.py:161-172) -> time MLP -> 6-way projection
+      text MLP with GELU(tanh);  i2v: CLIP MLP (LN -> Linear -> GELU(erf) -> Linear -> LN), concat
+  WanPostInfer.infer  lightx2v/models/networks/wan/infer/post_infer.py:15-50
+      LN -> (1+scale), shift from head.modulation + embed -> Linear(D -> 64) -> unpatchify -> fp32
+Weights are a flat dict with the checkpoint's key names (patch_embedding.*, text_embedding.{0,2}.*, time_embedding.{0,2}.*,
+time_projection.1.*, img_emb.proj.{0,1,3,4}.*, head.head.*, head.modulation, blocks.*)."""
+from __future__ import annotations
+
+import math
+from typing import Dict, Optional
+
+import torch
+import torch.nn.functional as F
+
+from .. import lib
+from .wan_infer import WanTransformerInfer
+from .wan_weights import WanTransformerWeights
+
+
+def sinusoidal_embedding_1d(dim: int, position: torch.Tensor) -> torch.Tensor:
+    """utils.py:161-172 (BF16 mode: fp64 math, one rounding to bf16)."""
+    half = dim // 2
+    position = position.type(torch.float64)
+    sinusoid = torch.outer(position, torch.pow(10000, -torch.arange(half).to(position).div(half)))
+    return torch.cat([torch.cos(sinusoid), torch.sin(sinusoid)], dim=1).to(torch.bfloat16)
+
+
+def rope_params(max_seq_len: int, dim: int, theta: float = 10000.0) -> torch.Tensor:
+    """utils.py:151-158."""
+    freqs = torch.outer(torch.arange(max_seq_len), 1.0 / torch.pow(theta, torch.arange(0, dim, 2).to(torch.float64).div(dim)))
+    return torch.polar(torch.ones_like(freqs), freqs)
+
+
+class WanPreInfer:
+    def __init__(self, config):
+        d = config["dim"] // config["num_heads"]
+        self.task = config["task"]
+        self.freqs = torch.cat([rope_params(1024, d - 4 * (d // 6)), rope_params(1024, 2 * (d // 6)), rope_params(1024, 2 * (d // 6))], dim=1)
+        self.freq_dim = config["freq_dim"]
+        self.dim = config["dim"]
+        self.text_len = config["text_len"]
+        self.scheduler = None
+
+    def set_scheduler(self, scheduler):
+        self.scheduler = scheduler
+
+    def infer(self, W: Dict[str, torch.Tensor], inputs, positive: bool):
+        x = self.scheduler.latents                                       # [C, F, H, W] (bf16 after step_pre)
+        t = torch.stack([self.scheduler.timesteps[self.scheduler.step_index]])
+        context = inputs["text_encoder_output"]["context" if positive else "context_null"]
+        if self.task == "i2v":
+            clip_fea = inputs["image_encoder_output"]["clip_encoder_out"]
+            x = torch.cat([x, inputs["image_encoder_output"]["vae_encode_out"].to(x.dtype)], dim=0)
+        C, Fr, H, Wd = x.shape
+        gh, gw = H // 2, Wd // 2
+        grid_sizes = torch.tensor([[Fr, gh, gw]], dtype=torch.long)
+        # patch embedding as a GEMM: token (f, y, x) <- patch x[:, f, 2y:2y+2, 2x:2x+2] flattened in (c, dy, dx) order
+        patches = x.to(torch.bfloat16).view(C, Fr, gh, 2, gw, 2).permute(1, 2, 4, 0, 3, 5).reshape(Fr * gh * gw, C * 4).contiguous()
+        pw = W["patch_embedding.weight"].reshape(self.dim, C * 4)
+        xs = lib.gemm_bf16(patches, pw, W["patch_embedding.bias"])
+        seq_lens = torch.tensor([xs.shape[0]], dtype=torch.long)
+
+        embed = sinusoidal_embedding_1d(self.freq_dim, t.flatten().cpu()).to(xs.device)
+        embed = lib.gemm_bf16(embed, W["time_embedding.0.weight"], W["time_embedding.0.bias"])
+        embed = F.silu(embed)
+        embed = lib.gemm_bf16(embed, W["time_embedding.2.weight"], W["time_embedding.2.bias"])
+        embed0 = lib.gemm_bf16(F.silu(embed), W["time_projection.1.weight"], W["time_projection.1.bias"]).unflatten(1, (6, self.dim))
+
+        ctx = context
+        if ctx.shape[0] < self.text_len:
+            ctx = torch.cat([ctx, ctx.new_zeros(self.text_len - ctx.shape[0], ctx.shape[1])])
+        out = lib.gemm_bf16(ctx.contiguous(), W["text_embedding.0.weight"], W["text_embedding.0.bias"], epilogue=lib.EPI_BIAS_GELU)
+        context = lib.gemm_bf16(out, W["text_embedding.2.weight"], W["text_embedding.2.bias"])
+        if self.task == "i2v":
+            c = lib.ln_modulate(clip_fea.contiguous(), weight=W["img_emb.proj.0.weight"], bias=W["img_emb.proj.0.bias"], eps=1e-6)
+            c = lib.gemm_bf16(c, W["img_emb.proj.1.weight"], W["img_emb.proj.1.bias"])
+            c = F.gelu(c, approximate="none")
+            c = lib.gemm_bf16(c, W["img_emb.proj.3.weight"], W["img_emb.proj.3.bias"])
+            c = lib.ln_modulate(c, weight=W["img_emb.proj.4.weight"], bias=W["img_emb.proj.4.bias"], eps=1e-6)
+            context = torch.cat([c, context], dim=0)
+        return embed, grid_sizes, (xs, embed0.squeeze(0), seq_lens, self.freqs, context)
+
+
+class WanPostInfer:
+    def __init__(self, config):
+        self.out_dim = config["out_dim"]
+        self.patch_size = (1, 2, 2)
+        self.scheduler = None
+
+    def set_scheduler(self, scheduler):
+        self.scheduler = scheduler
+
+    def infer(self, W, x, e, grid_sizes):
+        mod = (W["head.modulation"] + e.unsqueeze(1)).reshape(2, -1)       # post_infer.py:16-18: [shift, scale]
+        x = lib.ln_modulate(x, scale=mod[1], shift=mod[0], eps=1e-6)
+        x = lib.gemm_bf16(x, W["head.head.weight"], W["head.head.bias"])
+        return [u.float() for u in self.unpatchify(x, grid_sizes)]
+
+    def unpatchify(self, x, grid_sizes):
+        """post_infer.py:41-50."""
+        c = self.out_dim
+        out = []
+        for u, v in zip(x.unsqueeze(0), grid_sizes.tolist()):
+            u = u[: math.prod(v)].view(*v, *self.patch_size, c)
+            u = torch.einsum("fhwpqrc->cfphqwr", u)
+            out.append(u.reshape(c, *[i * j for i, j in zip(v, self.patch_size)]))
+        return out
+
+
+class WanModel:
+    """Weights already resident on the GPU (180 GB HBM3e: no offload), built from a flat checkpoint-named dict."""
+
+    def __init__(self, config, weight_dict: Dict[str, torch.Tensor]):
+        self.config = config
+        self.W = weight_dict
+        self.transformer_weights = WanTransformerWeights(config)
+        self.transformer_weights.load(weight_dict)
+        self.pre_infer = WanPreInfer(config)
+        self.post_infer = WanPostInfer(config)
+        self.transformer_infer = WanTransformerInfer(config)
+        self.scheduler = None
+        self.pre_process = None      # sequence-parallel hooks (host/ulysses.py)
+        self.post_process = None
+
+    def set_scheduler(self, scheduler):
+        self.scheduler = scheduler
+        self.pre_infer.set_scheduler(scheduler)
+        self.post_infer.set_scheduler(scheduler)
+
+    def _forward(self, inputs, positive: bool):
+        embed, grid_sizes, (x, embed0, seq_lens, freqs, context) = self.pre_infer.infer(self.W, inputs, positive)
+        if self.pre_process is not None:
+            x = self.pre_process(x)
+        x = self.transformer_infer.infer(self.transformer_weights, grid_sizes, embed, x, embed0, seq_lens, freqs, context)
+        if self.post_process is not None:
+            x = self.post_process(x)
+        return self.post_infer.infer(self.W, x, embed, grid_sizes)[0]
+
+    @torch.no_grad()
+    def infer(self, inputs):
+        """model.py:197-226: cond pass, then (enable_cfg) uncond pass and `uncond + g * (cond - uncond)` in fp32."""
+        cond = self._forward(inputs, True)
+        self.scheduler.noise_pred = cond
+        if self.config.get("enable_cfg", False):
+            uncond = self._forward(inputs, False)
+            self.scheduler.noise_pred = uncond + self.config["sample_guide_scale"] * (cond - uncond)

@@ -1,0 +1,138 @@
+"""CPU-only tests: C-ABI surface (header <-> exported symbols <-> ctypes table), host-side mirror of the reference
+operator interface, RoPE table construction, and the rule that the product path has no CPU fallback."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+from oracle import wan_oracle as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def built_lib():
+    import __graft_entry__ as g
+
+    if not os.path.exists(g.LIB_PATH):
+        g.build()
+    return ctypes.CDLL(g.LIB_PATH)
+
+
+def _header_symbols():
+    text = open(os.path.join(ROOT, "include", "b200_dit.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(b200_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_header_declares_what_ctypes_binds():
+    from lightx2v_b200 import lib
+
+    assert _header_symbols() == sorted(lib.SIGNATURES.keys())
+
+
+def test_library_exports_every_declared_symbol(built_lib):
+    for sym in _header_symbols():
+        assert hasattr(built_lib, sym), sym
+    built_lib.b200_version.restype = ctypes.c_int
+    assert built_lib.b200_version() >= 100
+
+
+def test_argument_validation_without_gpu(built_lib):
+    """Shape/alignment checks run before any CUDA call, so they are testable on the CPU box."""
+    f = built_lib.b200_gemm_bf16
+    f.restype = ctypes.c_int
+    f.argtypes = [ctypes.c_void_p, ctypes.c_int64] * 3 + [ctypes.c_void_p] * 2 + [ctypes.c_int64] * 3 + [ctypes.c_int] * 3 + [ctypes.c_void_p]
+    built_lib.b200_last_error.restype = ctypes.c_char_p
+    assert f(None, 8, None, 8, None, 8, None, None, 8, 8, 8, 0, 0, 0, None) == -1
+    assert b"null" in built_lib.b200_last_error()
+    assert f(16, 100, 16, 100, 16, 8, None, None, 8, 8, 100, 0, 0, 0, None) == -1     # K % 8 != 0
+    assert b"multiples of 8" in built_lib.b200_last_error()
+    assert f(16, 64, 16, 64, 16, 64, None, None, 8, 64, 64, 2, 0, 0, None) == -1       # gate epilogue without gate
+    g = built_lib.b200_fmha_fwd_d128
+    g.restype = ctypes.c_int
+    g.argtypes = [ctypes.c_void_p, ctypes.c_int64] * 4 + [ctypes.c_int64, ctypes.c_int64, ctypes.c_int, ctypes.c_float, ctypes.c_void_p]
+    assert g(16, 128, 16, 128, 16, 128, 16, 128, 0, 5, 1, 1.0, None) == -1             # empty segment
+    assert g(16, 100, 16, 128, 16, 128, 16, 128, 4, 4, 1, 1.0, None) == -1             # stride not multiple of 8
+
+
+def test_no_cpu_fallback():
+    from lightx2v_b200 import lib
+
+    x = torch.zeros(8, 64, dtype=torch.bfloat16)
+    with pytest.raises(lib.B200Error):
+        lib.gemm_bf16(x, x)
+    with pytest.raises(lib.B200Error):
+        lib.ln_modulate(x)
+    with pytest.raises(lib.B200Error):
+        lib.fmha(torch.zeros(4, 1, 128, dtype=torch.bfloat16), torch.zeros(4, 1, 128, dtype=torch.bfloat16), torch.zeros(4, 1, 128, dtype=torch.bfloat16))
+
+
+def test_product_code_never_imports_the_oracle():
+    for base, _, files in os.walk(os.path.join(ROOT, "lightx2v_b200")):
+        for fn in files:
+            if fn.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(base, fn)).read()
+                assert "oracle" not in src.replace("no oracle", ""), f"{fn} mentions the oracle"
+
+
+def test_registry_semantics_match_reference():
+    from lightx2v_b200.host.registry import Register
+
+    R = Register()
+
+    @R("a")
+    class A:  # noqa
+        pass
+
+    assert R["a"] is A and "a" in R
+    with pytest.raises(Exception):
+        R.register(A, key="a")                 # duplicate keys raise (registry_factory.py:19-20)
+    R["a"] = int                               # __setitem__ overrides silently (registry_factory.py:25-26)
+    assert R["a"] is int
+
+
+def test_weight_tree_keys_and_state_dict_round_trip():
+    from lightx2v_b200.host.wan_weights import WanTransformerWeights
+
+    dim, ffn = 256, 512
+    for task in ("t2v", "i2v"):
+        W = O.synth_block_weights(2, dim, ffn, task=task, seed=5)
+        cfg = dict(task=task, num_layers=2, num_heads=2, dim=dim, ffn_dim=ffn, mm_config={})
+        tree = WanTransformerWeights(cfg)
+        tree.load(W)
+        blk = tree.blocks[1]
+        assert [type(p).__name__ for p in blk.compute_phases] == ["WanModulation", "WanSelfAttention", "WanCrossAttention", "WanFFN"]
+        sa = blk.compute_phases[1]
+        assert sa.self_attn_q.weight.shape == (dim, dim) and not sa.self_attn_q.weight.is_contiguous()   # [K,N] view like mm_weight.py:76
+        assert sa.self_attn_q.weight_nk.is_contiguous()
+        sd = tree.state_dict()
+        assert set(sd.keys()) == set(W.keys())
+        for k in W:
+            assert torch.equal(sd[k], W[k]), k
+        assert tree.calculate_size() == sum(v.numel() * 2 for v in W.values())
+
+
+def test_rope_cos_sin_matches_reference_tables():
+    from lightx2v_b200.host.wan_infer import rope_cos_sin
+
+    freqs = O.wan_freqs_table(128)
+    grid = (3, 4, 5)
+    t = rope_cos_sin(grid, freqs, 128)
+    fi = O.compute_freqs(64, grid, freqs).reshape(60, 64)
+    assert torch.equal(t[..., 0], fi.real.float()) and torch.equal(t[..., 1], fi.imag.float())
+    # sharded (Ulysses) variant == compute_freqs_dist: pad rows are the identity rotation
+    for rank in range(4):
+        ts = rope_cos_sin(grid, freqs, 128, rows=16, row_offset=rank * 16)
+        fd = O.compute_freqs_dist(16, 64, grid, freqs, 4, rank).reshape(16, 64)
+        assert torch.equal(ts[..., 0], fd.real.float()) and torch.equal(ts[..., 1], fd.imag.float())
+
+
+def test_fmha_op_segment_bounds():
+    from lightx2v_b200.host.ops import FmhaWeightB200
+
+    assert FmhaWeightB200._bounds(None, 7) == [0, 7]
+    assert FmhaWeightB200._bounds(torch.tensor([0, 5, 9], dtype=torch.int32), 9) == [0, 5, 9]
+    assert FmhaWeightB200._bounds([0, 3], 3) == [0, 3]
