@@ -67,6 +67,28 @@ int b200_fmha_fwd_d128(const void* q, int64_t q_stride_s, const void* k, int64_t
                        int64_t v_stride_s, void* out, int64_t o_stride_s, int64_t sq, int64_t sk, int heads,
                        float softmax_scale, b200_stream_t stream);
 
+/* ---- w8a8-fp8 path (BASELINE config 3) ------------------------------------------------------------------------------- */
+
+/* C[M,N] (bf16) = epilogue( a_scale[m] * (b_scale[n] * (A[M,K] * B[N,K]^T)) + bias[N] ),  A and B e4m3 (1 byte/element, leading
+ * dimensions in elements, multiples of 16), a_scale [M] fp32 per-token, b_scale [N] fp32 per-out-channel.  Same epilogues as
+ * b200_gemm_bf16.  Replaces `torch.ops._C.cutlass_scaled_mm(out, xq, Wq, sx, sw, bias)` in
+ * MMWeightWfp8channelAfp8channeldynamicVllm.apply (lightx2v/common/ops/mm/mm_weight.py:304-319). */
+int b200_gemm_fp8(const void* A, int64_t lda, const void* B, int64_t ldb, void* C, int64_t ldc, const float* a_scale,
+                  const float* b_scale, const void* bias, const void* gate, int64_t M, int64_t N, int64_t K, int epilogue,
+                  int block_n, int max_ctas, b200_stream_t stream);
+
+/* Dynamic per-token e4m3 quantisation: scale[r] = max(absmax(x[r,:]) / 448, 1/(448*512)); q = e4m3_rn_sat(x / scale).
+ * Replaces `ops.scaled_fp8_quant(x, None, scale_ub=None, use_per_token_if_dynamic=True)`
+ * (act_quant_fp8_perchannel_sym_vllm, lightx2v/common/ops/mm/mm_weight.py:236-238). */
+int b200_quant_fp8_per_token(const void* x, int64_t ldx, void* q8, int64_t ldq, float* q_scale, int64_t rows, int D,
+                             b200_stream_t stream);
+
+/* b200_ln_modulate whose output goes straight to e4m3 + per-token scale (the bf16 tensor the reference would quantise is
+ * formed in registers and never written): LNWeight.apply + modulation + act quant in one pass. */
+int b200_ln_modulate_fp8(const void* x, int64_t ldx, void* q8, int64_t ldq, float* q_scale, const void* ln_w,
+                         const void* ln_b, const void* scale, const void* shift, int64_t rows, int D, float eps,
+                         b200_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

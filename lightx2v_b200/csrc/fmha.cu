@@ -141,28 +141,34 @@ fmha_fwd_d128_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     }
   } else if (warp == 1) {
     // ============================== MMA issuer ==============================
-    if (lane == 0) {
+    // The whole warp runs this (warp-uniform) control flow so that descriptors and loop state live in uniform registers;
+    // each tcgen05.mma / tcgen05.commit is executed by one elected lane (the *_w wrappers).
+    {
       constexpr uint32_t idesc_qk = make_idesc(FMT_BF16, FMT_BF16, 128, 128, 0, 0);  // A=Q K-major, B=K K-major
       constexpr uint32_t idesc_pv = make_idesc(FMT_BF16, FMT_BF16, 128, 128, 0, 1);  // A=P (TMEM), B=V MN-major
-      const uint32_t tS[2] = {tmem_base + COL_S0, tmem_base + COL_S1};
-      const uint32_t tO[2] = {tmem_base + COL_O0, tmem_base + COL_O1};
+      const uint32_t tb = __shfl_sync(0xffffffffu, tmem_base, 0);   // make the TMEM base provably warp-uniform (-> uniform register)
+      const uint32_t tS0 = tb + COL_S0, tS1 = tb + COL_S1;
+      const uint32_t tO0 = tb + COL_O0, tO1 = tb + COL_O1;
+      const uint32_t q_lo = desc_lo_kmajor(smem_u32(sQ));
+      const uint32_t kv_addr = smem_u32(sKV);
 
       auto issue_qk = [&](int t, int kstage) {
-        const uint32_t qa = smem_u32(sQ + t * FMHA_TILE_BYTES);
-        const uint32_t kb = smem_u32(sKV + kstage * FMHA_TILE_BYTES);
+        const uint32_t a = q_lo + t * (FMHA_TILE_BYTES >> 4);
+        const uint32_t b = desc_lo_kmajor(kv_addr + kstage * FMHA_TILE_BYTES);
+        const uint32_t d = t ? tS1 : tS0;
 #pragma unroll
         for (int ks = 0; ks < 8; ++ks) {  // d = 128 in steps of 16; 4 steps per 64-wide panel
-          const uint32_t off = (ks >> 2) * FMHA_PANEL_BYTES + (ks & 3) * 32;
-          mma_f16_ss(tS[t], make_desc_kmajor_sw128(qa + off), make_desc_kmajor_sw128(kb + off), idesc_qk,
-                     ks != 0 ? 1u : 0u);
+          const uint32_t off = ((ks >> 2) * FMHA_PANEL_BYTES + (ks & 3) * 32) >> 4;
+          mma_f16_ss_w(d, a + off, kDescHiSw128, b + off, kDescHiSw128, idesc_qk, ks != 0 ? 1u : 0u);
         }
       };
-      auto issue_pv = [&](int t, int vstage, bool accumulate) {
-        const uint32_t vb = smem_u32(sKV + vstage * FMHA_TILE_BYTES);
+      auto issue_pv = [&](int t, int vstage, uint32_t accumulate) {
+        const uint32_t b = desc_lo_mnmajor(kv_addr + vstage * FMHA_TILE_BYTES, FMHA_PANEL_BYTES);
+        const uint32_t d = t ? tO1 : tO0;
+        const uint32_t a = t ? tS1 : tS0;
 #pragma unroll
         for (int ks = 0; ks < 8; ++ks) {  // kv = 128 in steps of 16 rows (16 x 128 B = 2048 B); P: 8 columns per step
-          mma_f16_ts(tO[t], tS[t] + ks * 8, make_desc_mnmajor_sw128(vb + ks * 2048, FMHA_PANEL_BYTES), idesc_pv,
-                     (accumulate || ks != 0) ? 1u : 0u);
+          mma_f16_ts_w(d, a + ks * 8, b + ks * (2048 >> 4), kDescHiSw128, idesc_pv, ks != 0 ? 1u : accumulate);
         }
       };
 
@@ -180,10 +186,10 @@ fmha_fwd_d128_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       mbar_wait(&kv_full[stage], phase);
       tc_fence_after();
       issue_qk(0, stage);
-      tc_commit(&s_full[0]);
+      tc_commit_w(&s_full[0]);
       issue_qk(1, stage);
-      tc_commit(&s_full[1]);
-      tc_commit(&kv_empty[stage]);
+      tc_commit_w(&s_full[1]);
+      tc_commit_w(&kv_empty[stage]);
       advance();
 
       for (int j = 0; j < n_kv; ++j) {
@@ -199,27 +205,28 @@ fmha_fwd_d128_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
           advance();
         }
         const uint32_t pj = j & 1;
+        const uint32_t acc = j > 0 ? 1u : 0u;
         // ---- tile 0
         mbar_wait(&p_full[0], pj);
         tc_fence_after();
-        issue_pv(0, vstage, j > 0);
+        issue_pv(0, vstage, acc);
         if (has_next) {
           issue_qk(0, kstage);
-          tc_commit(&s_full[0]);
+          tc_commit_w(&s_full[0]);
         } else {
-          tc_commit(&o_full[0]);
+          tc_commit_w(&o_full[0]);
         }
         // ---- tile 1
         mbar_wait(&p_full[1], pj);
         tc_fence_after();
-        issue_pv(1, vstage, j > 0);
-        tc_commit(&kv_empty[vstage]);
+        issue_pv(1, vstage, acc);
+        tc_commit_w(&kv_empty[vstage]);
         if (has_next) {
           issue_qk(1, kstage);
-          tc_commit(&s_full[1]);
-          tc_commit(&kv_empty[kstage]);
+          tc_commit_w(&s_full[1]);
+          tc_commit_w(&kv_empty[kstage]);
         } else {
-          tc_commit(&o_full[1]);
+          tc_commit_w(&o_full[1]);
         }
       }
     }
@@ -396,7 +403,7 @@ int fmha_fwd_d128(const void* q, long long q_stride_s, const void* k, long long 
   static int poly = -1;
   if (poly < 0) {
     const char* e = getenv("B200_FMHA_POLY");
-    poly = e ? atoi(e) : 1;
+    poly = e ? atoi(e) : 1;   // measured on B200: 0 -> 1.19, 1 -> 1.23, 2 -> 1.13 PFLOP/s at S = 75 600 x 40 heads
     if (poly < 0 || poly > 3) poly = 1;
   }
   dim3 grid((unsigned)((sq + 2 * FMHA_BLOCK_Q - 1) / (2 * FMHA_BLOCK_Q)), (unsigned)heads, 1);

@@ -13,6 +13,8 @@
 #include "host_util.cuh"
 #include "ptx.cuh"
 
+#include <stdlib.h>
+
 namespace b200 {
 
 enum GemmEpilogue : int {
@@ -47,12 +49,15 @@ struct GemmParams {
   const __nv_bfloat16* gate;   // [N] (EPI_GATE_RESIDUAL)
   __nv_bfloat16* C;            // residual source (in-place epilogues)
   long long ldc;
+  int group_m;                 // M-blocks per rasterisation group
+  const float* scale_a;        // fp8 path: per-row (token) activation scale [M]
+  const float* scale_b;        // fp8 path: per-column (out-channel) weight scale [N]
 };
 
 // Tile rasterisation: groups of kGroupM m-blocks, n fastest inside a group-row sweep, so the ~148 tiles in flight
 // touch ~16 A panels and ~10 B panels (L2-resident) instead of 148 A panels.
 __device__ __forceinline__ void tile_coords(int tile, const GemmParams& p, int& m_blk, int& n_blk) {
-  constexpr int kGroupM = 16;
+  const int kGroupM = p.group_m;
   const int tiles_per_group = kGroupM * p.num_n_blocks;
   const int group = tile / tiles_per_group;
   const int first_m = group * kGroupM;
@@ -71,7 +76,10 @@ __device__ __forceinline__ float gelu_tanh_f(float x) {
   return 0.5f * x * (1.0f + t);
 }
 
-template <int BLOCK_N, int EPI>
+// kFp8 = false: bf16 x bf16 (kind::f16, 64 elements per 128-byte K-block)
+// kFp8 = true : e4m3 x e4m3 (kind::f8f6f4, 128 elements per 128-byte K-block), epilogue applies the per-token and
+//               per-channel scales:  y = sa[m] * (sb[n] * acc) + bias   (vLLM cutlass_scaled_mm semantics, mm_weight.py:304-319)
+template <int BLOCK_N, int EPI, bool kFp8>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ CUtensorMap tmC, const GemmParams p) {
@@ -127,8 +135,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         for (int kb = 0; kb < p.num_k_blocks; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
-          tma_load_2d(sA + stage * Cfg::kABytes, &tmA, &full_bar[stage], kb * GEMM_BLOCK_K, m_blk * GEMM_BLOCK_M);
-          tma_load_2d(sB + stage * Cfg::kBBytes, &tmB, &full_bar[stage], kb * GEMM_BLOCK_K, n_blk * BLOCK_N);
+          constexpr int kElemsPerKBlock = kFp8 ? 128 : 64;   // 128 bytes either way
+          tma_load_2d(sA + stage * Cfg::kABytes, &tmA, &full_bar[stage], kb * kElemsPerKBlock, m_blk * GEMM_BLOCK_M);
+          tma_load_2d(sB + stage * Cfg::kBBytes, &tmB, &full_bar[stage], kb * kElemsPerKBlock, n_blk * BLOCK_N);
           if (++stage == kStages) {
             stage = 0;
             phase ^= 1;
@@ -138,36 +147,42 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc(FMT_BF16, FMT_BF16, GEMM_BLOCK_M, BLOCK_N, 0, 0);
-      int stage = 0;
-      uint32_t phase = 0;
-      int acc = 0;
-      uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
+    // Whole warp, warp-uniform control flow (descriptors and loop state in uniform registers); one elected lane per
+    // tcgen05 instruction (the *_w wrappers in ptx.cuh).
+    constexpr uint32_t idesc = kFp8 ? make_idesc(FMT_E4M3, FMT_E4M3, GEMM_BLOCK_M, BLOCK_N, 0, 0)
+                                    : make_idesc(FMT_BF16, FMT_BF16, GEMM_BLOCK_M, BLOCK_N, 0, 0);
+    const uint32_t tb = __shfl_sync(0xffffffffu, tmem_base, 0);
+    const uint32_t a_lo0 = desc_lo_kmajor(smem_u32(sA));
+    const uint32_t b_lo0 = desc_lo_kmajor(smem_u32(sB));
+    int stage = 0;
+    uint32_t phase = 0;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tb + acc * BLOCK_N;
+      for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+        mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
-        for (int kb = 0; kb < p.num_k_blocks; ++kb) {
-          mbar_wait(&full_bar[stage], phase);
-          tc_fence_after();
-          const uint64_t a_desc = make_desc_kmajor_sw128(smem_u32(sA + stage * Cfg::kABytes));
-          const uint64_t b_desc = make_desc_kmajor_sw128(smem_u32(sB + stage * Cfg::kBBytes));
+        const uint32_t a_lo = a_lo0 + stage * (Cfg::kABytes >> 4);
+        const uint32_t b_lo = b_lo0 + stage * (Cfg::kBBytes >> 4);
 #pragma unroll
-          for (int k = 0; k < GEMM_BLOCK_K / GEMM_UMMA_K; ++k) {
-            // +32 bytes along K inside the 128B swizzle row = +2 in the (addr >> 4) field
-            mma_f16_ss(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
-          }
-          tc_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs have read it
-          if (++stage == kStages) {
-            stage = 0;
-            phase ^= 1;
-          }
+        for (int k = 0; k < GEMM_BLOCK_K / GEMM_UMMA_K; ++k) {
+          // +32 bytes along K inside the 128B swizzle row = +2 in the (addr >> 4) field
+          const uint32_t accum = (kb | k) != 0 ? 1u : 0u;
+          if constexpr (kFp8) mma_f8_ss_w(d_tmem, a_lo + 2 * k, kDescHiSw128, b_lo + 2 * k, kDescHiSw128, idesc, accum);
+          else mma_f16_ss_w(d_tmem, a_lo + 2 * k, kDescHiSw128, b_lo + 2 * k, kDescHiSw128, idesc, accum);
         }
-        tc_commit(&tmem_full_bar[acc]);  // accumulator complete -> epilogue
-        acc ^= 1;
-        if (acc == 0) acc_phase ^= 1;
+        tc_commit_w(&empty_bar[stage]);  // frees the smem slot once these MMAs have read it
+        if (++stage == kStages) {
+          stage = 0;
+          phase ^= 1;
+        }
       }
+      tc_commit_w(&tmem_full_bar[acc]);  // accumulator complete -> epilogue
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
     }
   } else if (warp >= 4) {
     // ===================== epilogue =====================
@@ -186,6 +201,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       tc_fence_after();
       const uint32_t t_row = tmem_base + acc * BLOCK_N + (uint32_t(ewarp * 32) << 16);
       const bool row_ok = (m0 + row) < p.M;
+      float sa = 1.0f;
+      if constexpr (kFp8) sa = row_ok ? __ldg(p.scale_a + m0 + row) : 0.0f;
 
 #pragma unroll 1
       for (int c = 0; c < BLOCK_N / GEMM_EPI_CHUNK; ++c) {
@@ -208,6 +225,15 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           float f[8];
 #pragma unroll
           for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(v[j * 8 + e]);
+          if constexpr (kFp8) {
+            if (col < p.N) {
+              const float4 s0 = __ldg(reinterpret_cast<const float4*>(p.scale_b + col));
+              const float4 s1 = __ldg(reinterpret_cast<const float4*>(p.scale_b + col + 4));
+              const float sb[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+#pragma unroll
+              for (int e = 0; e < 8; ++e) f[e] = sa * (sb[e] * f[e]);
+            }
+          }
           if (p.bias != nullptr && col < p.N) {
             uint4 bv = __ldg(reinterpret_cast<const uint4*>(p.bias + col));
             const uint32_t bw[4] = {bv.x, bv.y, bv.z, bv.w};
@@ -276,11 +302,11 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   }
 }
 
-template <int BLOCK_N, int EPI>
+template <int BLOCK_N, int EPI, bool kFp8>
 static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const GemmParams& p,
                        int max_ctas, cudaStream_t stream) {
   using Cfg = GemmCfg<BLOCK_N>;
-  auto kern = gemm_bf16_kernel<BLOCK_N, EPI>;
+  auto kern = gemm_bf16_kernel<BLOCK_N, EPI, kFp8>;
   static bool attr_set = false;
   if (!attr_set) {
     B200_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
@@ -293,14 +319,14 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUt
   return B200_OK;
 }
 
-template <int BLOCK_N>
+template <int BLOCK_N, bool kFp8>
 static int dispatch_epi(int epi, const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC,
                         const GemmParams& p, int max_ctas, cudaStream_t stream) {
   switch (epi) {
-    case EPI_BIAS: return launch_gemm<BLOCK_N, EPI_BIAS>(tmA, tmB, tmC, p, max_ctas, stream);
-    case EPI_BIAS_GELU: return launch_gemm<BLOCK_N, EPI_BIAS_GELU>(tmA, tmB, tmC, p, max_ctas, stream);
-    case EPI_GATE_RESIDUAL: return launch_gemm<BLOCK_N, EPI_GATE_RESIDUAL>(tmA, tmB, tmC, p, max_ctas, stream);
-    case EPI_RESIDUAL: return launch_gemm<BLOCK_N, EPI_RESIDUAL>(tmA, tmB, tmC, p, max_ctas, stream);
+    case EPI_BIAS: return launch_gemm<BLOCK_N, EPI_BIAS, kFp8>(tmA, tmB, tmC, p, max_ctas, stream);
+    case EPI_BIAS_GELU: return launch_gemm<BLOCK_N, EPI_BIAS_GELU, kFp8>(tmA, tmB, tmC, p, max_ctas, stream);
+    case EPI_GATE_RESIDUAL: return launch_gemm<BLOCK_N, EPI_GATE_RESIDUAL, kFp8>(tmA, tmB, tmC, p, max_ctas, stream);
+    case EPI_RESIDUAL: return launch_gemm<BLOCK_N, EPI_RESIDUAL, kFp8>(tmA, tmB, tmC, p, max_ctas, stream);
   }
   set_last_error("b200_gemm_bf16: unknown epilogue %d", epi);
   return B200_ERR_INVALID;
@@ -341,8 +367,70 @@ int gemm_bf16(const void* A, long long lda, const void* B, long long ldb, void* 
   p.gate = reinterpret_cast<const __nv_bfloat16*>(gate);
   p.C = reinterpret_cast<__nv_bfloat16*>(C);
   p.ldc = ldc;
-  if (block_n == 256) return dispatch_epi<256>(epilogue, tmA, tmB, tmC, p, max_ctas, stream);
-  return dispatch_epi<128>(epilogue, tmA, tmB, tmC, p, max_ctas, stream);
+  {
+    static int group_m = 0;
+    if (group_m == 0) {
+      const char* e = getenv("B200_GEMM_GROUP_M");
+      group_m = e ? atoi(e) : 16;
+      if (group_m < 1) group_m = 16;
+    }
+    p.group_m = group_m;
+  }
+  p.scale_a = nullptr;
+  p.scale_b = nullptr;
+  if (block_n == 256) return dispatch_epi<256, false>(epilogue, tmA, tmB, tmC, p, max_ctas, stream);
+  return dispatch_epi<128, false>(epilogue, tmA, tmB, tmC, p, max_ctas, stream);
+}
+
+// e4m3 x e4m3 -> bf16 with per-token / per-channel scales.  A [M,K] e4m3, B [N,K] e4m3 (lda/ldb in elements = bytes).
+int gemm_fp8(const void* A, long long lda, const void* B, long long ldb, void* C, long long ldc, const float* scale_a,
+             const float* scale_b, const void* bias, const void* gate, long long M, long long N, long long K,
+             int epilogue, int block_n, int max_ctas, cudaStream_t stream) {
+  B200_CHECK_ARG(A && B && C && scale_a && scale_b, "b200_gemm_fp8: null operand / scale pointer");
+  B200_CHECK_ARG(M > 0 && N > 0 && K > 0, "b200_gemm_fp8: non-positive shape M=%lld N=%lld K=%lld", M, N, K);
+  B200_CHECK_ARG(K % 16 == 0 && N % 8 == 0, "b200_gemm_fp8: K (%lld) must be a multiple of 16 and N (%lld) of 8", K, N);
+  B200_CHECK_ARG(lda % 16 == 0 && ldb % 16 == 0 && ldc % 8 == 0 && lda >= K && ldb >= K && ldc >= N,
+                 "b200_gemm_fp8: bad leading dimensions (lda=%lld ldb=%lld ldc=%lld)", lda, ldb, ldc);
+  B200_CHECK_ARG(((uintptr_t)A % 16 == 0) && ((uintptr_t)B % 16 == 0) && ((uintptr_t)C % 16 == 0) &&
+                     ((uintptr_t)scale_b % 16 == 0),
+                 "b200_gemm_fp8: operands must be 16-byte aligned");
+  B200_CHECK_ARG(epilogue != EPI_GATE_RESIDUAL || gate != nullptr, "b200_gemm_fp8: gate epilogue needs a gate vector");
+  if (block_n == 0) block_n = (N >= 256) ? 256 : 128;
+  B200_CHECK_ARG(block_n == 128 || block_n == 256, "b200_gemm_fp8: block_n must be 128 or 256");
+  if (max_ctas <= 0) max_ctas = num_sms();
+
+  CUtensorMap tmA, tmB, tmC;
+  int rc;
+  {
+    uint64_t dims[2] = {(uint64_t)K, (uint64_t)M};
+    uint64_t strides[1] = {(uint64_t)lda};
+    uint32_t box[2] = {128, GEMM_BLOCK_M};
+    if ((rc = encode_tmap(&tmA, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, A, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
+  }
+  {
+    uint64_t dims[2] = {(uint64_t)K, (uint64_t)N};
+    uint64_t strides[1] = {(uint64_t)ldb};
+    uint32_t box[2] = {128, (uint32_t)block_n};
+    if ((rc = encode_tmap(&tmB, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, B, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
+  }
+  if ((rc = encode_tmap_2d_bf16(&tmC, C, M, N, ldc, GEMM_BLOCK_M, GEMM_EPI_CHUNK))) return rc;
+
+  GemmParams p;
+  p.M = (int)M;
+  p.N = (int)N;
+  p.K = (int)K;
+  p.num_m_blocks = (int)((M + GEMM_BLOCK_M - 1) / GEMM_BLOCK_M);
+  p.num_n_blocks = (int)((N + block_n - 1) / block_n);
+  p.num_k_blocks = (int)((K + 127) / 128);
+  p.bias = reinterpret_cast<const __nv_bfloat16*>(bias);
+  p.gate = reinterpret_cast<const __nv_bfloat16*>(gate);
+  p.C = reinterpret_cast<__nv_bfloat16*>(C);
+  p.ldc = ldc;
+  p.group_m = 16;
+  p.scale_a = scale_a;
+  p.scale_b = scale_b;
+  if (block_n == 256) return dispatch_epi<256, true>(epilogue, tmA, tmB, tmC, p, max_ctas, stream);
+  return dispatch_epi<128, true>(epilogue, tmA, tmB, tmC, p, max_ctas, stream);
 }
 
 }  // namespace b200

@@ -13,6 +13,8 @@
 #include "host_util.cuh"
 #include "ptx.cuh"
 
+#include <cuda_fp8.h>
+
 namespace b200 {
 
 constexpr int ROW_THREADS = 128;
@@ -28,6 +30,32 @@ __device__ __forceinline__ float block_sum_128(float v, float* red) {
   __syncthreads();
   return t;
 }
+
+__device__ __forceinline__ float block_max(float v, float* red, int nwarps) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  const int w = threadIdx.x >> 5;
+  if ((threadIdx.x & 31) == 0) red[w] = v;
+  __syncthreads();
+  float t = red[0];
+  for (int i = 1; i < nwarps; ++i) t = fmaxf(t, red[i]);
+  __syncthreads();
+  return t;
+}
+
+// 8 floats -> 8 e4m3 (round-to-nearest-even, saturate-to-finite), packed in 8 bytes
+__device__ __forceinline__ uint2 pack8_e4m3(const float* f) {
+  uint2 o;
+  o.x = (uint32_t)__nv_cvt_float2_to_fp8x2(make_float2(f[0], f[1]), __NV_SATFINITE, __NV_E4M3) |
+        ((uint32_t)__nv_cvt_float2_to_fp8x2(make_float2(f[2], f[3]), __NV_SATFINITE, __NV_E4M3) << 16);
+  o.y = (uint32_t)__nv_cvt_float2_to_fp8x2(make_float2(f[4], f[5]), __NV_SATFINITE, __NV_E4M3) |
+        ((uint32_t)__nv_cvt_float2_to_fp8x2(make_float2(f[6], f[7]), __NV_SATFINITE, __NV_E4M3) << 16);
+  return o;
+}
+
+// dynamic per-token scale of vLLM's scaled_fp8_quant(use_per_token_if_dynamic=True) (mm_weight.py:236-238):
+//   scale = max(absmax / 448, 1 / (448 * 512));  q = e4m3_rn_satfinite(x / scale)
+__device__ __forceinline__ float fp8_token_scale(float absmax) { return fmaxf(absmax / 448.0f, 1.0f / (448.0f * 512.0f)); }
 
 __device__ __forceinline__ void unpack8(const uint4& v, float* f) {
   f[0] = bf16_lo(v.x); f[1] = bf16_hi(v.x);
@@ -48,12 +76,12 @@ __device__ __forceinline__ uint4 pack8(const float* f) {
 // LayerNorm (eps, optional affine weight/bias) followed by optional AdaLN modulation  y = bf16(bf16(n * w1) + shift)
 // with w1 = bf16(1 + scale).  `scale` / `shift` are [D] bf16 vectors (one per block and pass).
 // ---------------------------------------------------------------------------------------------------------
-template <bool kAffine, bool kModulate>
+template <bool kAffine, bool kModulate, bool kFp8Out>
 __global__ void __launch_bounds__(ROW_THREADS)
 ln_modulate_kernel(const __nv_bfloat16* __restrict__ x, long long ldx, __nv_bfloat16* __restrict__ y, long long ldy,
                    const __nv_bfloat16* __restrict__ ln_w, const __nv_bfloat16* __restrict__ ln_b,
                    const __nv_bfloat16* __restrict__ scale, const __nv_bfloat16* __restrict__ shift, int D,
-                   float eps) {
+                   float eps, uint8_t* __restrict__ q8, long long ldq, float* __restrict__ q_scale) {
   __shared__ float red[4];
   const long long row = blockIdx.x;
   const int nvec = D >> 3;
@@ -88,6 +116,7 @@ ln_modulate_kernel(const __nv_bfloat16* __restrict__ x, long long ldx, __nv_bflo
   }
   const float rstd = rsqrtf(block_sum_128(sq, red) / (float)D + eps);
   uint4* yr = reinterpret_cast<uint4*>(y + row * ldy);
+  float amax = 0.f;
 #pragma unroll
   for (int i = 0; i < ROW_MAX_VEC; ++i) {
     const int v = threadIdx.x + i * ROW_THREADS;
@@ -113,17 +142,43 @@ ln_modulate_kernel(const __nv_bfloat16* __restrict__ x, long long ldx, __nv_bflo
           f[e] = bf16_round(bf16_round(f[e]) * w1) + sh[e];
         }
       }
-      yr[v] = pack8(f);
+      if constexpr (kFp8Out) {
+        raw[i] = pack8(f);   // the bf16 tensor the reference would hand to the quantiser
+        unpack8(raw[i], f);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) amax = fmaxf(amax, fabsf(f[e]));
+      } else {
+        yr[v] = pack8(f);
+      }
+    }
+  }
+  if constexpr (kFp8Out) {
+    const float sc = fp8_token_scale(block_max(amax, red, ROW_THREADS / 32));
+    if (threadIdx.x == 0) q_scale[row] = sc;
+    uint2* qr = reinterpret_cast<uint2*>(q8 + row * ldq);
+#pragma unroll
+    for (int i = 0; i < ROW_MAX_VEC; ++i) {
+      const int v = threadIdx.x + i * ROW_THREADS;
+      if (v < nvec) {
+        float f[8];
+        unpack8(raw[i], f);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) f[e] = f[e] / sc;
+        qr[v] = pack8_e4m3(f);
+      }
     }
   }
 }
 
-int ln_modulate(const void* x, long long ldx, void* y, long long ldy, const void* ln_w, const void* ln_b,
-                const void* scale, const void* shift, long long rows, int D, float eps, cudaStream_t stream) {
-  B200_CHECK_ARG(x && y, "b200_ln_modulate: null pointer");
+static int ln_modulate_impl(const void* x, long long ldx, void* y, long long ldy, const void* ln_w, const void* ln_b,
+                            const void* scale, const void* shift, long long rows, int D, float eps, void* q8, long long ldq,
+                            float* q_scale, cudaStream_t stream) {
+  const bool fp8 = q8 != nullptr;
+  B200_CHECK_ARG(x && (y || fp8), "b200_ln_modulate: null pointer");
   B200_CHECK_ARG(rows > 0 && D > 0 && D % 8 == 0 && D <= ROW_THREADS * ROW_MAX_VEC * 8,
                  "b200_ln_modulate: D=%d must be a multiple of 8 and <= %d", D, ROW_THREADS * ROW_MAX_VEC * 8);
-  B200_CHECK_ARG(ldx % 8 == 0 && ldy % 8 == 0 && ldx >= D && ldy >= D, "b200_ln_modulate: bad leading dimension");
+  B200_CHECK_ARG(ldx % 8 == 0 && ldx >= D && (fp8 ? (ldq % 8 == 0 && ldq >= D && q_scale) : (ldy % 8 == 0 && ldy >= D)),
+                 "b200_ln_modulate: bad leading dimension");
   B200_CHECK_ARG((ln_w == nullptr) == (ln_b == nullptr), "b200_ln_modulate: affine weight and bias go together");
   B200_CHECK_ARG((scale == nullptr) == (shift == nullptr), "b200_ln_modulate: scale and shift go together");
   const auto* xp = reinterpret_cast<const __nv_bfloat16*>(x);
@@ -132,11 +187,89 @@ int ln_modulate(const void* x, long long ldx, void* y, long long ldy, const void
   const auto* b = reinterpret_cast<const __nv_bfloat16*>(ln_b);
   const auto* sc = reinterpret_cast<const __nv_bfloat16*>(scale);
   const auto* sh = reinterpret_cast<const __nv_bfloat16*>(shift);
+  auto* q = reinterpret_cast<uint8_t*>(q8);
   dim3 grid((unsigned)rows);
-  if (w && sc) ln_modulate_kernel<true, true><<<grid, ROW_THREADS, 0, stream>>>(xp, ldx, yp, ldy, w, b, sc, sh, D, eps);
-  else if (w) ln_modulate_kernel<true, false><<<grid, ROW_THREADS, 0, stream>>>(xp, ldx, yp, ldy, w, b, sc, sh, D, eps);
-  else if (sc) ln_modulate_kernel<false, true><<<grid, ROW_THREADS, 0, stream>>>(xp, ldx, yp, ldy, w, b, sc, sh, D, eps);
-  else ln_modulate_kernel<false, false><<<grid, ROW_THREADS, 0, stream>>>(xp, ldx, yp, ldy, w, b, sc, sh, D, eps);
+#define B200_LN_LAUNCH(AFF, MOD, F8) \
+  ln_modulate_kernel<AFF, MOD, F8><<<grid, ROW_THREADS, 0, stream>>>(xp, ldx, yp, ldy, w, b, sc, sh, D, eps, q, ldq, q_scale)
+  if (fp8) {
+    if (w && sc) B200_LN_LAUNCH(true, true, true);
+    else if (w) B200_LN_LAUNCH(true, false, true);
+    else if (sc) B200_LN_LAUNCH(false, true, true);
+    else B200_LN_LAUNCH(false, false, true);
+  } else {
+    if (w && sc) B200_LN_LAUNCH(true, true, false);
+    else if (w) B200_LN_LAUNCH(true, false, false);
+    else if (sc) B200_LN_LAUNCH(false, true, false);
+    else B200_LN_LAUNCH(false, false, false);
+  }
+#undef B200_LN_LAUNCH
+  B200_CHECK_CUDA(cudaGetLastError());
+  return B200_OK;
+}
+
+int ln_modulate(const void* x, long long ldx, void* y, long long ldy, const void* ln_w, const void* ln_b,
+                const void* scale, const void* shift, long long rows, int D, float eps, cudaStream_t stream) {
+  return ln_modulate_impl(x, ldx, y, ldy, ln_w, ln_b, scale, shift, rows, D, eps, nullptr, 0, nullptr, stream);
+}
+
+int ln_modulate_fp8(const void* x, long long ldx, void* q8, long long ldq, float* q_scale, const void* ln_w,
+                    const void* ln_b, const void* scale, const void* shift, long long rows, int D, float eps,
+                    cudaStream_t stream) {
+  B200_CHECK_ARG(q8 && q_scale, "b200_ln_modulate_fp8: null output pointer");
+  return ln_modulate_impl(x, ldx, nullptr, 0, ln_w, ln_b, scale, shift, rows, D, eps, q8, ldq, q_scale, stream);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Dynamic per-token e4m3 quantisation of a bf16 [rows, D] tensor (act_quant_fp8_perchannel_sym_vllm, mm_weight.py:236-238).
+// 256 threads per row, row in registers: read once (2 B/elem), write once (1 B/elem + 4 B/row).
+// ---------------------------------------------------------------------------------------------------------
+constexpr int QUANT_THREADS = 256;
+constexpr int QUANT_MAX_VEC = 8;   // D <= 16384
+
+__global__ void __launch_bounds__(QUANT_THREADS)
+quant_fp8_kernel(const __nv_bfloat16* __restrict__ x, long long ldx, uint8_t* __restrict__ q8, long long ldq,
+                 float* __restrict__ q_scale, int D) {
+  __shared__ float red[QUANT_THREADS / 32];
+  const long long row = blockIdx.x;
+  const int nvec = D >> 3;
+  const uint4* xr = reinterpret_cast<const uint4*>(x + row * ldx);
+  uint4 raw[QUANT_MAX_VEC];
+  float amax = 0.f;
+#pragma unroll
+  for (int i = 0; i < QUANT_MAX_VEC; ++i) {
+    const int v = threadIdx.x + i * QUANT_THREADS;
+    if (v < nvec) {
+      raw[i] = xr[v];
+      float f[8];
+      unpack8(raw[i], f);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) amax = fmaxf(amax, fabsf(f[e]));
+    }
+  }
+  const float sc = fp8_token_scale(block_max(amax, red, QUANT_THREADS / 32));
+  if (threadIdx.x == 0) q_scale[row] = sc;
+  uint2* qr = reinterpret_cast<uint2*>(q8 + row * ldq);
+#pragma unroll
+  for (int i = 0; i < QUANT_MAX_VEC; ++i) {
+    const int v = threadIdx.x + i * QUANT_THREADS;
+    if (v < nvec) {
+      float f[8];
+      unpack8(raw[i], f);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) f[e] = f[e] / sc;
+      qr[v] = pack8_e4m3(f);
+    }
+  }
+}
+
+int quant_fp8_per_token(const void* x, long long ldx, void* q8, long long ldq, float* q_scale, long long rows, int D,
+                        cudaStream_t stream) {
+  B200_CHECK_ARG(x && q8 && q_scale, "b200_quant_fp8_per_token: null pointer");
+  B200_CHECK_ARG(rows > 0 && D > 0 && D % 8 == 0 && D <= QUANT_THREADS * QUANT_MAX_VEC * 8,
+                 "b200_quant_fp8_per_token: D=%d must be a multiple of 8 and <= %d", D, QUANT_THREADS * QUANT_MAX_VEC * 8);
+  B200_CHECK_ARG(ldx % 8 == 0 && ldx >= D && ldq % 8 == 0 && ldq >= D, "b200_quant_fp8_per_token: bad leading dimension");
+  quant_fp8_kernel<<<(unsigned)rows, QUANT_THREADS, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(x), ldx,
+                                                               reinterpret_cast<uint8_t*>(q8), ldq, q_scale, D);
   B200_CHECK_CUDA(cudaGetLastError());
   return B200_OK;
 }

@@ -100,6 +100,77 @@ class MMWeightB200(_WeightOp):
         return destination
 
 
+FP8_MM_KEY = "W-fp8-channel-sym-A-fp8-channel-sym-dynamic-B200"
+
+
+def quantize_weight_fp8_per_channel(w: torch.Tensor):
+    """Per-out-channel symmetric e4m3 weight quantisation — FloatQuantizer("e4m3", True, "per_channel").real_quant_tensor
+    (lightx2v/utils/quant_utils.py:41-53,149-161; same rule as tools/convert/converter.py:313-339):
+    scale[n] = clamp(absmax(w[n,:]), 1e-5) / 448;  q = round_to_nearest_e4m3(clip(w / scale, -448, 448))."""
+    wf = w.to(torch.float32)
+    absmax = wf.abs().amax(dim=-1, keepdim=True).clamp(min=1e-5)
+    scale = absmax / 448.0
+    q = torch.clip(wf / scale, -448.0, 448.0).to(torch.float8_e4m3fn)
+    return q, scale.to(torch.float32)
+
+
+@MM_WEIGHT_REGISTER(FP8_MM_KEY)
+class MMWeightFp8B200(_WeightOp):
+    """w8a8-fp8 linear (BASELINE config 3): e4m3 weight [N,K] + `weight_scale` [N,1] fp32 (the checkpoint contract of
+    tools/convert/converter.py:294-339 and MMWeightQuantTemplate.load_quantized, mm_weight.py:161-166), dynamic per-token e4m3
+    activations, `y = sx * (sw * (xq @ wq^T)) + b`.  Mirrors MMWeightWfp8channelAfp8channeldynamicVllm (mm_weight.py:287-319):
+    `config["weight_auto_quant"]` quantises a bf16 checkpoint at load, otherwise `<name>.weight` must already be e4m3 and
+    `<name>.weight_scale` present."""
+
+    _attrs = ("weight", "weight_scale", "bias")
+
+    def __init__(self, weight_name, bias_name, lazy_load=False, lazy_load_file=None):
+        self.weight_name = weight_name
+        self.bias_name = bias_name
+        self.weight_scale_name = weight_name.removesuffix(".weight") + ".weight_scale"
+        self.lazy_load = lazy_load
+        self.lazy_load_file = lazy_load_file
+        self.config = {}
+        self.weight = self.weight_scale = self.bias = None
+
+    def load(self, weight_dict):
+        w = weight_dict[self.weight_name]
+        if (self.config or {}).get("weight_auto_quant", False) or w.dtype != torch.float8_e4m3fn:
+            if w.dtype == torch.float8_e4m3fn:
+                raise lib.B200Error(f"{self.weight_name}: already e4m3 but weight_auto_quant requested")
+            q, sc = quantize_weight_fp8_per_channel(w)
+        else:
+            q, sc = w, weight_dict[self.weight_scale_name].float()
+        self.weight = q.contiguous().t()                       # [K,N] view, like the reference (weight_need_transpose)
+        self.weight_scale = sc.reshape(-1, 1).contiguous()
+        self.bias = weight_dict[self.bias_name] if self.bias_name is not None else None
+
+    def to_cuda(self, non_blocking=False):
+        self.weight = self.weight.t().cuda(non_blocking=non_blocking).t()
+        self.weight_scale = self.weight_scale.cuda(non_blocking=non_blocking)
+        if self.bias is not None:
+            self.bias = self.bias.cuda(non_blocking=non_blocking)
+
+    def to_cpu(self, non_blocking=False):
+        self.weight = self.weight.t().to("cpu", non_blocking=non_blocking).t()
+        self.weight_scale = self.weight_scale.to("cpu", non_blocking=non_blocking)
+        if self.bias is not None:
+            self.bias = self.bias.to("cpu", non_blocking=non_blocking)
+
+    def apply(self, input_tensor, *, out=None, epilogue: int = lib.EPI_BIAS, gate=None):
+        xq, sx = lib.quant_fp8_per_token(input_tensor)
+        return lib.gemm_fp8(xq, sx, self.weight.t(), self.weight_scale, self.bias, out=out, epilogue=epilogue, gate=gate)
+
+    def state_dict(self, destination=None):
+        if destination is None:
+            destination = {}
+        destination[self.weight_name] = self.weight.cpu().detach().clone().t().contiguous()
+        destination[self.weight_scale_name] = self.weight_scale.cpu().detach().clone()
+        if self.bias is not None:
+            destination[self.bias_name] = self.bias.cpu().detach().clone()
+        return destination
+
+
 class RMSWeightB200(_WeightOp):
     """Full-row RMSNorm with the reference's bf16 rounding points (rms_norm_weight.py:111-113)."""
 

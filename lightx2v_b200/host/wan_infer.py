@@ -50,11 +50,12 @@ def rope_cos_sin(grid_sizes, freqs: torch.Tensor, head_dim: int, rows: Optional[
 class _BlockCache:
     """Per-block derived tensors: concatenated QKV weight/bias, cached cross-attention text K/V."""
 
-    __slots__ = ("wqkv", "bqkv", "ctx_key", "ck", "cv", "ck_img", "cv_img")
+    __slots__ = ("wqkv", "bqkv", "sqkv", "ctx_key", "ck", "cv", "ck_img", "cv_img")
 
     def __init__(self):
         self.wqkv = None
         self.bqkv = None
+        self.sqkv = None
         self.ctx_key = None
         self.ck = self.cv = self.ck_img = self.cv_img = None
 
@@ -141,6 +142,49 @@ class WanTransformerInfer:
         w = mm.weight.t()
         return w if w.is_contiguous() else w.contiguous()
 
+    # ------------------------------------------------------------------ bf16 / w8a8-fp8 dispatch
+    @staticmethod
+    def _is_fp8(mm) -> bool:
+        return getattr(mm, "weight_scale", None) is not None
+
+    def _ln(self, x, fp8, name, **kw):
+        """LayerNorm(+modulate) into the bf16 scratch buffer, or (fp8 mode) straight into e4m3 + per-token scale."""
+        S, D = x.shape
+        if fp8:
+            q = self._buf8(name, (S, D), x.device)
+            sc = self._buff32(name + "_s", (S, 1), x.device)
+            return lib.ln_modulate_fp8(x, out=q, out_scale=sc, **kw)
+        return lib.ln_modulate(x, out=self._buf(name, (S, D), x.device), **kw)
+
+    def _linear(self, mm, a, *, w=None, b=None, ws=None, out=None, epilogue=lib.EPI_BIAS, gate=None, qname="q8"):
+        """y = epilogue(a @ W^T + b).  `a` is a bf16 tensor, or an (e4m3, scale) pair when the producer already quantised."""
+        w = self._nk(mm) if w is None else w
+        b = mm.bias if b is None and mm is not None else b
+        if mm is not None and self._is_fp8(mm) or ws is not None:
+            ws = mm.weight_scale if ws is None else ws
+            if not isinstance(a, tuple):
+                q = self._buf8(qname, tuple(a.shape), a.device)
+                sc = self._buff32(qname + "_s", (a.shape[0], 1), a.device)
+                a = lib.quant_fp8_per_token(a, out=q, scale=sc)
+            return lib.gemm_fp8(a[0], a[1], w, ws, b, out=out, epilogue=epilogue, gate=gate)
+        return lib.gemm_bf16(a, w, b, out=out, epilogue=epilogue, gate=gate)
+
+    def _buf8(self, name, shape, device):
+        key = (name, tuple(shape), str(device), "fp8")
+        t = self._bufs.get(key)
+        if t is None:
+            t = torch.empty(shape, dtype=lib.FP8, device=device)
+            self._bufs[key] = t
+        return t
+
+    def _buff32(self, name, shape, device):
+        key = (name, tuple(shape), str(device), "f32")
+        t = self._bufs.get(key)
+        if t is None:
+            t = torch.empty(shape, dtype=torch.float32, device=device)
+            self._bufs[key] = t
+        return t
+
     # ------------------------------------------------------------------ phases
     def infer_self_attn(self, weights, grid_sizes, x, seq_lens, freqs, shift_msa, scale_msa, gate_msa=None):
         """transformer_infer.py:321-396 (+ the gated residual of :402 when gate_msa is given: returns the updated x;
@@ -148,29 +192,30 @@ class WanTransformerInfer:
         S, D = x.shape
         dev = x.device
         c = self._cache(weights)
+        fp8 = self._is_fp8(weights.self_attn_q)
         if c.wqkv is None:
             c.wqkv = torch.cat([self._nk(weights.self_attn_q), self._nk(weights.self_attn_k), self._nk(weights.self_attn_v)], dim=0).contiguous()
             c.bqkv = torch.cat([weights.self_attn_q.bias, weights.self_attn_k.bias, weights.self_attn_v.bias]).contiguous()
-        n1 = self._buf("a", (S, D), dev)
-        lib.ln_modulate(x, scale=scale_msa, shift=shift_msa, eps=weights.norm1.eps, out=n1)
+            if fp8:
+                c.sqkv = torch.cat([m.weight_scale.reshape(-1) for m in (weights.self_attn_q, weights.self_attn_k, weights.self_attn_v)]).contiguous()
+        n1 = self._ln(x, fp8, "a", scale=scale_msa, shift=shift_msa, eps=weights.norm1.eps)
         qkv = self._buf("qkv", (S, 3 * D), dev)
-        lib.gemm_bf16(n1, c.wqkv, c.bqkv, out=qkv)
+        self._linear(None, n1, w=c.wqkv, b=c.bqkv, ws=c.sqkv, out=qkv)
         q, k, v = qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:]
         cs = self._rope_table(grid_sizes, freqs, S, dev)
         lib.rms_rope_(q, weights.self_attn_norm_q.weight, k, weights.self_attn_norm_k.weight, eps=weights.self_attn_norm_q.eps,
                       cos_sin=cs, rope_rows=min(S, cs.shape[0]))
         H, d = self.num_heads, self.head_dim
         q3, k3, v3 = (t.unflatten(1, (H, d)) for t in (q, k, v))
-        attn = n1.view(S, H, d)          # n1 is dead after the QKV GEMM: reuse it for the attention output
+        attn = self._buf("a", (S, D), dev).view(S, H, d)   # the LN scratch is dead after the QKV GEMM: reuse it for the attention output
         if self.parallel_attention is None:
             lib.fmha(q3, k3, v3, out=attn)
         else:
             attn = self.parallel_attention(q=q3, k=k3, v=v3, out=attn)
         attn2 = attn.reshape(S, D)
         if gate_msa is None:
-            return lib.gemm_bf16(attn2, self._nk(weights.self_attn_o), weights.self_attn_o.bias)
-        lib.gemm_bf16(attn2, self._nk(weights.self_attn_o), weights.self_attn_o.bias, out=x,
-                      epilogue=lib.EPI_GATE_RESIDUAL, gate=gate_msa)
+            return self._linear(weights.self_attn_o, attn2)
+        self._linear(weights.self_attn_o, attn2, out=x, epilogue=lib.EPI_GATE_RESIDUAL, gate=gate_msa)
         return x
 
     def _context_kv(self, weights, context, c: _BlockCache):
@@ -182,14 +227,14 @@ class WanTransformerInfer:
             context_img, ctx = context[:257], context[257:]
         else:
             context_img, ctx = None, context
-        ck = lib.gemm_bf16(ctx, self._nk(weights.cross_attn_k), weights.cross_attn_k.bias)
+        ck = self._linear(weights.cross_attn_k, ctx.contiguous(), qname="ctx8")
         lib.rms_rope_(ck, weights.cross_attn_norm_k.weight, eps=weights.cross_attn_norm_k.eps)
-        cv = lib.gemm_bf16(ctx, self._nk(weights.cross_attn_v), weights.cross_attn_v.bias)
+        cv = self._linear(weights.cross_attn_v, ctx.contiguous(), qname="ctx8")
         c.ck, c.cv = ck.view(-1, H, d), cv.view(-1, H, d)
         if context_img is not None:
-            ki = lib.gemm_bf16(context_img, self._nk(weights.cross_attn_k_img), weights.cross_attn_k_img.bias)
+            ki = self._linear(weights.cross_attn_k_img, context_img.contiguous(), qname="img8")
             lib.rms_rope_(ki, weights.cross_attn_norm_k_img.weight, eps=weights.cross_attn_norm_k_img.eps)
-            vi = lib.gemm_bf16(context_img, self._nk(weights.cross_attn_v_img), weights.cross_attn_v_img.bias)
+            vi = self._linear(weights.cross_attn_v_img, context_img.contiguous(), qname="img8")
             c.ck_img, c.cv_img = ki.view(-1, H, d), vi.view(-1, H, d)
         c.ctx_key = key
 
@@ -203,18 +248,18 @@ class WanTransformerInfer:
         if y_out is not None:
             x.add_(y_out * gate_msa)
         c = self._cache(weights)
-        n3 = self._buf("a", (S, D), dev)
-        lib.ln_modulate(x, weight=weights.norm3.weight, bias=weights.norm3.bias, eps=weights.norm3.eps, out=n3)
+        fp8 = self._is_fp8(weights.cross_attn_q)
+        n3 = self._ln(x, fp8, "a", weight=weights.norm3.weight, bias=weights.norm3.bias, eps=weights.norm3.eps)
         cq = self._buf("b", (S, D), dev)
-        lib.gemm_bf16(n3, self._nk(weights.cross_attn_q), weights.cross_attn_q.bias, out=cq)
+        self._linear(weights.cross_attn_q, n3, out=cq)
         lib.rms_rope_(cq, weights.cross_attn_norm_q.weight, eps=weights.cross_attn_norm_q.eps)
         self._context_kv(weights, context, c)
-        attn = n3.view(S, H, d)
+        attn = self._buf("a", (S, D), dev).view(S, H, d)
         lib.fmha(cq.view(S, H, d), c.ck, c.cv, out=attn)
         if self.task == "i2v":
             img = lib.fmha(cq.view(S, H, d), c.ck_img, c.cv_img, out=self._buf("c", (S, H, d), dev))
             attn.add_(img)                                                      # :454 (two softmaxes, summed in bf16)
-        lib.gemm_bf16(attn.reshape(S, D), self._nk(weights.cross_attn_o), weights.cross_attn_o.bias, out=x, epilogue=lib.EPI_RESIDUAL)
+        self._linear(weights.cross_attn_o, attn.reshape(S, D), out=x, epilogue=lib.EPI_RESIDUAL)
         return x, None
 
     def infer_ffn(self, weights, x, attn_out, c_shift_msa, c_scale_msa, c_gate_msa=None):
@@ -223,14 +268,14 @@ class WanTransformerInfer:
         dev = x.device
         if attn_out is not None:
             x.add_(attn_out)
-        n2 = self._buf("a", (S, D), dev)
-        lib.ln_modulate(x, scale=c_scale_msa, shift=c_shift_msa, eps=weights.norm2.eps, out=n2)
+        fp8 = self._is_fp8(weights.ffn_0)
+        n2 = self._ln(x, fp8, "a", scale=c_scale_msa, shift=c_shift_msa, eps=weights.norm2.eps)
         w0 = self._nk(weights.ffn_0)
         hidden = self._buf("h", (S, w0.shape[0]), dev)
-        lib.gemm_bf16(n2, w0, weights.ffn_0.bias, out=hidden, epilogue=lib.EPI_BIAS_GELU)
+        self._linear(weights.ffn_0, n2, w=w0, out=hidden, epilogue=lib.EPI_BIAS_GELU)
         if c_gate_msa is None:
-            return lib.gemm_bf16(hidden, self._nk(weights.ffn_2), weights.ffn_2.bias)
-        lib.gemm_bf16(hidden, self._nk(weights.ffn_2), weights.ffn_2.bias, out=x, epilogue=lib.EPI_GATE_RESIDUAL, gate=c_gate_msa)
+            return self._linear(weights.ffn_2, hidden, qname="h8")
+        self._linear(weights.ffn_2, hidden, out=x, epilogue=lib.EPI_GATE_RESIDUAL, gate=c_gate_msa, qname="h8")
         return None
 
     def post_process(self, x, y, c_gate_msa):

@@ -25,6 +25,9 @@ SIGNATURES = {
     "b200_ln_modulate": (_i32, [_ptr, _i64, _ptr, _i64, _ptr, _ptr, _ptr, _ptr, _i64, _i32, _f32, _ptr]),
     "b200_rms_rope": (_i32, [_ptr, _i64, _ptr, _ptr, _i64, _ptr, _i64, _i32, _f32, _ptr, _i64, _i64, _ptr]),
     "b200_fmha_fwd_d128": (_i32, [_ptr, _i64, _ptr, _i64, _ptr, _i64, _ptr, _i64, _i64, _i64, _i32, _f32, _ptr]),
+    "b200_gemm_fp8": (_i32, [_ptr, _i64, _ptr, _i64, _ptr, _i64, _ptr, _ptr, _ptr, _ptr, _i64, _i64, _i64, _i32, _i32, _i32, _ptr]),
+    "b200_quant_fp8_per_token": (_i32, [_ptr, _i64, _ptr, _i64, _ptr, _i64, _i32, _ptr]),
+    "b200_ln_modulate_fp8": (_i32, [_ptr, _i64, _ptr, _i64, _ptr, _ptr, _ptr, _ptr, _ptr, _i64, _i32, _f32, _ptr]),
 }
 
 EPI_BIAS, EPI_BIAS_GELU, EPI_GATE_RESIDUAL, EPI_RESIDUAL = 0, 1, 2, 3
@@ -142,4 +145,56 @@ def fmha(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, *, softmax_scale: Op
     rc = load().b200_fmha_fwd_d128(q.data_ptr(), q.stride(0), k.data_ptr(), k.stride(0), v.data_ptr(), v.stride(0),
                                    out.data_ptr(), out.stride(0), sq, sk, H, scale, _stream())
     _check(rc, "b200_fmha_fwd_d128")
+    return out
+
+
+# ---------------------------------------------------------------------------------------------------------------- fp8 (w8a8)
+FP8 = torch.float8_e4m3fn
+
+
+def quant_fp8_per_token(x: torch.Tensor, out: Optional[torch.Tensor] = None, scale: Optional[torch.Tensor] = None):
+    """bf16 [rows, D] -> (e4m3 [rows, D], fp32 scale [rows, 1]), dynamic per-token (mm_weight.py:236-238)."""
+    _req(x, "x")
+    rows, D = x.shape
+    if out is None:
+        out = torch.empty((rows, D), dtype=FP8, device=x.device)
+    if scale is None:
+        scale = torch.empty((rows, 1), dtype=torch.float32, device=x.device)
+    rc = load().b200_quant_fp8_per_token(x.data_ptr(), x.stride(0), out.data_ptr(), out.stride(0), scale.data_ptr(), rows, D, _stream())
+    _check(rc, "b200_quant_fp8_per_token")
+    return out, scale
+
+
+def ln_modulate_fp8(x: torch.Tensor, *, weight=None, bias=None, scale=None, shift=None, eps: float = 1e-6,
+                    out: Optional[torch.Tensor] = None, out_scale: Optional[torch.Tensor] = None):
+    _req(x, "x")
+    rows, D = x.shape
+    if out is None:
+        out = torch.empty((rows, D), dtype=FP8, device=x.device)
+    if out_scale is None:
+        out_scale = torch.empty((rows, 1), dtype=torch.float32, device=x.device)
+    rc = load().b200_ln_modulate_fp8(x.data_ptr(), x.stride(0), out.data_ptr(), out.stride(0), out_scale.data_ptr(), _p(weight), _p(bias),
+                                     _p(scale), _p(shift), rows, D, eps, _stream())
+    _check(rc, "b200_ln_modulate_fp8")
+    return out, out_scale
+
+
+def gemm_fp8(a_q: torch.Tensor, a_scale: torch.Tensor, w_q: torch.Tensor, w_scale: torch.Tensor, bias: Optional[torch.Tensor] = None, *,
+             out: Optional[torch.Tensor] = None, epilogue: int = EPI_BIAS, gate: Optional[torch.Tensor] = None, block_n: int = 0,
+             max_ctas: int = 0) -> torch.Tensor:
+    """out[M,N] bf16 = epilogue(a_scale * (w_scale * (a_q[M,K] @ w_q[N,K]^T)) + bias); a_q, w_q e4m3."""
+    _req(a_q, "a_q", FP8); _req(w_q, "w_q", FP8)
+    _req(a_scale, "a_scale", torch.float32); _req(w_scale, "w_scale", torch.float32)
+    M, K = a_q.shape
+    N, K2 = w_q.shape
+    if K != K2 or a_scale.numel() != M or w_scale.numel() != N:
+        raise B200Error(f"gemm_fp8: shape mismatch a{tuple(a_q.shape)} w{tuple(w_q.shape)} sa{tuple(a_scale.shape)} sw{tuple(w_scale.shape)}")
+    if out is None:
+        if epilogue in (EPI_GATE_RESIDUAL, EPI_RESIDUAL):
+            raise B200Error("gemm_fp8: residual epilogues need out= (the residual stream, updated in place)")
+        out = torch.empty((M, N), dtype=torch.bfloat16, device=a_q.device)
+    _req(out, "out")
+    rc = load().b200_gemm_fp8(a_q.data_ptr(), a_q.stride(0), w_q.data_ptr(), w_q.stride(0), out.data_ptr(), out.stride(0),
+                              a_scale.data_ptr(), w_scale.data_ptr(), _p(bias), _p(gate), M, N, K, epilogue, block_n, max_ctas, _stream())
+    _check(rc, "b200_gemm_fp8")
     return out

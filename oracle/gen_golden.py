@@ -123,5 +123,65 @@ def main():
               os.path.getsize(os.path.join(GOLD, name + ".safetensors")))
 
 
+def gen_scheduler_fixture():
+    """Real WanScheduler (lightx2v/models/schedulers/wan/scheduler.py) driven for 8 of 20 steps on CPU with seeded pseudo
+    model outputs; pins lightx2v_b200/host/wan_scheduler.py (tests/test_host_cpu.py)."""
+    from safetensors.torch import save_file
+
+    from lightx2v.models.schedulers.wan.scheduler import WanScheduler
+
+    cfg = Cfg(infer_steps=20, target_video_length=17, sample_shift=5.0, seed=42, task="t2v", target_shape=(16, 3, 8, 8), patch_size=(1, 2, 2))
+    sch = WanScheduler(cfg)
+    sch.device = torch.device("cpu")
+    sch.prepare()
+    g = torch.Generator().manual_seed(11)
+    tensors = {"latents_0": sch.latents.clone(), "timesteps": sch.timesteps.clone(), "sigmas": sch.sigmas.clone()}
+    for i in range(8):
+        sch.step_pre(i)
+        tensors[f"latents_pre_{i}"] = sch.latents.clone()
+        sch.noise_pred = torch.randn(sch.latents.shape, generator=g)
+        tensors[f"noise_pred_{i}"] = sch.noise_pred.clone()
+        sch.step_post()
+        tensors[f"latents_post_{i}"] = sch.latents.clone()
+    save_file({k: v.contiguous() for k, v in tensors.items()}, os.path.join(GOLD, "wan_scheduler_unipc.safetensors"),
+              metadata={"infer_steps": "20", "sample_shift": "5.0", "seed": "42", "generator": "oracle/gen_golden.py:gen_scheduler_fixture"})
+    print("wan_scheduler_unipc", os.path.getsize(os.path.join(GOLD, "wan_scheduler_unipc.safetensors")))
+
+
+def gen_vae_fixture():
+    """Real WanVAE_ (lightx2v/models/video_encoders/hf/wan/vae.py) decoder, seeded synthetic weights loaded through its own
+    state_dict, decode of a [16, 3, 8, 8] latent -> [1, 3, 9, 64, 64]; pins oracle/vae_oracle.py."""
+    from safetensors.torch import save_file
+
+    from lightx2v.models.video_encoders.hf.wan.vae import WanVAE_
+
+    from oracle import vae_oracle as V
+
+    W = V.synth_vae_weights(seed=0)
+    model = WanVAE_(dim=96, z_dim=16, dim_mult=[1, 2, 4, 4], num_res_blocks=2, attn_scales=[], temperal_downsample=[False, True, True], dropout=0.0).eval()
+    res = model.load_state_dict(W, strict=False)
+    assert not res.unexpected_keys, res.unexpected_keys
+    assert all(k.startswith("encoder.") or k.startswith("conv1.") for k in res.missing_keys), res.missing_keys
+    g = torch.Generator().manual_seed(5)
+    zs = torch.randn(16, 3, 8, 8, generator=g)
+    scale = [torch.tensor(V.MEAN), 1.0 / torch.tensor(V.STD)]
+    with torch.no_grad():
+        out = model.decode(zs.unsqueeze(0), scale).float().clamp_(-1, 1)
+    save_file({"zs": zs, "images": out.contiguous()}, os.path.join(GOLD, "wan_vae_decode_small.safetensors"),
+              metadata={"weights_seed": "0", "generator": "oracle/gen_golden.py:gen_vae_fixture", "reference": "ModelTC/lightx2v@0591c35e"})
+    print("wan_vae_decode_small", tuple(out.shape), "absmax", float(out.abs().max()), "frac clamped", float((out.abs() >= 1).float().mean()))
+
+
 if __name__ == "__main__":
-    main()
+    if os.environ.get("GOLDEN_ONLY", "") == "vae":
+        install_shims()
+        os.makedirs(GOLD, exist_ok=True)
+        gen_vae_fixture()
+    elif os.environ.get("GOLDEN_ONLY", "") == "scheduler":
+        install_shims()
+        os.makedirs(GOLD, exist_ok=True)
+        gen_scheduler_fixture()
+    else:
+        main()
+        gen_scheduler_fixture()
+        gen_vae_fixture()

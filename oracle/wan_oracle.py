@@ -31,6 +31,64 @@ def mm_apply(x: torch.Tensor, weight_nk: torch.Tensor, bias: Optional[torch.Tens
     return torch.addmm(bias, x, weight_nk.t())
 
 
+# ---- w8a8-fp8 linear (BASELINE config 3) ------------------------------------------------------------------------
+def fp8_weight_quant(w: torch.Tensor):
+    """FloatQuantizer("e4m3", True, "per_channel").real_quant_tensor — utils/quant_utils.py:41-53 (absmax.clamp(1e-5)/qmax),
+    :149-161 (clip to +-448, round to nearest e4m3); used by load_fp8_perchannel_sym, mm_weight.py:167-183."""
+    wf = w.to(torch.float32)
+    scale = wf.abs().amax(dim=-1, keepdim=True).clamp(min=1e-5) / 448.0
+    q = torch.clip(wf / scale, -448.0, 448.0).to(torch.float8_e4m3fn)
+    return q, scale
+
+
+def fp8_act_quant(x: torch.Tensor):
+    """vLLM ops.scaled_fp8_quant(x, None, scale_ub=None, use_per_token_if_dynamic=True) — mm_weight.py:236-238.
+    vLLM is a third-party dependency absent from /root/reference (docs pin 0.9.2; the image has 0.22): published algorithm of
+    its dynamic_per_token_scaled_fp8_quant kernel: scale = max(absmax/448, 1/(448*512)); q = sat_e4m3_rn(x / scale)."""
+    xf = x.to(torch.float32)
+    # true fp32 division (a tensor divisor: torch turns `tensor / python_scalar` into a multiply by the reciprocal on CUDA)
+    scale = torch.div(xf.abs().amax(dim=-1, keepdim=True), torch.full((), 448.0, device=xf.device)).clamp(min=1.0 / (448.0 * 512.0))
+    q = torch.clip(xf / scale, -448.0, 448.0).to(torch.float8_e4m3fn)
+    return q, scale
+
+
+def mm_fp8_apply(x: torch.Tensor, wq: torch.Tensor, wscale: torch.Tensor, bias: Optional[torch.Tensor]) -> torch.Tensor:
+    """MMWeightWfp8channelAfp8channeldynamicVllm.apply — mm_weight.py:304-319: act quant, then cutlass_scaled_mm:
+    out = a_scale * (b_scale * (xq @ wq^T)) + bias in fp32, rounded once to bf16."""
+    xq, sx = fp8_act_quant(x)
+    acc = xq.to(torch.float32) @ wq.to(torch.float32).t()
+    y = sx * (wscale.reshape(1, -1) * acc)
+    if bias is not None:
+        y = y + bias.to(torch.float32)
+    return y.to(torch.bfloat16)
+
+
+def mm_named(W: Dict[str, torch.Tensor], name: str, x: torch.Tensor) -> torch.Tensor:
+    """Linear `name` of a checkpoint-named dict: bf16 MMWeight, or the w8a8-fp8 class when `<name>.weight_scale` is present
+    (the reference picks the class from mm_config.mm_type, transformer_weights.py:20-23; the quantised checkpoint carries the scales)."""
+    if name + ".weight_scale" in W:
+        return mm_fp8_apply(x, W[name + ".weight"], W[name + ".weight_scale"], W.get(name + ".bias"))
+    return mm_apply(x, W[name + ".weight"], W.get(name + ".bias"))
+
+
+def quantize_checkpoint_fp8(W: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
+    """Offline w8a8 conversion of the block linears (tools/convert/converter.py:294-407): `<name>.weight` -> e4m3 + `<name>.weight_scale`."""
+    out = dict(W)
+    for k, v in W.items():
+        if k.endswith(".weight") and v.dim() == 2 and ("attn." in k or "ffn." in k) and "norm" not in k:
+            q, s = fp8_weight_quant(v)
+            out[k] = q
+            out[k[: -len(".weight")] + ".weight_scale"] = s
+    return out
+
+
+def psnr(got: torch.Tensor, ref: torch.Tensor) -> float:
+    """PSNR in dB with the reference's peak as signal (north_star: fp8 / nvfp4 paths report PSNR vs the bf16 reference)."""
+    got, ref = got.float(), ref.float()
+    mse = (got - ref).pow(2).mean().clamp(min=1e-30)
+    return float(10.0 * torch.log10(ref.abs().max().pow(2) / mse))
+
+
 def rms_apply(x: torch.Tensor, weight: torch.Tensor, eps: float = 1e-6) -> torch.Tensor:
     """RMSWeightSgl.apply, bf16 fallback taken when sgl_kernel is absent — common/ops/norm/rms_norm_weight.py:109-113."""
     x = x * torch.rsqrt(x.pow(2).mean(-1, keepdim=True) + eps)
@@ -128,16 +186,16 @@ def infer_self_attn(W, pre, x, freqs_i, shift_msa, scale_msa, num_heads, attn="t
     s, n = norm1_out.shape[0], num_heads
     d = norm1_out.shape[1] // n
     sa = pre + "self_attn."
-    q = rms_apply(mm_apply(norm1_out, W[sa + "q.weight"], W[sa + "q.bias"]), W[sa + "norm_q.weight"]).view(s, n, d)   # :341
-    k = rms_apply(mm_apply(norm1_out, W[sa + "k.weight"], W[sa + "k.bias"]), W[sa + "norm_k.weight"]).view(s, n, d)   # :342
-    v = mm_apply(norm1_out, W[sa + "v.weight"], W[sa + "v.bias"]).view(s, n, d)                                       # :343
+    q = rms_apply(mm_named(W, sa + "q", norm1_out), W[sa + "norm_q.weight"]).view(s, n, d)   # :341
+    k = rms_apply(mm_named(W, sa + "k", norm1_out), W[sa + "norm_k.weight"]).view(s, n, d)   # :342
+    v = mm_named(W, sa + "v", norm1_out).view(s, n, d)                                       # :343
     q = apply_rotary_emb(q, freqs_i)                                     # :358
     k = apply_rotary_emb(k, freqs_i)                                     # :359
     if parallel_attention is None:
         attn_out = attn_apply(q, k, v, attn)                             # :369-379
     else:
         attn_out = parallel_attention(q, k, v)                           # :381-388
-    return mm_apply(attn_out, W[sa + "o.weight"], W[sa + "o.bias"])      # :390
+    return mm_named(W, sa + "o", attn_out)      # :390
 
 
 def infer_cross_attn(W, pre, x, context, y_out, gate_msa, num_heads, task="t2v", attn="torch_sdpa"):
@@ -149,16 +207,16 @@ def infer_cross_attn(W, pre, x, context, y_out, gate_msa, num_heads, task="t2v",
         context_img, context = context[:257], context[257:]             # :405-407
     n = num_heads
     d = x.shape[1] // n
-    q = rms_apply(mm_apply(norm3_out, W[ca + "q.weight"], W[ca + "q.bias"]), W[ca + "norm_q.weight"]).view(-1, n, d)  # :418
-    k = rms_apply(mm_apply(context, W[ca + "k.weight"], W[ca + "k.bias"]), W[ca + "norm_k.weight"]).view(-1, n, d)    # :419
-    v = mm_apply(context, W[ca + "v.weight"], W[ca + "v.bias"]).view(-1, n, d)                                        # :420
+    q = rms_apply(mm_named(W, ca + "q", norm3_out), W[ca + "norm_q.weight"]).view(-1, n, d)  # :418
+    k = rms_apply(mm_named(W, ca + "k", context), W[ca + "norm_k.weight"]).view(-1, n, d)    # :419
+    v = mm_named(W, ca + "v", context).view(-1, n, d)                                        # :420
     attn_out = attn_apply(q, k, v, attn)                                 # :425-434
     if task == "i2v":
-        k_img = rms_apply(mm_apply(context_img, W[ca + "k_img.weight"], W[ca + "k_img.bias"]), W[ca + "norm_k_img.weight"]).view(-1, n, d)
-        v_img = mm_apply(context_img, W[ca + "v_img.weight"], W[ca + "v_img.bias"]).view(-1, n, d)
+        k_img = rms_apply(mm_named(W, ca + "k_img", context_img), W[ca + "norm_k_img.weight"]).view(-1, n, d)
+        v_img = mm_named(W, ca + "v_img", context_img).view(-1, n, d)
         attn_out = attn_out.clone() if not attn_out.is_contiguous() else attn_out
         attn_out.add_(attn_apply(q, k_img, v_img, attn))                 # :436-454
-    attn_out = mm_apply(attn_out, W[ca + "o.weight"], W[ca + "o.bias"])  # :460
+    attn_out = mm_named(W, ca + "o", attn_out)  # :460
     return x, attn_out
 
 
@@ -169,9 +227,9 @@ def infer_ffn(W, pre, x, attn_out, c_shift_msa, c_scale_msa):
     norm2_bias = c_shift_msa.squeeze(0)
     norm2_out = ln_apply(x)                                              # :481
     norm2_out.mul_(norm2_weight).add_(norm2_bias)                        # :484
-    y = mm_apply(norm2_out, W[pre + "ffn.0.weight"], W[pre + "ffn.0.bias"])   # :488
+    y = mm_named(W, pre + "ffn.0", norm2_out)   # :488
     y = F.gelu(y, approximate="tanh")                                    # :492
-    return mm_apply(y, W[pre + "ffn.2.weight"], W[pre + "ffn.2.bias"])   # :495
+    return mm_named(W, pre + "ffn.2", y)   # :495
 
 
 def post_process(x, y, c_gate_msa):

@@ -136,3 +136,26 @@ def test_fmha_op_segment_bounds():
     assert FmhaWeightB200._bounds(None, 7) == [0, 7]
     assert FmhaWeightB200._bounds(torch.tensor([0, 5, 9], dtype=torch.int32), 9) == [0, 5, 9]
     assert FmhaWeightB200._bounds([0, 3], 3) == [0, 3]
+
+
+def test_unipc_scheduler_matches_reference_fixture(golden_dir):
+    """host/wan_scheduler.py vs the REAL WanScheduler run in the build container (oracle/gen_golden.py:gen_scheduler_fixture)."""
+    from safetensors import safe_open
+
+    from lightx2v_b200.host.wan_scheduler import WanScheduler
+
+    with safe_open(os.path.join(golden_dir, "wan_scheduler_unipc.safetensors"), framework="pt") as f:
+        T = {k: f.get_tensor(k) for k in f.keys()}
+    cfg = dict(infer_steps=20, sample_shift=5.0, seed=42, target_shape=(16, 3, 8, 8), patch_size=(1, 2, 2))
+    sch = WanScheduler(cfg, device="cpu")
+    sch.prepare()
+    assert torch.equal(sch.latents, T["latents_0"])
+    assert torch.equal(sch.timesteps, T["timesteps"]) and torch.equal(sch.sigmas, T["sigmas"])
+    for i in range(8):
+        sch.step_pre(i)
+        assert torch.equal(sch.latents, T[f"latents_pre_{i}"])
+        sch.noise_pred = T[f"noise_pred_{i}"]
+        sch.step_post()
+        ref = T[f"latents_post_{i}"]
+        assert sch.latents.dtype == ref.dtype
+        assert torch.allclose(sch.latents, ref, rtol=1e-5, atol=1e-5), (i, (sch.latents - ref).abs().max())

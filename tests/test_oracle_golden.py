@@ -56,3 +56,17 @@ def test_block_flops_matches_survey():
     # 163.1 TFLOP per block at 14B / 720p
     fl = O.block_flops(75600, 5120, 13824)
     assert abs(fl / 1e12 - 163.1) < 0.2
+
+
+def test_vae_oracle_matches_reference_fixture(golden_dir):
+    """oracle/vae_oracle.py vs the REAL WanVAE_.decode (per-frame causal-cache loop), bit for bit."""
+    from oracle import vae_oracle as V
+
+    T, _ = _load(os.path.join(golden_dir, "wan_vae_decode_small.safetensors"))
+    out = V.vae_decode(V.synth_vae_weights(0), T["zs"])
+    assert out.shape == (1, 3, 9, 64, 64)
+    # fp32 convolutions: oneDNN's summation order depends on thread count / primitive cache, so exact equality holds only
+    # run-to-run in the same process state; tolerance 2e-5 absolute on outputs in [-1, 1] (observed: 0 .. 4e-6)
+    err = (out - T["images"]).abs().max().item()
+    assert err <= 2e-5, err
+    assert V.count_causal_convs(V.decoder_layout()[1]) == 33          # SURVEY.md §8c: 33 CausalConv3d in the decoder

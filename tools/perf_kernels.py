@@ -1,0 +1,45 @@
+#!/usr/bin/env python
+"""Kernel-level timing sweeps (one process per env setting). Usage: python tools/perf_kernels.py fmha|gemm"""
+import json, os, subprocess, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+def child(kind):
+    import torch
+    from lightx2v_b200 import lib
+    from tools.bringup import _time_cuda
+    if kind == "fmha":
+        for (S, H) in ((75600, 40),):
+            q = torch.randn(S, H, 128, device="cuda").bfloat16(); k = torch.randn(S, H, 128, device="cuda").bfloat16(); v = torch.randn(S, H, 128, device="cuda").bfloat16()
+            o = torch.empty_like(q)
+            ms = _time_cuda(lambda: lib.fmha(q, k, v, out=o), iters=3, warmup=1)
+            print(json.dumps({"case": f"fmha_S{S}_H{H}", "env": os.environ.get("B200_FMHA_POLY"), "ms": ms, "tflops": 4 * S * S * H * 128 / ms / 1e9}))
+            ref = torch.nn.functional.scaled_dot_product_attention(q[:2048].float().transpose(0, 1), k[:4096].float().transpose(0, 1), v[:4096].float().transpose(0, 1)).transpose(0, 1)
+            got = lib.fmha(q[:2048], k[:4096], v[:4096])
+            print(json.dumps({"case": "fmha_err", "env": os.environ.get("B200_FMHA_POLY"), "max_abs_err": float((got.float() - ref).abs().max())}))
+    elif kind == "gemm8":
+        for (M, N, K) in ((75600, 5120, 5120), (75600, 13824, 5120), (75600, 5120, 13824), (75600, 15360, 5120)):
+            a = torch.randn(M, K, device="cuda").bfloat16(); w = (torch.randn(N, K, device="cuda") * 0.05).bfloat16(); b = torch.randn(N, device="cuda").bfloat16()
+            o = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+            aq, sa = lib.quant_fp8_per_token(a)
+            wq, sw = lib.quant_fp8_per_token(w)
+            ms = _time_cuda(lambda: lib.gemm_fp8(aq, sa, wq, sw, b, out=o))
+            print(json.dumps({"case": f"gemm_fp8_{M}x{N}x{K}", "ms": ms, "tflops": 2 * M * N * K / ms / 1e9}))
+            ms = _time_cuda(lambda: lib.quant_fp8_per_token(a, out=aq, scale=sa))
+            print(json.dumps({"case": f"quant_fp8_{M}x{K}", "ms": ms, "gbs": M * K * 3 / ms / 1e6}))
+    else:
+        for (M, N, K) in ((75600, 5120, 5120), (75600, 13824, 5120), (75600, 5120, 13824), (75600, 15360, 5120)):
+            a = torch.randn(M, K, device="cuda").bfloat16(); w = (torch.randn(N, K, device="cuda") * 0.05).bfloat16(); b = torch.randn(N, device="cuda").bfloat16()
+            o = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+            ms = _time_cuda(lambda: lib.gemm_bf16(a, w, b, out=o))
+            print(json.dumps({"case": f"gemm_{M}x{N}x{K}", "env": os.environ.get("B200_GEMM_GROUP_M"), "ms": ms, "tflops": 2 * M * N * K / ms / 1e9}))
+
+if __name__ == "__main__":
+    if len(sys.argv) > 2:
+        child(sys.argv[1])
+    else:
+        kind = sys.argv[1]
+        var, vals = {"fmha": ("B200_FMHA_POLY", ["0", "1", "2"]), "gemm": ("B200_GEMM_GROUP_M", ["16"]), "gemm8": ("B200_X", ["0"])}[kind]
+        for v in vals:
+            env = dict(os.environ); env[var] = v
+            subprocess.run([sys.executable, os.path.abspath(__file__), kind, "child"], env=env, cwd=ROOT)
