@@ -266,6 +266,11 @@ def run_ours(args):
             "clocks": clk,
             "roofline": roof,
         }
+        if args.vae and world == 1:
+            del model, W
+            sched.latents = None
+            torch.cuda.empty_cache()
+            out["vae_decode"] = vae_decode_bench(cfg, dev, with_reference=args.gpu_reference)
         if args.cpu_baseline and world == 1:
             out["cpu_baseline"] = cpu_reference_sample(cfg, flops_step, budget_s=args.cpu_budget)
         if args.gpu_reference and world == 1:
@@ -301,6 +306,55 @@ def cpu_reference_sample(cfg, flops_step, budget_s=20.0):
     return {"value": 1.0 / est_step_s, "unit": "latents/s", "cores": threads, "kind": "port",
             "sample": f"1 DiT block (D={D}, F={F_}) at {S} tokens, {n} runs, {sec:.2f} s/block = {tflops:.3f} TFLOP/s on {threads} threads; "
                       f"extrapolated to the {flops_step / 1e12:.0f} TFLOP step by the FLOP model (SURVEY.md 8d)"}
+
+
+def vae_decode_bench(cfg, dev, with_reference=True):
+    """Second half of BASELINE.json's metric: Wan VAE decode MPix/s on the workload's latent ([16, 21, 90, 160] -> 81 x 720 x 1280)."""
+    from lightx2v_b200.host.wan_vae import WanVAEDecoderB200
+    from oracle import vae_oracle as V           # synthetic weights + (optional) the reference decode loop as GPU baseline
+    C, Fr, Hh, Ww = cfg["target_shape"]
+    Wd = V.synth_vae_weights(0)
+    dec = WanVAEDecoderB200(Wd, device=dev)
+    g = torch.Generator(device=dev).manual_seed(3)
+    zs = torch.randn(C, Fr, Hh, Ww, generator=g, device=dev)
+    mpix = (1 + 4 * (Fr - 1)) * Hh * 8 * Ww * 8 / 1e6
+    res = {"unit": "MPix/s", "output": [3, 1 + 4 * (Fr - 1), Hh * 8, Ww * 8], "mpix": round(mpix, 2), "dtype": "bf16 activations, fp32 accumulate"}
+    try:
+        img = dec.decode(zs)
+        torch.cuda.synchronize()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        n = 2
+        for _ in range(n):
+            img = dec.decode(zs)
+        e.record()
+        torch.cuda.synchronize()
+        ms = s.elapsed_time(e) / n
+        res.update(value=round(mpix / (ms * 1e-3), 1), ms=round(ms, 1), achieved_tflops=round(639.3 / (ms * 1e-3) / 1e3 * 1e0, 1),
+                   peak_mem_gb=round(torch.cuda.max_memory_allocated() / 2**30, 1))
+        del img
+    except Exception as ex:  # noqa
+        res["error"] = str(ex)[:300]
+    if with_reference:
+        try:
+            del dec
+            torch.cuda.empty_cache()
+            Wg = {k: v.to(dev) for k, v in Wd.items()}
+            zs_small = zs[:, :6]                                   # the reference loop is per latent frame: 6 frames -> 21 video frames
+            V.vae_decode(Wg, zs_small[:, :2])
+            torch.cuda.synchronize()
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            V.vae_decode(Wg, zs_small)
+            e.record()
+            torch.cuda.synchronize()
+            frames = 1 + 4 * (zs_small.shape[1] - 1)
+            mp = frames * Hh * 8 * Ww * 8 / 1e6
+            res["gpu_reference"] = {"value": round(mp / (s.elapsed_time(e) * 1e-3), 1), "unit": "MPix/s",
+                                    "sample": f"reference per-frame decode loop (fp32, cuDNN TF32), {zs_small.shape[1]} latent frames -> {frames} frames"}
+        except Exception as ex:  # noqa
+            res["gpu_reference"] = {"unavailable": str(ex)[:200]}
+    return res
 
 
 def gpu_reference_sample(cfg, S, dev):
@@ -361,6 +415,7 @@ def main():
     ap.add_argument("--workload", default="wan2.1-t2v-14b-720p-81f", choices=list(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false")
     ap.add_argument("--no-gpu-reference", dest="gpu_reference", action="store_false")
+    ap.add_argument("--no-vae", dest="vae", action="store_false")
     ap.add_argument("--cpu-budget", type=float, default=20.0)
     args = ap.parse_args()
     if args.impl == "reference":

@@ -89,6 +89,29 @@ int b200_ln_modulate_fp8(const void* x, int64_t ldx, void* q8, int64_t ldq, floa
                          const void* ln_b, const void* scale, const void* shift, int64_t rows, int D, float eps,
                          b200_stream_t stream);
 
+/* ---- Wan 3-D causal VAE decoder (channels-last bf16 activations [T, H, W, C]) ---------------------------------------- */
+
+/* out[t,h,w,n] = bias[n] + sum_tap sum_c in[t+dt, h+dh, w+dw, c] * wt[n, tap*cin + c] (+ residual[t,h,w,n]) (clamped to [-1,1] if
+ * clamp_out).  in / out / residual are channels-last VIEWS given by a base pointer and element strides for (t, h, w); reads
+ * outside [0,T)x[0,H)x[0,W) are zero (the convolution's zero padding, causal along t).  taps: ntaps x (dt, dh, dw) int32.
+ * cin multiple of 32, cout 16 or a multiple of 64 / 96 / 192.  Replaces CausalConv3d.forward / nn.Conv2d of the decoder
+ * (lightx2v/models/video_encoders/hf/wan/vae.py:19-44, 88-97, 185-223) incl. the two-frame cache protocol (:203-217). */
+int b200_conv3d_cl(const void* in, int64_t in_st, int64_t in_sh, int64_t in_sw, const void* wt, const void* bias, void* out,
+                   int64_t out_st, int64_t out_sh, int64_t out_sw, const void* residual, int64_t res_st, int64_t res_sh,
+                   int64_t res_sw, int T, int H, int W, int cin, int cout, int ntaps, const int32_t* taps, int clamp_out,
+                   b200_stream_t stream);
+
+/* y[v, :] = [silu] ( x[v, :] / max(||x[v, :]||_2, 1e-12) * sqrt(C) * gamma ) over `voxels` channels-last rows of C in {96,192,384}.
+ * Replaces RMS_norm.forward + nn.SiLU (vae.py:47-59, 192-195, 430-433). */
+int b200_rms_silu_cl(const void* x, void* y, const float* gamma, int64_t voxels, int C, int apply_silu, b200_stream_t stream);
+
+/* z [CZ,T,H,W] fp32 -> channels-last bf16 [T,H,W,CP] of (z / inv_std + mean), channels >= CZ zero (WanVAE_.decode, vae.py:716-719). */
+int b200_latent_to_cl(const float* z, void* out, const float* mean, const float* inv_std, int64_t voxels, int CZ, int CP,
+                      b200_stream_t stream);
+
+/* channels-last bf16 [voxels, CP] (3 valid channels) -> fp32 [3, voxels]  (the `.float()` video tensor, vae.py:951). */
+int b200_cl_to_video(const void* in, float* out, int64_t voxels, int CP, b200_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -23,6 +23,14 @@ int quant_fp8_per_token(const void* x, long long ldx, void* q8, long long ldq, f
 int ln_modulate_fp8(const void* x, long long ldx, void* q8, long long ldq, float* q_scale, const void* ln_w,
                     const void* ln_b, const void* scale, const void* shift, long long rows, int D, float eps,
                     cudaStream_t stream);
+int conv3d_cl(const void* in, long long in_st, long long in_sh, long long in_sw, const void* wt, const void* bias,
+              void* out, long long out_st, long long out_sh, long long out_sw, const void* residual, long long res_st,
+              long long res_sh, long long res_sw, int T, int H, int W, int cin, int cout, int ntaps, const int* taps,
+              int clamp_out, cudaStream_t stream);
+int rms_silu_cl(const void* x, void* y, const float* gamma, long long voxels, int C, int apply_silu, cudaStream_t stream);
+int latent_to_cl(const float* z, void* out, const float* mean, const float* inv_std, long long voxels, int CZ, int CP,
+                 cudaStream_t stream);
+int cl_to_video(const void* in, float* out, long long voxels, int CP, cudaStream_t stream);
 }  // namespace b200
 
 extern "C" {
@@ -74,6 +82,27 @@ int b200_ln_modulate_fp8(const void* x, int64_t ldx, void* q8, int64_t ldq, floa
                          b200_stream_t stream) {
   return b200::ln_modulate_fp8(x, ldx, q8, ldq, q_scale, ln_w, ln_b, scale, shift, rows, D, eps,
                                reinterpret_cast<cudaStream_t>(stream));
+}
+
+int b200_conv3d_cl(const void* in, int64_t in_st, int64_t in_sh, int64_t in_sw, const void* wt, const void* bias, void* out,
+                   int64_t out_st, int64_t out_sh, int64_t out_sw, const void* residual, int64_t res_st, int64_t res_sh,
+                   int64_t res_sw, int T, int H, int W, int cin, int cout, int ntaps, const int32_t* taps, int clamp_out,
+                   b200_stream_t stream) {
+  return b200::conv3d_cl(in, in_st, in_sh, in_sw, wt, bias, out, out_st, out_sh, out_sw, residual, res_st, res_sh, res_sw, T,
+                         H, W, cin, cout, ntaps, taps, clamp_out, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int b200_rms_silu_cl(const void* x, void* y, const float* gamma, int64_t voxels, int C, int apply_silu, b200_stream_t stream) {
+  return b200::rms_silu_cl(x, y, gamma, voxels, C, apply_silu, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int b200_latent_to_cl(const float* z, void* out, const float* mean, const float* inv_std, int64_t voxels, int CZ, int CP,
+                      b200_stream_t stream) {
+  return b200::latent_to_cl(z, out, mean, inv_std, voxels, CZ, CP, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int b200_cl_to_video(const void* in, float* out, int64_t voxels, int CP, b200_stream_t stream) {
+  return b200::cl_to_video(in, out, voxels, CP, reinterpret_cast<cudaStream_t>(stream));
 }
 
 }  // extern "C"

@@ -363,6 +363,311 @@ fmha_fwd_d128_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
   }
 }
 
+// =====================================================================================================================
+// v3: same tiling and TMEM plan, but TWO softmax warpgroups per query tile (each thread owns half a row: 64 score columns),
+// and P is handed to the MMA warp in two halves so PV_j starts while the second half of the exponentials is still running.
+// Rationale (ncu, v2): with P aliased onto S the per-tile loop is serial — softmax (Ts) then PV + QK (1024 tensor cycles) —
+// so tensor utilisation = 2048 / (Ts + 1024 + latencies); v2 had Ts ~ 1600 cycles (one warp per scheduler, 128 elements per
+// thread).  Halving the per-thread work and doubling the warps per scheduler brings Ts towards the MUFU floor.
+//   warps 4..7  : tile 0, columns   0..63      warps  8..11 : tile 0, columns 64..127
+//   warps 12..15: tile 1, columns   0..63      warps 16..19 : tile 1, columns 64..127
+// Row max and the final row sum are exchanged between the two owners of a row through shared memory + a 256-thread named barrier.
+// =====================================================================================================================
+constexpr int FMHA3_THREADS = 640;
+constexpr int FMHA3_SMEM_BYTES = FMHA_SMEM_BYTES + 2 * 2 * 2 * 128 * 4 + 2 * 2 * 128 * 4;   // + max exchange (double-buffered) + sum exchange
+
+template <int kPolyPairs>
+__global__ void __launch_bounds__(FMHA3_THREADS, 1)
+fmha_fwd_d128_v3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                        const __grid_constant__ CUtensorMap tmV, const FmhaParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;
+  uint8_t* sKV = smem + 2 * FMHA_TILE_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sKV + FMHA_KV_STAGES * FMHA_TILE_BYTES);
+  uint64_t* q_full = bars;               // [1]
+  uint64_t* kv_full = bars + 1;          // [4]
+  uint64_t* kv_empty = bars + 5;         // [4]
+  uint64_t* s_full = bars + 9;           // [2]
+  uint64_t* p_half = bars + 11;          // [2 tiles][2 halves]
+  uint64_t* o_full = bars + 15;          // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 17);
+  float* xmax = reinterpret_cast<float*>(bars + 20);      // [parity 2][tile 2][half 2][128]
+  float* xsum = xmax + 2 * 2 * 2 * 128;                   // [tile 2][half 2][128]
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int head = blockIdx.y;
+  const int q0 = blockIdx.x * (2 * FMHA_BLOCK_Q);
+  const int n_kv = p.num_kv_tiles;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmQ);
+    prefetch_tmap(&tmK);
+    prefetch_tmap(&tmV);
+  }
+  if (warp == 1 && lane == 0) {
+    mbar_init(q_full, 1);
+    for (int i = 0; i < FMHA_KV_STAGES; ++i) {
+      mbar_init(&kv_full[i], 1);
+      mbar_init(&kv_empty[i], 1);
+    }
+    for (int t = 0; t < 2; ++t) {
+      mbar_init(&s_full[t], 1);
+      mbar_init(&p_half[t * 2 + 0], 128);
+      mbar_init(&p_half[t * 2 + 1], 128);
+      mbar_init(&o_full[t], 1);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  constexpr uint32_t COL_S0 = 0, COL_S1 = 128, COL_O0 = 256, COL_O1 = 384;
+
+  if (warp < 4) {
+    // 640 threads launch with 96 registers each; 128*48 + 512*104 <= 640*96
+    reg_dealloc<48>();
+    if (warp == 0) {
+      // ============================== TMA producer ==============================
+      if (lane == 0) {
+        mbar_arrive_expect_tx(q_full, 2 * FMHA_TILE_BYTES);
+        for (int t = 0; t < 2; ++t)
+          for (int h = 0; h < 2; ++h)
+            tma_load_3d(sQ + t * FMHA_TILE_BYTES + h * FMHA_PANEL_BYTES, &tmQ, q_full, h * 64, head, q0 + t * FMHA_BLOCK_Q);
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int it = 0; it < 2 * n_kv; ++it) {   // K_0, V_0, K_1, V_1, ...
+          const int j = it >> 1;
+          const CUtensorMap* tm = (it & 1) ? &tmV : &tmK;
+          mbar_wait(&kv_empty[stage], phase ^ 1);
+          mbar_arrive_expect_tx(&kv_full[stage], FMHA_TILE_BYTES);
+          for (int h = 0; h < 2; ++h)
+            tma_load_3d(sKV + stage * FMHA_TILE_BYTES + h * FMHA_PANEL_BYTES, tm, &kv_full[stage], h * 64, head, j * FMHA_BLOCK_KV);
+          if (++stage == FMHA_KV_STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    } else if (warp == 1) {
+      // ============================== MMA issuer (whole warp, warp-uniform) ==============================
+      constexpr uint32_t idesc_qk = make_idesc(FMT_BF16, FMT_BF16, 128, 128, 0, 0);
+      constexpr uint32_t idesc_pv = make_idesc(FMT_BF16, FMT_BF16, 128, 128, 0, 1);
+      const uint32_t tb = __shfl_sync(0xffffffffu, tmem_base, 0);
+      const uint32_t tS0 = tb + COL_S0, tS1 = tb + COL_S1;
+      const uint32_t tO0 = tb + COL_O0, tO1 = tb + COL_O1;
+      const uint32_t q_lo = desc_lo_kmajor(smem_u32(sQ));
+      const uint32_t kv_addr = smem_u32(sKV);
+
+      auto issue_qk = [&](int t, int kstage) {
+        const uint32_t a = q_lo + t * (FMHA_TILE_BYTES >> 4);
+        const uint32_t b = desc_lo_kmajor(kv_addr + kstage * FMHA_TILE_BYTES);
+        const uint32_t d = t ? tS1 : tS0;
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks) {
+          const uint32_t off = ((ks >> 2) * FMHA_PANEL_BYTES + (ks & 3) * 32) >> 4;
+          mma_f16_ss_w(d, a + off, kDescHiSw128, b + off, kDescHiSw128, idesc_qk, ks != 0 ? 1u : 0u);
+        }
+      };
+      // half = 0: kv rows 0..63 (P columns 0..31), half = 1: kv rows 64..127
+      auto issue_pv_half = [&](int t, int vstage, int half, uint32_t accumulate) {
+        const uint32_t b = desc_lo_mnmajor(kv_addr + vstage * FMHA_TILE_BYTES, FMHA_PANEL_BYTES);
+        const uint32_t d = t ? tO1 : tO0;
+        const uint32_t a = t ? tS1 : tS0;
+#pragma unroll
+        for (int k4 = 0; k4 < 4; ++k4) {
+          const int ks = half * 4 + k4;
+          mma_f16_ts_w(d, a + ks * 8, b + ks * (2048 >> 4), kDescHiSw128, idesc_pv, (half | k4) != 0 ? 1u : accumulate);
+        }
+      };
+
+      int stage = 0;
+      uint32_t phase = 0;
+      auto advance = [&]() {
+        if (++stage == FMHA_KV_STAGES) {
+          stage = 0;
+          phase ^= 1;
+        }
+      };
+
+      mbar_wait(q_full, 0);
+      mbar_wait(&kv_full[stage], phase);
+      tc_fence_after();
+      issue_qk(0, stage);
+      tc_commit_w(&s_full[0]);
+      issue_qk(1, stage);
+      tc_commit_w(&s_full[1]);
+      tc_commit_w(&kv_empty[stage]);
+      advance();
+
+      for (int j = 0; j < n_kv; ++j) {
+        const bool has_next = (j + 1) < n_kv;
+        const int vstage = stage;
+        mbar_wait(&kv_full[stage], phase);
+        advance();
+        const int kstage = stage;
+        if (has_next) {
+          mbar_wait(&kv_full[stage], phase);
+          advance();
+        }
+        const uint32_t pj = j & 1;
+        const uint32_t acc = j > 0 ? 1u : 0u;
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+          mbar_wait(&p_half[t * 2 + 0], pj);
+          tc_fence_after();
+          issue_pv_half(t, vstage, 0, acc);
+          mbar_wait(&p_half[t * 2 + 1], pj);
+          tc_fence_after();
+          issue_pv_half(t, vstage, 1, acc);
+          if (t == 1) tc_commit_w(&kv_empty[vstage]);
+          if (has_next) {
+            issue_qk(t, kstage);
+            tc_commit_w(&s_full[t]);
+            if (t == 1) tc_commit_w(&kv_empty[kstage]);
+          } else {
+            tc_commit_w(&o_full[t]);
+          }
+        }
+      }
+    }
+  } else {
+    // ============================== softmax / correction / epilogue ==============================
+    reg_alloc<104>();
+    const int sw = warp - 4;
+    const int t = sw >> 3;                     // query tile
+    const int hf = (sw >> 2) & 1;              // column half owned by this thread
+    const int lg = warp & 3;                   // TMEM lane group
+    const int row = lg * 32 + lane;
+    const uint32_t lane_off = uint32_t(lg * 32) << 16;
+    const uint32_t tS = tmem_base + (t ? COL_S1 : COL_S0) + lane_off;
+    const uint32_t tSh = tS + hf * 64;         // my 64 score columns
+    const uint32_t tPh = tS + hf * 32;         // my 32 packed P columns
+    const uint32_t tOh = tmem_base + (t ? COL_O1 : COL_O0) + lane_off + hf * 64;
+    const float sl2 = p.scale_log2;
+    const uint32_t bar_id = 2 + t;
+
+    float m_used = -INFINITY;
+    float l_sum = 0.f;                          // partial: my 64 columns only
+
+    for (int j = 0; j < n_kv; ++j) {
+      mbar_wait(&s_full[t], j & 1);
+      tc_fence_after();
+      uint32_t s[64];
+      tmem_ld_x32(tSh, s);
+      tmem_ld_x32(tSh + 32, s + 32);
+      tmem_ld_wait();
+
+      const int kv_valid = p.sk - j * FMHA_BLOCK_KV - hf * 64;   // valid columns among my 64 (may be <= 0)
+      if (kv_valid < 64) {
+#pragma unroll
+        for (int i = 0; i < 64; ++i)
+          if (i >= kv_valid) s[i] = 0xff800000u;  // -inf
+      }
+      float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+      for (int i = 0; i < 64; i += 2) {
+        mx0 = fmaxf(mx0, __uint_as_float(s[i]));
+        mx1 = fmaxf(mx1, __uint_as_float(s[i + 1]));
+      }
+      const float mloc = fmaxf(mx0, mx1);
+      float* xm = xmax + (((j & 1) * 2 + t) * 2) * 128;
+      xm[hf * 128 + row] = mloc;
+      named_bar_sync(bar_id, 256);             // also: every S column of this tile has been read -> P may overwrite it
+      const float m_new = fmaxf(fmaxf(mloc, xm[(hf ^ 1) * 128 + row]), m_used);
+
+      if (j == 0) {
+        m_used = m_new;
+      } else {
+        const bool need = (m_new - m_used) * sl2 > 8.0f;
+        if (__any_sync(0xffffffffu, need)) {
+          float alpha = 1.0f;
+          if (need) {
+            alpha = ex2((m_used - m_new) * sl2);
+            m_used = m_new;
+          }
+          l_sum *= alpha;
+#pragma unroll 1
+          for (int c = 0; c < 64; c += 32) {
+            uint32_t o[32];
+            tmem_ld_x32(tOh + c, o);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+            tmem_st_x32(tOh + c, o);
+          }
+          tmem_st_wait();
+        }
+      }
+
+      const float2 sl2v = make_float2(sl2, sl2);
+      const float neg_m = -m_used * sl2;
+      const float2 negm = make_float2(neg_m, neg_m);
+      float2 acc[4] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
+      uint32_t pk[32];
+#pragma unroll
+      for (int g = 0; g < 8; ++g) {
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) {
+          const int i = g * 4 + jj;
+          const float2 x = __ffma2_rn(make_float2(__uint_as_float(s[2 * i]), __uint_as_float(s[2 * i + 1])), sl2v, negm);
+          float2 e;
+          if (jj < kPolyPairs) {
+            e = exp2_poly2(x);
+          } else {
+            e.x = ex2(x.x);
+            e.y = ex2(x.y);
+          }
+          acc[jj] = __fadd2_rn(acc[jj], e);
+          pk[i] = pack_bf16(e.x, e.y);
+        }
+      }
+      const float2 a01 = __fadd2_rn(acc[0], acc[1]), a23 = __fadd2_rn(acc[2], acc[3]);
+      l_sum += (a01.x + a01.y) + (a23.x + a23.y);
+      tmem_st_x32(tPh, pk);
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive(&p_half[t * 2 + hf]);
+    }
+
+    // ---- epilogue: exchange the partial row sums, then O / l -> bf16 -> global (my 64 of the 128 head-dim columns)
+    xsum[(t * 2 + hf) * 128 + row] = l_sum;
+    named_bar_sync(bar_id, 256);
+    const float inv_l = 1.0f / (l_sum + xsum[(t * 2 + (hf ^ 1)) * 128 + row]);
+    mbar_wait(&o_full[t], 0);
+    tc_fence_after();
+    const int q_row = q0 + t * FMHA_BLOCK_Q + row;
+    __nv_bfloat16* orow = p.out + (long long)q_row * p.o_stride_s + (long long)head * FMHA_D + hf * 64;
+#pragma unroll 1
+    for (int c = 0; c < 64; c += 32) {
+      uint32_t o[32];
+      tmem_ld_x32(tOh + c, o);
+      tmem_ld_wait();
+      if (q_row < p.sq) {
+#pragma unroll
+        for (int v = 0; v < 4; ++v) {
+          uint4 w;
+          w.x = pack_bf16(__uint_as_float(o[v * 8 + 0]) * inv_l, __uint_as_float(o[v * 8 + 1]) * inv_l);
+          w.y = pack_bf16(__uint_as_float(o[v * 8 + 2]) * inv_l, __uint_as_float(o[v * 8 + 3]) * inv_l);
+          w.z = pack_bf16(__uint_as_float(o[v * 8 + 4]) * inv_l, __uint_as_float(o[v * 8 + 5]) * inv_l);
+          w.w = pack_bf16(__uint_as_float(o[v * 8 + 6]) * inv_l, __uint_as_float(o[v * 8 + 7]) * inv_l);
+          *reinterpret_cast<uint4*>(orow + c + v * 8) = w;
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
 // q/k/v: [rows, H, 128] bf16 with arbitrary row stride (elements), heads contiguous (stride 128).
 static int encode_qkv_map(CUtensorMap* tm, const void* base, long long rows, int heads, long long stride_s) {
   uint64_t dims[3] = {128, (uint64_t)heads, (uint64_t)rows};
@@ -407,17 +712,32 @@ int fmha_fwd_d128(const void* q, long long q_stride_s, const void* k, long long 
     if (poly < 0 || poly > 3) poly = 1;
   }
   dim3 grid((unsigned)((sq + 2 * FMHA_BLOCK_Q - 1) / (2 * FMHA_BLOCK_Q)), (unsigned)heads, 1);
-  auto launch = [&](auto kern) -> int {
-    B200_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, FMHA_SMEM_BYTES));
-    kern<<<grid, FMHA_THREADS, FMHA_SMEM_BYTES, stream>>>(tmQ, tmK, tmV, p);
+  static int ver = -1;
+  if (ver < 0) {
+    const char* e = getenv("B200_FMHA_VER");
+    ver = e ? atoi(e) : 3;
+    if (ver != 2 && ver != 3) ver = 3;
+  }
+  auto launch = [&](auto kern, int threads, int smem_bytes) -> int {
+    B200_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+    kern<<<grid, threads, smem_bytes, stream>>>(tmQ, tmK, tmV, p);
     return B200_OK;
   };
   int rc2;
-  switch (poly) {
-    case 0: rc2 = launch(fmha_fwd_d128_kernel<0>); break;
-    case 2: rc2 = launch(fmha_fwd_d128_kernel<2>); break;
-    case 3: rc2 = launch(fmha_fwd_d128_kernel<3>); break;
-    default: rc2 = launch(fmha_fwd_d128_kernel<1>); break;
+  if (ver == 3) {
+    switch (poly) {
+      case 0: rc2 = launch(fmha_fwd_d128_v3_kernel<0>, FMHA3_THREADS, FMHA3_SMEM_BYTES); break;
+      case 2: rc2 = launch(fmha_fwd_d128_v3_kernel<2>, FMHA3_THREADS, FMHA3_SMEM_BYTES); break;
+      case 3: rc2 = launch(fmha_fwd_d128_v3_kernel<3>, FMHA3_THREADS, FMHA3_SMEM_BYTES); break;
+      default: rc2 = launch(fmha_fwd_d128_v3_kernel<1>, FMHA3_THREADS, FMHA3_SMEM_BYTES); break;
+    }
+  } else {
+    switch (poly) {
+      case 0: rc2 = launch(fmha_fwd_d128_kernel<0>, FMHA_THREADS, FMHA_SMEM_BYTES); break;
+      case 2: rc2 = launch(fmha_fwd_d128_kernel<2>, FMHA_THREADS, FMHA_SMEM_BYTES); break;
+      case 3: rc2 = launch(fmha_fwd_d128_kernel<3>, FMHA_THREADS, FMHA_SMEM_BYTES); break;
+      default: rc2 = launch(fmha_fwd_d128_kernel<1>, FMHA_THREADS, FMHA_SMEM_BYTES); break;
+    }
   }
   if (rc2) return rc2;
   B200_CHECK_CUDA(cudaGetLastError());

@@ -1,0 +1,152 @@
+// Element-wise / layout kernels of the Wan VAE decoder on channels-last bf16 activations.
+//   rms_silu      : RMS_norm (per-voxel L2 normalisation over channels, * sqrt(C) * gamma) + SiLU
+//                   (lightx2v/models/video_encoders/hf/wan/vae.py:47-59 RMS_norm, :192-195 the norm->SiLU->conv pattern)
+//   latent_to_cl  : z[16,T,H,W] fp32 -> (z / inv_std + mean) -> channels-last bf16 [T,H,W,32] (zero-padded channels)  (vae.py:716-719)
+//   cl_to_video   : channels-last bf16 [T,H,W,16] (3 valid) -> fp32 [3,T,H,W]                                           (vae.py:951)
+#include "host_util.cuh"
+#include "ptx.cuh"
+
+namespace b200 {
+
+// One warp handles `VPW` voxels per iteration; each lane owns 8 channels (16 bytes); C/8 lanes per voxel.
+template <int C>
+__global__ void __launch_bounds__(256)
+rms_silu_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, const float* __restrict__ gamma,
+                long long voxels, int apply_silu) {
+  constexpr int LPV = C / 8;                 // lanes per voxel
+  constexpr int G = (LPV <= 16) ? 16 : ((LPV <= 32) ? 32 : 64);   // lanes reserved per voxel (power of two)
+  static_assert(G <= 64, "C too large");
+  constexpr int VPW = (G <= 32) ? 32 / G : 1;                      // voxels per warp pass
+  const int lane = threadIdx.x & 31;
+  const long long warp_global = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
+  const float sqrt_c = sqrtf((float)C);
+  if constexpr (G <= 32) {
+    const int sub = lane / G, l = lane % G;
+    float g[8];
+    if (l < LPV) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) g[e] = gamma[l * 8 + e] * sqrt_c;
+    }
+    for (long long v0 = warp_global * VPW; v0 < voxels; v0 += nwarps * VPW) {
+      const long long v = v0 + sub;
+      const bool ok = v < voxels && l < LPV;
+      uint4 raw = make_uint4(0, 0, 0, 0);
+      if (ok) raw = *reinterpret_cast<const uint4*>(x + v * C + l * 8);
+      float f[8] = {bf16_lo(raw.x), bf16_hi(raw.x), bf16_lo(raw.y), bf16_hi(raw.y), bf16_lo(raw.z), bf16_hi(raw.z), bf16_lo(raw.w), bf16_hi(raw.w)};
+      float ss = 0.f;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) ss += f[e] * f[e];
+#pragma unroll
+      for (int o = G / 2; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+      const float inv = 1.0f / fmaxf(sqrtf(ss), 1e-12f);        // F.normalize: x / max(||x||_2, eps)
+      if (ok) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          float t = f[e] * inv * g[e];
+          if (apply_silu) t = t / (1.0f + __expf(-t));
+          f[e] = t;
+        }
+        uint4 o;
+        o.x = pack_bf16(f[0], f[1]); o.y = pack_bf16(f[2], f[3]); o.z = pack_bf16(f[4], f[5]); o.w = pack_bf16(f[6], f[7]);
+        *reinterpret_cast<uint4*>(y + v * C + l * 8) = o;
+      }
+    }
+  } else {
+    // C = 384: 48 lanes' worth of data per voxel -> each lane takes 2 x 8 channels (lanes 0..23 active twice)
+    for (long long v = warp_global; v < voxels; v += nwarps) {
+      float f[2][8];
+      float ss = 0.f;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int c0 = (lane + h * 32) * 8;
+        uint4 raw = make_uint4(0, 0, 0, 0);
+        if (c0 < C) raw = *reinterpret_cast<const uint4*>(x + v * C + c0);
+        const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          f[h][2 * e] = bf16_lo(w[e]);
+          f[h][2 * e + 1] = bf16_hi(w[e]);
+          ss += f[h][2 * e] * f[h][2 * e] + f[h][2 * e + 1] * f[h][2 * e + 1];
+        }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+      const float inv = sqrt_c / fmaxf(sqrtf(ss), 1e-12f);
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int c0 = (lane + h * 32) * 8;
+        if (c0 < C) {
+          float o8[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            float t = f[h][e] * inv * gamma[c0 + e];
+            if (apply_silu) t = t / (1.0f + __expf(-t));
+            o8[e] = t;
+          }
+          uint4 o;
+          o.x = pack_bf16(o8[0], o8[1]); o.y = pack_bf16(o8[2], o8[3]); o.z = pack_bf16(o8[4], o8[5]); o.w = pack_bf16(o8[6], o8[7]);
+          *reinterpret_cast<uint4*>(y + v * C + c0) = o;
+        }
+      }
+    }
+  }
+}
+
+int rms_silu_cl(const void* x, void* y, const float* gamma, long long voxels, int C, int apply_silu, cudaStream_t stream) {
+  B200_CHECK_ARG(x && y && gamma, "b200_rms_silu_cl: null pointer");
+  B200_CHECK_ARG(voxels > 0, "b200_rms_silu_cl: empty tensor");
+  const auto* xp = reinterpret_cast<const __nv_bfloat16*>(x);
+  auto* yp = reinterpret_cast<__nv_bfloat16*>(y);
+  const int blocks = num_sms() * 8;
+  switch (C) {
+    case 96: rms_silu_kernel<96><<<blocks, 256, 0, stream>>>(xp, yp, gamma, voxels, apply_silu); break;
+    case 192: rms_silu_kernel<192><<<blocks, 256, 0, stream>>>(xp, yp, gamma, voxels, apply_silu); break;
+    case 384: rms_silu_kernel<384><<<blocks, 256, 0, stream>>>(xp, yp, gamma, voxels, apply_silu); break;
+    default:
+      set_last_error("b200_rms_silu_cl: unsupported channel count %d (96 / 192 / 384)", C);
+      return B200_ERR_UNSUPPORTED;
+  }
+  B200_CHECK_CUDA(cudaGetLastError());
+  return B200_OK;
+}
+
+// z [CZ, T, H, W] fp32 -> out [T, H, W, CP] bf16 with out[..., c] = z[c] / inv_std[c] + mean[c] for c < CZ, 0 otherwise
+__global__ void latent_to_cl_kernel(const float* __restrict__ z, __nv_bfloat16* __restrict__ out, const float* __restrict__ mean,
+                                    const float* __restrict__ inv_std, long long voxels, int CZ, int CP) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= voxels * CP) return;
+  const long long v = i / CP;
+  const int c = (int)(i - v * CP);
+  float val = 0.f;
+  if (c < CZ) val = z[(long long)c * voxels + v] / inv_std[c] + mean[c];
+  out[i] = __float2bfloat16_rn(val);
+}
+
+int latent_to_cl(const float* z, void* out, const float* mean, const float* inv_std, long long voxels, int CZ, int CP,
+                 cudaStream_t stream) {
+  B200_CHECK_ARG(z && out && mean && inv_std && voxels > 0 && CZ > 0 && CP >= CZ, "b200_latent_to_cl: bad arguments");
+  const long long n = voxels * CP;
+  latent_to_cl_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(z, reinterpret_cast<__nv_bfloat16*>(out), mean, inv_std, voxels, CZ, CP);
+  B200_CHECK_CUDA(cudaGetLastError());
+  return B200_OK;
+}
+
+// in [voxels, CP] bf16 (first 3 channels valid) -> out [3, voxels] fp32
+__global__ void cl_to_video_kernel(const __nv_bfloat16* __restrict__ in, float* __restrict__ out, long long voxels, int CP) {
+  const long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= voxels) return;
+  const __nv_bfloat16* p = in + v * CP;
+  out[v] = __bfloat162float(p[0]);
+  out[voxels + v] = __bfloat162float(p[1]);
+  out[2 * voxels + v] = __bfloat162float(p[2]);
+}
+
+int cl_to_video(const void* in, float* out, long long voxels, int CP, cudaStream_t stream) {
+  B200_CHECK_ARG(in && out && voxels > 0 && CP >= 3, "b200_cl_to_video: bad arguments");
+  cl_to_video_kernel<<<(unsigned)((voxels + 255) / 256), 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(in), out, voxels, CP);
+  B200_CHECK_CUDA(cudaGetLastError());
+  return B200_OK;
+}
+
+}  // namespace b200

@@ -28,6 +28,11 @@ SIGNATURES = {
     "b200_gemm_fp8": (_i32, [_ptr, _i64, _ptr, _i64, _ptr, _i64, _ptr, _ptr, _ptr, _ptr, _i64, _i64, _i64, _i32, _i32, _i32, _ptr]),
     "b200_quant_fp8_per_token": (_i32, [_ptr, _i64, _ptr, _i64, _ptr, _i64, _i32, _ptr]),
     "b200_ln_modulate_fp8": (_i32, [_ptr, _i64, _ptr, _i64, _ptr, _ptr, _ptr, _ptr, _ptr, _i64, _i32, _f32, _ptr]),
+    "b200_conv3d_cl": (_i32, [_ptr, _i64, _i64, _i64, _ptr, _ptr, _ptr, _i64, _i64, _i64, _ptr, _i64, _i64, _i64, _i32, _i32, _i32, _i32, _i32,
+                              _i32, _ptr, _i32, _ptr]),
+    "b200_rms_silu_cl": (_i32, [_ptr, _ptr, _ptr, _i64, _i32, _i32, _ptr]),
+    "b200_latent_to_cl": (_i32, [_ptr, _ptr, _ptr, _ptr, _i64, _i32, _i32, _ptr]),
+    "b200_cl_to_video": (_i32, [_ptr, _ptr, _i64, _i32, _ptr]),
 }
 
 EPI_BIAS, EPI_BIAS_GELU, EPI_GATE_RESIDUAL, EPI_RESIDUAL = 0, 1, 2, 3
@@ -197,4 +202,53 @@ def gemm_fp8(a_q: torch.Tensor, a_scale: torch.Tensor, w_q: torch.Tensor, w_scal
     rc = load().b200_gemm_fp8(a_q.data_ptr(), a_q.stride(0), w_q.data_ptr(), w_q.stride(0), out.data_ptr(), out.stride(0),
                               a_scale.data_ptr(), w_scale.data_ptr(), _p(bias), _p(gate), M, N, K, epilogue, block_n, max_ctas, _stream())
     _check(rc, "b200_gemm_fp8")
+    return out
+
+
+# ---------------------------------------------------------------------------------------------------------------- VAE (channels-last)
+def conv3d_cl(x: torch.Tensor, wt: torch.Tensor, bias: Optional[torch.Tensor], out: torch.Tensor, taps, *, residual: Optional[torch.Tensor] = None,
+              clamp_out: bool = False) -> torch.Tensor:
+    """x, out, residual: channels-last VIEWS [T, H, W, C] (channels contiguous, arbitrary t/h/w strides, same T/H/W extent);
+    wt [cout, ntaps*cin]; taps: sequence of (dt, dh, dw) input offsets."""
+    _req(x, "x"); _req(wt, "wt"); _req(out, "out")
+    T, H, W, cin = x.shape
+    cout = wt.shape[0]
+    if tuple(out.shape) != (T, H, W, cout) or wt.shape[1] != len(taps) * cin:
+        raise B200Error(f"conv3d_cl: shape mismatch x{tuple(x.shape)} wt{tuple(wt.shape)} out{tuple(out.shape)} taps {len(taps)}")
+    tp = (ctypes.c_int32 * (3 * len(taps)))(*[int(v) for t3 in taps for v in t3])
+    rs = (0, 0, 0) if residual is None else (residual.stride(0), residual.stride(1), residual.stride(2))
+    rc = load().b200_conv3d_cl(x.data_ptr(), x.stride(0), x.stride(1), x.stride(2), wt.data_ptr(), _p(bias), out.data_ptr(), out.stride(0),
+                               out.stride(1), out.stride(2), _p(residual), rs[0], rs[1], rs[2], T, H, W, cin, cout, len(taps),
+                               ctypes.cast(tp, ctypes.c_void_p), 1 if clamp_out else 0, _stream())
+    _check(rc, "b200_conv3d_cl")
+    return out
+
+
+def rms_silu_cl(x: torch.Tensor, gamma: torch.Tensor, *, silu: bool = True, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    _req(x, "x"); _req(gamma, "gamma", torch.float32)
+    if not x.is_contiguous():
+        raise B200Error("rms_silu_cl: x must be contiguous channels-last")
+    C = x.shape[-1]
+    if out is None:
+        out = torch.empty_like(x)
+    rc = load().b200_rms_silu_cl(x.data_ptr(), out.data_ptr(), gamma.data_ptr(), x.numel() // C, C, 1 if silu else 0, _stream())
+    _check(rc, "b200_rms_silu_cl")
+    return out
+
+
+def latent_to_cl(z: torch.Tensor, mean: torch.Tensor, inv_std: torch.Tensor, cp: int = 32) -> torch.Tensor:
+    _req(z, "z", torch.float32)
+    CZ, T, H, W = z.shape
+    out = torch.empty((T, H, W, cp), dtype=torch.bfloat16, device=z.device)
+    rc = load().b200_latent_to_cl(z.contiguous().data_ptr(), out.data_ptr(), mean.data_ptr(), inv_std.data_ptr(), T * H * W, CZ, cp, _stream())
+    _check(rc, "b200_latent_to_cl")
+    return out
+
+
+def cl_to_video(x: torch.Tensor) -> torch.Tensor:
+    _req(x, "x")
+    T, H, W, CP = x.shape
+    out = torch.empty((3, T, H, W), dtype=torch.float32, device=x.device)
+    rc = load().b200_cl_to_video(x.contiguous().data_ptr(), out.data_ptr(), T * H * W, CP, _stream())
+    _check(rc, "b200_cl_to_video")
     return out

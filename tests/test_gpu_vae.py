@@ -1,0 +1,109 @@
+"""GPU parity of the Wan VAE decoder path: the implicit-GEMM convolution against F.conv3d with the reference's causal
+padding, the phase-decomposed upsample convolution against Upsample(nearest-exact) + Conv2d, RMS_norm+SiLU against the
+oracle, and the whole decoder against (a) the fixture produced by the REAL WanVAE_ on CPU in fp32 and (b) the oracle's
+frame-by-frame restatement executed on the GPU.  The reference VAE computes in fp32 (TF32 on the GPU); this path keeps bf16
+activations, so results are reported as PSNR with a stated floor, plus max-abs-error caps on the [-1, 1] output."""
+import os
+
+import pytest
+import torch
+import torch.nn.functional as F
+from safetensors import safe_open
+
+from oracle import vae_oracle as V
+from oracle.wan_oracle import psnr
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from lightx2v_b200 import lib as L
+
+    L.load()
+    return L
+
+
+def _cl(x):      # [C, T, H, W] -> channels-last bf16 [T, H, W, C]
+    return x.permute(1, 2, 3, 0).contiguous().to(torch.bfloat16)
+
+
+@pytest.mark.parametrize("cin,cout,k,T,H,W", [(96, 96, (3, 3, 3), 3, 12, 40), (192, 96, (1, 1, 1), 2, 8, 32), (384, 384, (3, 3, 3), 2, 6, 33),
+                                              (32, 384, (3, 3, 3), 3, 8, 8), (96, 16, (3, 3, 3), 2, 9, 70), (192, 384, (3, 1, 1), 4, 5, 32)])
+def test_conv3d_cl_vs_causal_conv3d(lib, cin, cout, k, T, H, W):
+    from lightx2v_b200.host.wan_vae import _Conv
+
+    g = torch.Generator(device="cuda").manual_seed(1)
+    x = torch.randn(cin, T, H, W, generator=g, device="cuda")
+    w = torch.randn(cout, cin, *k, generator=g, device="cuda") / (cin * k[0] * k[1] * k[2]) ** 0.5
+    b = torch.randn(cout, generator=g, device="cuda") * 0.1
+    xb, wb, bb = x.to(torch.bfloat16).float(), w.to(torch.bfloat16).float(), b.to(torch.bfloat16).float()
+    torch.backends.cudnn.allow_tf32 = False
+    ref = V.causal_conv3d(xb.unsqueeze(0), wb, bb)[0]                       # fp32 math on the bf16-rounded operands
+    conv = _Conv(w, b, "cuda")
+    res = torch.randn(T, H, W, cout, generator=g, device="cuda").to(torch.bfloat16)
+    out = conv(_cl(x))
+    got = out.permute(3, 0, 1, 2).float()
+    assert (got - ref).abs().max() <= 2e-2 + 1e-2 * ref.abs().max()
+    assert psnr(got, ref) > 45
+    out2 = conv(_cl(x), residual=res)
+    ref2 = ref + res.permute(3, 0, 1, 2).float()
+    assert psnr(out2.permute(3, 0, 1, 2).float(), ref2) > 45
+
+
+def test_upsample_conv_phase_decomposition(lib):
+    from lightx2v_b200.host.wan_vae import _UpsampleConv
+
+    g = torch.Generator(device="cuda").manual_seed(2)
+    C, T, H, W = 192, 2, 10, 36
+    x = torch.randn(C, T, H, W, generator=g, device="cuda")
+    w = torch.randn(C // 2, C, 3, 3, generator=g, device="cuda") / (C * 9) ** 0.5
+    b = torch.randn(C // 2, generator=g, device="cuda") * 0.1
+    xb = x.to(torch.bfloat16).float()
+    torch.backends.cudnn.allow_tf32 = False
+    frames = xb.permute(1, 0, 2, 3)
+    ref = F.conv2d(F.interpolate(frames, scale_factor=(2.0, 2.0), mode="nearest-exact"), w, b, padding=1).permute(1, 0, 2, 3)
+    got = _UpsampleConv(w, b, "cuda")(_cl(x)).permute(3, 0, 1, 2).float()
+    assert got.shape == ref.shape
+    assert psnr(got, ref) > 40          # pre-summed bf16 weights vs fp32 weights on the upsampled image
+
+
+@pytest.mark.parametrize("C", [96, 192, 384])
+def test_rms_silu(lib, C):
+    g = torch.Generator(device="cuda").manual_seed(3)
+    x = torch.randn(1000, C, generator=g, device="cuda").to(torch.bfloat16)
+    gamma = 1 + 0.1 * torch.randn(C, generator=g, device="cuda")
+    ref = F.silu(V.rms_norm(x.float(), gamma, channel_dim=1))
+    got = lib.rms_silu_cl(x, gamma).float()
+    assert (got - ref).abs().max() < 2e-2
+    got2 = lib.rms_silu_cl(x, gamma, silu=False).float()
+    assert (got2 - V.rms_norm(x.float(), gamma, channel_dim=1)).abs().max() < 3e-2
+
+
+def test_decoder_vs_reference_fixture(golden_dir):
+    from lightx2v_b200.host.wan_vae import WanVAEDecoderB200
+
+    with safe_open(os.path.join(golden_dir, "wan_vae_decode_small.safetensors"), framework="pt") as f:
+        zs, ref = f.get_tensor("zs"), f.get_tensor("images")
+    dec = WanVAEDecoderB200(V.synth_vae_weights(0), device="cuda")
+    out = dec.decode(zs.cuda()).cpu()
+    assert out.shape == ref.shape
+    p = psnr(out, ref)
+    err = (out - ref).abs()
+    print(f"VAE decode vs real reference (fp32 CPU): PSNR {p:.1f} dB, max abs err {err.max():.4f}, mean {err.mean():.5f}")
+    assert p > 35 and err.max() < 0.15 and err.mean() < 1.5e-2
+
+
+def test_decoder_vs_oracle_on_gpu_larger():
+    """[16, 5, 24, 40] latent -> 17 frames of 192 x 320: whole-sequence bf16 path vs the frame-by-frame fp32/TF32 oracle on the GPU."""
+    from lightx2v_b200.host.wan_vae import WanVAEDecoderB200
+
+    W = V.synth_vae_weights(1, device="cuda")
+    g = torch.Generator(device="cuda").manual_seed(7)
+    zs = torch.randn(16, 5, 24, 40, generator=g, device="cuda")
+    ref = V.vae_decode(W, zs)
+    out = WanVAEDecoderB200(W, device="cuda").decode(zs)
+    assert out.shape == ref.shape == (1, 3, 17, 192, 320)
+    p = psnr(out, ref)
+    print(f"VAE decode 17x192x320 vs oracle on GPU: PSNR {p:.1f} dB, max abs err {(out - ref).abs().max():.4f}")
+    assert p > 35

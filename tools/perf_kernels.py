@@ -8,12 +8,12 @@ def child(kind):
     import torch
     from lightx2v_b200 import lib
     from tools.bringup import _time_cuda
-    if kind == "fmha":
+    if kind in ("fmha", "fmha3"):
         for (S, H) in ((75600, 40),):
             q = torch.randn(S, H, 128, device="cuda").bfloat16(); k = torch.randn(S, H, 128, device="cuda").bfloat16(); v = torch.randn(S, H, 128, device="cuda").bfloat16()
             o = torch.empty_like(q)
             ms = _time_cuda(lambda: lib.fmha(q, k, v, out=o), iters=3, warmup=1)
-            print(json.dumps({"case": f"fmha_S{S}_H{H}", "env": os.environ.get("B200_FMHA_POLY"), "ms": ms, "tflops": 4 * S * S * H * 128 / ms / 1e9}))
+            print(json.dumps({"case": f"fmha_S{S}_H{H}", "env": os.environ.get("B200_FMHA_POLY"), "ver": os.environ.get("B200_FMHA_VER"), "ms": ms, "tflops": 4 * S * S * H * 128 / ms / 1e9}))
             ref = torch.nn.functional.scaled_dot_product_attention(q[:2048].float().transpose(0, 1), k[:4096].float().transpose(0, 1), v[:4096].float().transpose(0, 1)).transpose(0, 1)
             got = lib.fmha(q[:2048], k[:4096], v[:4096])
             print(json.dumps({"case": "fmha_err", "env": os.environ.get("B200_FMHA_POLY"), "max_abs_err": float((got.float() - ref).abs().max())}))
@@ -39,7 +39,9 @@ if __name__ == "__main__":
         child(sys.argv[1])
     else:
         kind = sys.argv[1]
-        var, vals = {"fmha": ("B200_FMHA_POLY", ["0", "1", "2"]), "gemm": ("B200_GEMM_GROUP_M", ["16"]), "gemm8": ("B200_X", ["0"])}[kind]
+        var, vals = {"fmha": ("B200_FMHA_POLY", ["0", "1", "2"]), "fmha3": ("B200_FMHA_POLY", ["0", "1", "2"]), "gemm": ("B200_GEMM_GROUP_M", ["16"]), "gemm8": ("B200_X", ["0"])}[kind]
         for v in vals:
             env = dict(os.environ); env[var] = v
+            if kind == "fmha": env["B200_FMHA_VER"] = "2"
+            if kind == "fmha3": env["B200_FMHA_VER"] = "3"
             subprocess.run([sys.executable, os.path.abspath(__file__), kind, "child"], env=env, cwd=ROOT)
