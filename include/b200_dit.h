@@ -89,6 +89,23 @@ int b200_ln_modulate_fp8(const void* x, int64_t ldx, void* q8, int64_t ldq, floa
                          const void* ln_b, const void* scale, const void* shift, int64_t rows, int D, float eps,
                          b200_stream_t stream);
 
+/* ---- Ulysses sequence parallelism fused into the kernels (peer memory over NVLink / NVSwitch) ------------------------------ */
+
+/* q/k RMSNorm + RoPE (and a copy of v) of the local token shard qkv[rows, 3*D], every 16-byte vector stored directly into the
+ * peer GPU that owns its head: peers[r] is rank r's receive buffer [world*rows_per_rank, 3, H/world, 128] (peer-mapped device
+ * pointers, host array of `world` entries).  Replaces all2all_seq2head x3 (+ transposes + cuda.synchronize) of ulysses_attn
+ * (lightx2v/attentions/distributed/ulysses/attn.py:41-48, lightx2v/attentions/distributed/comm/all2all.py:7-44). */
+int b200_rms_rope_scatter(const void* qkv, int64_t ld, const void* wq, const void* wk, int64_t rows, int D, float eps,
+                          const void* cos_sin, int64_t rope_rows, void* const* peers, int world, int rank,
+                          int64_t rows_per_rank, b200_stream_t stream);
+
+/* b200_fmha_fwd_d128 whose epilogue scatters each query row to the rank that owns the token: row r -> peers[r / rows_per_rank]
+ * at [(r % rows_per_rank), head_offset + head, :] with row stride peer_stride_s.  Replaces the attention + all2all_head2seq of
+ * ulysses_attn (attn.py:51-88, all2all.py:48-89). */
+int b200_fmha_fwd_d128_scatter(const void* q, int64_t q_stride_s, const void* k, int64_t k_stride_s, const void* v,
+                               int64_t v_stride_s, void* const* peers, int world, int64_t rows_per_rank, int64_t peer_stride_s,
+                               int head_offset, int64_t sq, int64_t sk, int heads, float softmax_scale, b200_stream_t stream);
+
 /* ---- Wan 3-D causal VAE decoder (channels-last bf16 activations [T, H, W, C]) ---------------------------------------- */
 
 /* out[t,h,w,n] = bias[n] + sum_tap sum_c in[t+dt, h+dh, w+dw, c] * wt[n, tap*cin + c] (+ residual[t,h,w,n]) (clamped to [-1,1] if

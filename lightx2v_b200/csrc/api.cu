@@ -31,6 +31,12 @@ int rms_silu_cl(const void* x, void* y, const float* gamma, long long voxels, in
 int latent_to_cl(const float* z, void* out, const float* mean, const float* inv_std, long long voxels, int CZ, int CP,
                  cudaStream_t stream);
 int cl_to_video(const void* in, float* out, long long voxels, int CP, cudaStream_t stream);
+int rms_rope_scatter(const void* qkv, long long ld, const void* wq, const void* wk, long long rows, int D, float eps,
+                     const void* cos_sin, long long rope_rows, void* const* peers, int world, int rank,
+                     long long rows_per_rank, cudaStream_t stream);
+int fmha_fwd_d128_scatter(const void* q, long long q_stride_s, const void* k, long long k_stride_s, const void* v,
+                          long long v_stride_s, void* const* peers, int world, long long rows_per_rank, long long peer_stride_s,
+                          int head_offset, long long sq, long long sk, int heads, float softmax_scale, cudaStream_t stream);
 }  // namespace b200
 
 extern "C" {
@@ -103,6 +109,20 @@ int b200_latent_to_cl(const float* z, void* out, const float* mean, const float*
 
 int b200_cl_to_video(const void* in, float* out, int64_t voxels, int CP, b200_stream_t stream) {
   return b200::cl_to_video(in, out, voxels, CP, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int b200_rms_rope_scatter(const void* qkv, int64_t ld, const void* wq, const void* wk, int64_t rows, int D, float eps,
+                          const void* cos_sin, int64_t rope_rows, void* const* peers, int world, int rank,
+                          int64_t rows_per_rank, b200_stream_t stream) {
+  return b200::rms_rope_scatter(qkv, ld, wq, wk, rows, D, eps, cos_sin, rope_rows, peers, world, rank, rows_per_rank,
+                                reinterpret_cast<cudaStream_t>(stream));
+}
+
+int b200_fmha_fwd_d128_scatter(const void* q, int64_t q_stride_s, const void* k, int64_t k_stride_s, const void* v,
+                               int64_t v_stride_s, void* const* peers, int world, int64_t rows_per_rank, int64_t peer_stride_s,
+                               int head_offset, int64_t sq, int64_t sk, int heads, float softmax_scale, b200_stream_t stream) {
+  return b200::fmha_fwd_d128_scatter(q, q_stride_s, k, k_stride_s, v, v_stride_s, peers, world, rows_per_rank, peer_stride_s,
+                                     head_offset, sq, sk, heads, softmax_scale, reinterpret_cast<cudaStream_t>(stream));
 }
 
 }  // extern "C"

@@ -36,7 +36,21 @@ struct FmhaParams {
   float scale_log2;         // softmax_scale * log2(e)
   __nv_bfloat16* out;       // [sq, H, 128] (+ stride)
   long long o_stride_s;     // elements between consecutive rows of out
+  // Ulysses return exchange fused into the epilogue: when rows_per_rank > 0, query row r belongs to rank r / rows_per_rank and
+  // is stored straight into that peer's buffer peer_out[rank] at local row r % rows_per_rank, head (head_offset + head).
+  __nv_bfloat16* peer_out[8];
+  long long rows_per_rank;
+  int head_offset;
 };
+
+__device__ __forceinline__ __nv_bfloat16* fmha_out_row(const FmhaParams& p, int q_row, int head) {
+  if (p.rows_per_rank > 0) {
+    const int dest = (int)(q_row / p.rows_per_rank);
+    const long long local = q_row - (long long)dest * p.rows_per_rank;
+    return p.peer_out[dest] + local * p.o_stride_s + (long long)(p.head_offset + head) * FMHA_D;
+  }
+  return p.out + (long long)q_row * p.o_stride_s + (long long)head * FMHA_D;
+}
 
 __device__ __forceinline__ float ex2(float x) {
   float y;
@@ -63,7 +77,9 @@ __device__ __forceinline__ float2 exp2_poly2(float2 x) {
   return r;
 }
 
-template <int kPolyPairs>
+// kSplitP: P is published to the MMA warp in two 64-column halves (two mbarriers per tile) so that the first four PV
+// MMAs run while the second half of the exponentials is still being computed.
+template <int kPolyPairs, bool kSplitP>
 __global__ void __launch_bounds__(FMHA_THREADS, 1)
 fmha_fwd_d128_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                      const __grid_constant__ CUtensorMap tmV, const FmhaParams p) {
@@ -76,9 +92,9 @@ fmha_fwd_d128_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
   uint64_t* kv_full = bars + 1;          // [4]
   uint64_t* kv_empty = bars + 5;         // [4]
   uint64_t* s_full = bars + 9;           // [2]
-  uint64_t* p_full = bars + 11;          // [2]
-  uint64_t* o_full = bars + 13;          // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 15);
+  uint64_t* p_full = bars + 11;          // [2 tiles][2 halves] (the second half only with kSplitP)
+  uint64_t* o_full = bars + 15;          // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 17);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -99,7 +115,8 @@ fmha_fwd_d128_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     }
     for (int t = 0; t < 2; ++t) {
       mbar_init(&s_full[t], 1);
-      mbar_init(&p_full[t], 128);
+      mbar_init(&p_full[2 * t], 128);
+      mbar_init(&p_full[2 * t + 1], 128);
       mbar_init(&o_full[t], 1);
     }
     fence_mbar_init();
@@ -162,13 +179,26 @@ fmha_fwd_d128_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
           mma_f16_ss_w(d, a + off, kDescHiSw128, b + off, kDescHiSw128, idesc_qk, ks != 0 ? 1u : 0u);
         }
       };
-      auto issue_pv = [&](int t, int vstage, uint32_t accumulate) {
+      // kv = 128 in steps of 16 rows (16 x 128 B = 2048 B); P: 8 columns per step; ks in [ks0, ks1)
+      auto issue_pv_range = [&](int t, int vstage, uint32_t accumulate, int ks0, int ks1) {
         const uint32_t b = desc_lo_mnmajor(kv_addr + vstage * FMHA_TILE_BYTES, FMHA_PANEL_BYTES);
         const uint32_t d = t ? tO1 : tO0;
         const uint32_t a = t ? tS1 : tS0;
 #pragma unroll
-        for (int ks = 0; ks < 8; ++ks) {  // kv = 128 in steps of 16 rows (16 x 128 B = 2048 B); P: 8 columns per step
-          mma_f16_ts_w(d, a + ks * 8, b + ks * (2048 >> 4), kDescHiSw128, idesc_pv, ks != 0 ? 1u : accumulate);
+        for (int ks = 0; ks < 8; ++ks) {
+          if (ks >= ks0 && ks < ks1) mma_f16_ts_w(d, a + ks * 8, b + ks * (2048 >> 4), kDescHiSw128, idesc_pv, ks != 0 ? 1u : accumulate);
+        }
+      };
+      auto issue_pv = [&](int t, int vstage, uint32_t accumulate, uint32_t parity) {
+        mbar_wait(&p_full[2 * t], parity);
+        tc_fence_after();
+        if constexpr (kSplitP) {
+          issue_pv_range(t, vstage, accumulate, 0, 4);
+          mbar_wait(&p_full[2 * t + 1], parity);
+          tc_fence_after();
+          issue_pv_range(t, vstage, accumulate, 4, 8);
+        } else {
+          issue_pv_range(t, vstage, accumulate, 0, 8);
         }
       };
 
@@ -207,9 +237,7 @@ fmha_fwd_d128_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         const uint32_t pj = j & 1;
         const uint32_t acc = j > 0 ? 1u : 0u;
         // ---- tile 0
-        mbar_wait(&p_full[0], pj);
-        tc_fence_after();
-        issue_pv(0, vstage, acc);
+        issue_pv(0, vstage, acc, pj);
         if (has_next) {
           issue_qk(0, kstage);
           tc_commit_w(&s_full[0]);
@@ -217,9 +245,7 @@ fmha_fwd_d128_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
           tc_commit_w(&o_full[0]);
         }
         // ---- tile 1
-        mbar_wait(&p_full[1], pj);
-        tc_fence_after();
-        issue_pv(1, vstage, acc);
+        issue_pv(1, vstage, acc, pj);
         tc_commit_w(&kv_empty[vstage]);
         if (has_next) {
           issue_qk(1, kstage);
@@ -320,14 +346,29 @@ fmha_fwd_d128_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
           acc[j] = __fadd2_rn(acc[j], e);
           pk[i] = pack_bf16(e.x, e.y);
         }
+        if constexpr (kSplitP) {
+          if (g == 7) {               // columns 0..63 done: publish the first half of P
+            tmem_st_x32(tS + 0, pk + 0);
+            tmem_st_wait();
+            tc_fence_before();
+            mbar_arrive(&p_full[2 * t]);
+          }
+        }
       }
       const float2 a01 = __fadd2_rn(acc[0], acc[1]), a23 = __fadd2_rn(acc[2], acc[3]);
       l_sum += (a01.x + a01.y) + (a23.x + a23.y);
-      tmem_st_x32(tS + 0, pk + 0);    // P (bf16 pairs) overwrites the first 64 columns of S
-      tmem_st_x32(tS + 32, pk + 32);
-      tmem_st_wait();
-      tc_fence_before();
-      mbar_arrive(&p_full[t]);
+      if constexpr (kSplitP) {
+        tmem_st_x32(tS + 32, pk + 32);
+        tmem_st_wait();
+        tc_fence_before();
+        mbar_arrive(&p_full[2 * t + 1]);
+      } else {
+        tmem_st_x32(tS + 0, pk + 0);    // P (bf16 pairs) overwrites the first 64 columns of S
+        tmem_st_x32(tS + 32, pk + 32);
+        tmem_st_wait();
+        tc_fence_before();
+        mbar_arrive(&p_full[2 * t]);
+      }
     }
 
     // ---- epilogue: O / l -> bf16 -> global
@@ -335,7 +376,7 @@ fmha_fwd_d128_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     tc_fence_after();
     const float inv_l = 1.0f / l_sum;
     const int q_row = q0 + t * FMHA_BLOCK_Q + row;
-    __nv_bfloat16* orow = p.out + (long long)q_row * p.o_stride_s + (long long)head * FMHA_D;
+    __nv_bfloat16* orow = q_row < p.sq ? fmha_out_row(p, q_row, head) : p.out;
 #pragma unroll 1
     for (int c = 0; c < 128; c += 32) {
       uint32_t o[32];
@@ -640,7 +681,7 @@ fmha_fwd_d128_v3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
     mbar_wait(&o_full[t], 0);
     tc_fence_after();
     const int q_row = q0 + t * FMHA_BLOCK_Q + row;
-    __nv_bfloat16* orow = p.out + (long long)q_row * p.o_stride_s + (long long)head * FMHA_D + hf * 64;
+    __nv_bfloat16* orow = (q_row < p.sq ? fmha_out_row(p, q_row, head) : p.out) + hf * 64;
 #pragma unroll 1
     for (int c = 0; c < 64; c += 32) {
       uint32_t o[32];
@@ -676,9 +717,16 @@ static int encode_qkv_map(CUtensorMap* tm, const void* base, long long rows, int
   return encode_tmap(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, base, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
 }
 
-int fmha_fwd_d128(const void* q, long long q_stride_s, const void* k, long long k_stride_s, const void* v,
-                  long long v_stride_s, void* out, long long o_stride_s, long long sq, long long sk, int heads,
-                  float softmax_scale, cudaStream_t stream) {
+int fmha_fwd_d128_impl(const void* q, long long q_stride_s, const void* k, long long k_stride_s, const void* v,
+                       long long v_stride_s, void* out, long long o_stride_s, long long sq, long long sk, int heads,
+                       float softmax_scale, void* const* peers, int world, long long rows_per_rank, int head_offset,
+                       cudaStream_t stream) {
+  if (peers != nullptr) {
+    B200_CHECK_ARG(world >= 1 && world <= 8 && rows_per_rank > 0 && sq <= world * rows_per_rank,
+                   "b200_fmha_fwd_d128_scatter: bad world %d / rows_per_rank %lld for sq %lld", world, rows_per_rank, sq);
+    for (int i = 0; i < world; ++i) B200_CHECK_ARG(peers[i] != nullptr, "b200_fmha_fwd_d128_scatter: null peer pointer %d", i);
+    out = peers[0];
+  }
   B200_CHECK_ARG(q && k && v && out, "b200_fmha_fwd_d128: null pointer");
   B200_CHECK_ARG(sq > 0 && sk > 0 && heads > 0, "b200_fmha_fwd_d128: empty problem sq=%lld sk=%lld heads=%d", sq, sk,
                  heads);
@@ -703,6 +751,9 @@ int fmha_fwd_d128(const void* q, long long q_stride_s, const void* k, long long 
   p.scale_log2 = softmax_scale * 1.4426950408889634f;
   p.out = reinterpret_cast<__nv_bfloat16*>(out);
   p.o_stride_s = o_stride_s;
+  p.rows_per_rank = peers ? rows_per_rank : 0;
+  p.head_offset = head_offset;
+  for (int i = 0; i < 8; ++i) p.peer_out[i] = (peers && i < world) ? reinterpret_cast<__nv_bfloat16*>(peers[i]) : nullptr;
 
   // fraction of exp2 evaluated by the FMA-pipe polynomial: B200_FMHA_POLY = 0..3 pairs out of every 4 (default 1)
   static int poly = -1;
@@ -715,8 +766,8 @@ int fmha_fwd_d128(const void* q, long long q_stride_s, const void* k, long long 
   static int ver = -1;
   if (ver < 0) {
     const char* e = getenv("B200_FMHA_VER");
-    ver = e ? atoi(e) : 3;
-    if (ver != 2 && ver != 3) ver = 3;
+    ver = e ? atoi(e) : 4;     // 2: one softmax warpgroup per tile (1.23 PF); 3: two per tile (1.14 PF); 4: v2 + split-P publication (1.28 PF, default)
+    if (ver < 2 || ver > 4) ver = 4;
   }
   auto launch = [&](auto kern, int threads, int smem_bytes) -> int {
     B200_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
@@ -731,17 +782,38 @@ int fmha_fwd_d128(const void* q, long long q_stride_s, const void* k, long long 
       case 3: rc2 = launch(fmha_fwd_d128_v3_kernel<3>, FMHA3_THREADS, FMHA3_SMEM_BYTES); break;
       default: rc2 = launch(fmha_fwd_d128_v3_kernel<1>, FMHA3_THREADS, FMHA3_SMEM_BYTES); break;
     }
+  } else if (ver == 4) {
+    switch (poly) {
+      case 0: rc2 = launch(fmha_fwd_d128_kernel<0, true>, FMHA_THREADS, FMHA_SMEM_BYTES); break;
+      case 2: rc2 = launch(fmha_fwd_d128_kernel<2, true>, FMHA_THREADS, FMHA_SMEM_BYTES); break;
+      default: rc2 = launch(fmha_fwd_d128_kernel<1, true>, FMHA_THREADS, FMHA_SMEM_BYTES); break;
+    }
   } else {
     switch (poly) {
-      case 0: rc2 = launch(fmha_fwd_d128_kernel<0>, FMHA_THREADS, FMHA_SMEM_BYTES); break;
-      case 2: rc2 = launch(fmha_fwd_d128_kernel<2>, FMHA_THREADS, FMHA_SMEM_BYTES); break;
-      case 3: rc2 = launch(fmha_fwd_d128_kernel<3>, FMHA_THREADS, FMHA_SMEM_BYTES); break;
-      default: rc2 = launch(fmha_fwd_d128_kernel<1>, FMHA_THREADS, FMHA_SMEM_BYTES); break;
+      case 0: rc2 = launch(fmha_fwd_d128_kernel<0, false>, FMHA_THREADS, FMHA_SMEM_BYTES); break;
+      case 2: rc2 = launch(fmha_fwd_d128_kernel<2, false>, FMHA_THREADS, FMHA_SMEM_BYTES); break;
+      case 3: rc2 = launch(fmha_fwd_d128_kernel<3, false>, FMHA_THREADS, FMHA_SMEM_BYTES); break;
+      default: rc2 = launch(fmha_fwd_d128_kernel<1, false>, FMHA_THREADS, FMHA_SMEM_BYTES); break;
     }
   }
   if (rc2) return rc2;
   B200_CHECK_CUDA(cudaGetLastError());
   return B200_OK;
+}
+
+int fmha_fwd_d128(const void* q, long long q_stride_s, const void* k, long long k_stride_s, const void* v,
+                  long long v_stride_s, void* out, long long o_stride_s, long long sq, long long sk, int heads,
+                  float softmax_scale, cudaStream_t stream) {
+  return fmha_fwd_d128_impl(q, q_stride_s, k, k_stride_s, v, v_stride_s, out, o_stride_s, sq, sk, heads, softmax_scale, nullptr,
+                            0, 0, 0, stream);
+}
+
+int fmha_fwd_d128_scatter(const void* q, long long q_stride_s, const void* k, long long k_stride_s, const void* v,
+                          long long v_stride_s, void* const* peers, int world, long long rows_per_rank, long long peer_stride_s,
+                          int head_offset, long long sq, long long sk, int heads, float softmax_scale, cudaStream_t stream) {
+  B200_CHECK_ARG(peers != nullptr, "b200_fmha_fwd_d128_scatter: null peer table");
+  return fmha_fwd_d128_impl(q, q_stride_s, k, k_stride_s, v, v_stride_s, nullptr, peer_stride_s, sq, sk, heads, softmax_scale, peers,
+                            world, rows_per_rank, head_offset, stream);
 }
 
 }  // namespace b200

@@ -363,4 +363,169 @@ int rms_rope(void* x0, long long ld0, const void* w0, void* x1, long long ld1, c
   return B200_OK;
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// HunyuanVideo flavour: RMSNorm PER HEAD (over the 128 elements of one head, weight [128]) on q and k laid out [rows, H, 128]
+// (lightx2v/models/networks/hunyuan/infer/transformer_infer.py:289-292, 342-343; bf16 chain of utils_bf16.py:5-8), then
+// x*cos + rotate_half(x)*sin in bf16 arithmetic with bf16 cos/sin (utils_bf16.py:11-31) for rows < rope_rows (image tokens).
+// 16 lanes own one head (8 elements each); a 128-thread CTA covers 8 heads per pass.
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(ROW_THREADS)
+rms_rope_heads_kernel(RmsRopeArgs a, int H, float eps, const float2* __restrict__ cs, long long rope_rows) {
+  const long long row = blockIdx.x;
+  const int which = blockIdx.y;
+  const int l16 = threadIdx.x & 15;
+  __nv_bfloat16* xrow = a.x[which] + row * a.ld[which];
+  float w[8];
+  unpack8(__ldg(reinterpret_cast<const uint4*>(a.w[which]) + l16), w);
+  const bool rotate = cs != nullptr && row < rope_rows;
+  float2 c[4];
+  if (rotate) {
+#pragma unroll
+    for (int e = 0; e < 4; ++e) c[e] = __ldg(cs + row * 64 + l16 * 4 + e);
+  }
+  for (int head = threadIdx.x >> 4; head < H; head += ROW_THREADS / 16) {
+    uint4* p = reinterpret_cast<uint4*>(xrow + head * 128) + l16;
+    float f[8];
+    unpack8(*p, f);
+    float ssq = 0.f;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) ssq += bf16_round(f[e] * f[e]);
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) ssq += __shfl_xor_sync(0xffffffffu, ssq, o);
+    float ms = bf16_round(ssq / 128.0f);
+    ms = bf16_round(ms + eps);
+    const float rinv = bf16_round(rsqrtf(ms));
+#pragma unroll
+    for (int e = 0; e < 8; ++e) f[e] = bf16_round(bf16_round(f[e] * rinv) * w[e]);
+    if (rotate) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float re = f[2 * e], im = f[2 * e + 1];
+        // x*cos + rotate_half(x)*sin with rotate_half = (-im, re); every product and the sum are bf16 tensors
+        f[2 * e] = bf16_round(re * c[e].x) + bf16_round(-im * c[e].y);
+        f[2 * e + 1] = bf16_round(im * c[e].x) + bf16_round(re * c[e].y);
+      }
+    }
+    *p = pack8(f);
+  }
+}
+
+int rms_rope_heads(void* x0, long long ld0, const void* w0, void* x1, long long ld1, const void* w1, long long rows,
+                   int H, float eps, const void* cos_sin, long long rope_rows, cudaStream_t stream) {
+  B200_CHECK_ARG(x0 && w0, "b200_rms_rope_heads: null pointer");
+  B200_CHECK_ARG(rows > 0 && H > 0, "b200_rms_rope_heads: empty problem");
+  B200_CHECK_ARG(ld0 % 8 == 0 && ld0 >= 128LL * H && (x1 == nullptr || (ld1 % 8 == 0 && ld1 >= 128LL * H && w1)),
+                 "b200_rms_rope_heads: bad leading dimension / missing weight");
+  RmsRopeArgs a;
+  a.x[0] = reinterpret_cast<__nv_bfloat16*>(x0);
+  a.w[0] = reinterpret_cast<const __nv_bfloat16*>(w0);
+  a.ld[0] = ld0;
+  a.x[1] = reinterpret_cast<__nv_bfloat16*>(x1);
+  a.w[1] = reinterpret_cast<const __nv_bfloat16*>(w1);
+  a.ld[1] = ld1;
+  dim3 grid((unsigned)rows, x1 ? 2 : 1);
+  rms_rope_heads_kernel<<<grid, ROW_THREADS, 0, stream>>>(a, H, eps, reinterpret_cast<const float2*>(cos_sin), rope_rows);
+  B200_CHECK_CUDA(cudaGetLastError());
+  return B200_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Ulysses head scatter fused into the q/k RMSNorm + RoPE pass (and a plain copy for v): instead of normalising in
+// place and then packing + all-to-all'ing, every 16-byte vector is stored STRAIGHT INTO THE PEER GPU that owns its head
+// (NVLink P2P stores through NVSwitch), in the layout the attention kernel reads: recv[dest][token_global][which][h % hp][128].
+// Replaces all2all_seq2head x3 + the .contiguous() transposes + torch.cuda.synchronize()
+// (lightx2v/attentions/distributed/ulysses/attn.py:41-48, comm/all2all.py:7-44).
+// ---------------------------------------------------------------------------------------------------------
+struct ScatterArgs {
+  __nv_bfloat16* peer[8];    // peer-mapped base of each rank's receive buffer [world*rows_per_rank, 3, hp, 128]
+  int world, rank, hp;
+  long long rows_per_rank;
+};
+
+__global__ void __launch_bounds__(ROW_THREADS)
+rms_rope_scatter_kernel(const __nv_bfloat16* __restrict__ qkv, long long ld, const __nv_bfloat16* __restrict__ wq,
+                        const __nv_bfloat16* __restrict__ wk, int D, float eps, const float2* __restrict__ cs,
+                        long long rope_rows, ScatterArgs sc) {
+  __shared__ float red[4];
+  const long long row = blockIdx.x;
+  const int which = blockIdx.y;                         // 0 = q, 1 = k, 2 = v
+  const int nvec = D >> 3;
+  const uint4* xr = reinterpret_cast<const uint4*>(qkv + row * ld + (long long)which * D);
+  const uint4* wr = reinterpret_cast<const uint4*>(which == 0 ? wq : wk);
+  const long long token = (long long)sc.rank * sc.rows_per_rank + row;
+  uint4 raw[ROW_MAX_VEC];
+  float ssq = 0.f;
+#pragma unroll
+  for (int i = 0; i < ROW_MAX_VEC; ++i) {
+    const int v = threadIdx.x + i * ROW_THREADS;
+    if (v < nvec) {
+      raw[i] = xr[v];
+      float f[8];
+      unpack8(raw[i], f);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) ssq += bf16_round(f[e] * f[e]);
+    }
+  }
+  float rinv = 1.0f;
+  if (which < 2) {                                      // block-uniform branch
+    float ms = bf16_round(block_sum_128(ssq, red) / (float)D);
+    ms = bf16_round(ms + eps);
+    rinv = bf16_round(rsqrtf(ms));
+  }
+  const bool rotate = which < 2 && row < rope_rows;
+  const float2* csr = cs + row * 64;
+#pragma unroll
+  for (int i = 0; i < ROW_MAX_VEC; ++i) {
+    const int v = threadIdx.x + i * ROW_THREADS;
+    if (v < nvec) {
+      float f[8];
+      unpack8(raw[i], f);
+      if (which < 2) {
+        float w[8];
+        unpack8(__ldg(wr + v), w);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) f[e] = bf16_round(bf16_round(f[e] * rinv) * w[e]);
+        if (rotate) {
+          const int pair0 = ((v * 8) & 127) >> 1;
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float2 c = __ldg(csr + pair0 + e);
+            const float re = f[2 * e], im = f[2 * e + 1];
+            f[2 * e] = re * c.x - im * c.y;
+            f[2 * e + 1] = re * c.y + im * c.x;
+          }
+        }
+      }
+      const int head = v >> 4;                          // 16 vectors of 8 elements per 128-wide head
+      const int dest = head / sc.hp;
+      __nv_bfloat16* dst = sc.peer[dest] + ((token * 3 + which) * sc.hp + (head - dest * sc.hp)) * 128 + (v & 15) * 8;
+      *reinterpret_cast<uint4*>(dst) = pack8(f);
+    }
+  }
+}
+
+int rms_rope_scatter(const void* qkv, long long ld, const void* wq, const void* wk, long long rows, int D, float eps,
+                     const void* cos_sin, long long rope_rows, void* const* peers, int world, int rank,
+                     long long rows_per_rank, cudaStream_t stream) {
+  B200_CHECK_ARG(qkv && wq && wk && cos_sin && peers, "b200_rms_rope_scatter: null pointer");
+  B200_CHECK_ARG(world >= 1 && world <= 8 && rank >= 0 && rank < world, "b200_rms_rope_scatter: world %d / rank %d out of range", world, rank);
+  B200_CHECK_ARG(rows > 0 && rows <= rows_per_rank && D % 128 == 0 && D <= ROW_THREADS * ROW_MAX_VEC * 8 && (D / 128) % world == 0,
+                 "b200_rms_rope_scatter: bad shape rows=%lld D=%d world=%d", rows, D, world);
+  B200_CHECK_ARG(ld % 8 == 0 && ld >= 3LL * D, "b200_rms_rope_scatter: qkv leading dimension must cover 3*D");
+  ScatterArgs sc;
+  for (int i = 0; i < 8; ++i) sc.peer[i] = i < world ? reinterpret_cast<__nv_bfloat16*>(peers[i]) : nullptr;
+  for (int i = 0; i < world; ++i) B200_CHECK_ARG(peers[i] != nullptr, "b200_rms_rope_scatter: null peer pointer %d", i);
+  sc.world = world;
+  sc.rank = rank;
+  sc.hp = D / 128 / world;
+  sc.rows_per_rank = rows_per_rank;
+  dim3 grid((unsigned)rows, 3);
+  rms_rope_scatter_kernel<<<grid, ROW_THREADS, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(qkv), ld,
+                                                          reinterpret_cast<const __nv_bfloat16*>(wq),
+                                                          reinterpret_cast<const __nv_bfloat16*>(wk), D, eps,
+                                                          reinterpret_cast<const float2*>(cos_sin), rope_rows, sc);
+  B200_CHECK_CUDA(cudaGetLastError());
+  return B200_OK;
+}
+
 }  // namespace b200

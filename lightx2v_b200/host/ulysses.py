@@ -103,6 +103,64 @@ class UlyssesAttention:
         return unpack_out_from_a2a(orecv, out)
 
 
+class FusedUlyssesAttention:
+    """Ulysses exchange fused INTO the kernels over NVLink peer memory (no NCCL on the data path, no pack/unpack copies):
+
+      rms_rope_scatter : q/k RMSNorm + RoPE (+ v copy) of the local shard, each 16-byte vector stored straight into the
+                         receive buffer of the rank that owns its head            (replaces 3 all-to-alls + transposes)
+      fmha_scatter     : attention over all tokens for the local heads, the epilogue stores each output row straight into
+                         the buffer of the rank that owns the token               (replaces the return all-to-all)
+
+    Buffers are torch symmetric-memory allocations (peer-mapped through NVSwitch); two stream-ordered cross-GPU barriers per
+    block order the exchanges (writes of everyone -> my reads; my reads -> everyone's next writes).  Interface: called by
+    WanTransformerInfer with the fused QKV buffer instead of q/k/v."""
+
+    def __init__(self, total_rows: int, rows_per_rank: int, num_heads: int, device, group=None):
+        import torch.distributed._symmetric_memory as symm_mem
+
+        from .. import lib
+
+        self.lib = lib
+        self.group = group if group is not None else dist.group.WORLD
+        self.world = dist.get_world_size(self.group)
+        self.rank = dist.get_rank(self.group)
+        if num_heads % self.world != 0:
+            raise ValueError(f"Ulysses needs num_heads ({num_heads}) divisible by world size ({self.world})")
+        self.total_rows, self.s, self.H = total_rows, rows_per_rank, num_heads
+        self.hp = num_heads // self.world
+        # receive buffer of the head scatter: all tokens (incl. padding rows), q|k|v of my heads
+        self.recv = symm_mem.empty((self.world * self.s, 3, self.hp, 128), dtype=torch.bfloat16, device=device)
+        # attention output for my tokens, all heads (written by every rank)
+        self.attn = symm_mem.empty((self.s, num_heads, 128), dtype=torch.bfloat16, device=device)
+        self.recv_h = symm_mem.rendezvous(self.recv, self.group)
+        self.attn_h = symm_mem.rendezvous(self.attn, self.group)
+        self.recv_ptrs = list(self.recv_h.buffer_ptrs)
+        self.attn_ptrs = list(self.attn_h.buffer_ptrs)
+        self.fused = True
+
+    def run(self, qkv, wq, wk, cos_sin, eps) -> torch.Tensor:
+        """qkv [s, 3*D] local shard (pre-norm) -> attention output for my tokens [s, H, 128] (a view of the symmetric buffer)."""
+        lib = self.lib
+        lib.rms_rope_scatter(qkv, wq, wk, cos_sin, self.recv_ptrs, self.rank, self.s, eps=eps)
+        self.recv_h.barrier(channel=0)                                   # everyone's q/k/v for my heads have landed
+        full = self.recv[: self.total_rows]
+        lib.fmha_scatter(full[:, 0], full[:, 1], full[:, 2], self.attn_ptrs, self.s, self.H * 128, self.rank * self.hp)
+        self.attn_h.barrier(channel=1)                                   # everyone's outputs for my tokens have landed
+        return self.attn
+
+
+def parallelize_wan_fused(model, total_rows: int, group=None):
+    """Install the peer-memory Ulysses path on a host.wan_model.WanModel."""
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    ti = model.transformer_infer
+    s = shard_rows(total_rows, world)
+    ti.parallel_attention = FusedUlyssesAttention(total_rows, s, ti.num_heads, torch.device("cuda", torch.cuda.current_device()), group)
+    ti.sp_rank, ti.sp_world = rank, world
+    model.pre_process = lambda x: pre_process(x, rank, world)
+    model.post_process = lambda x: post_process(x, total_rows, group)
+    return model
+
+
 def parallelize_wan(model, total_rows: int, attention_fn: Callable, group=None):
     """Install the SP hooks on a host.wan_model.WanModel (wrap.py:53-71 does this by monkey-patching)."""
     world, rank = dist.get_world_size(group), dist.get_rank(group)

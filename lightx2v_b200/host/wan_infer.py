@@ -203,15 +203,20 @@ class WanTransformerInfer:
         self._linear(None, n1, w=c.wqkv, b=c.bqkv, ws=c.sqkv, out=qkv)
         q, k, v = qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:]
         cs = self._rope_table(grid_sizes, freqs, S, dev)
-        lib.rms_rope_(q, weights.self_attn_norm_q.weight, k, weights.self_attn_norm_k.weight, eps=weights.self_attn_norm_q.eps,
-                      cos_sin=cs, rope_rows=min(S, cs.shape[0]))
         H, d = self.num_heads, self.head_dim
-        q3, k3, v3 = (t.unflatten(1, (H, d)) for t in (q, k, v))
-        attn = self._buf("a", (S, D), dev).view(S, H, d)   # the LN scratch is dead after the QKV GEMM: reuse it for the attention output
-        if self.parallel_attention is None:
-            lib.fmha(q3, k3, v3, out=attn)
+        if getattr(self.parallel_attention, "fused", False):
+            # Ulysses over peer memory: norm + RoPE + head scatter in one kernel, attention with a token-scatter epilogue
+            attn = self.parallel_attention.run(qkv, weights.self_attn_norm_q.weight, weights.self_attn_norm_k.weight, cs,
+                                               weights.self_attn_norm_q.eps)
         else:
-            attn = self.parallel_attention(q=q3, k=k3, v=v3, out=attn)
+            lib.rms_rope_(q, weights.self_attn_norm_q.weight, k, weights.self_attn_norm_k.weight, eps=weights.self_attn_norm_q.eps,
+                          cos_sin=cs, rope_rows=min(S, cs.shape[0]))
+            q3, k3, v3 = (t.unflatten(1, (H, d)) for t in (q, k, v))
+            attn = self._buf("a", (S, D), dev).view(S, H, d)   # the LN scratch is dead after the QKV GEMM: reuse it for the attention output
+            if self.parallel_attention is None:
+                lib.fmha(q3, k3, v3, out=attn)
+            else:
+                attn = self.parallel_attention(q=q3, k=k3, v=v3, out=attn)
         attn2 = attn.reshape(S, D)
         if gate_msa is None:
             return self._linear(weights.self_attn_o, attn2)

@@ -28,6 +28,8 @@ SIGNATURES = {
     "b200_gemm_fp8": (_i32, [_ptr, _i64, _ptr, _i64, _ptr, _i64, _ptr, _ptr, _ptr, _ptr, _i64, _i64, _i64, _i32, _i32, _i32, _ptr]),
     "b200_quant_fp8_per_token": (_i32, [_ptr, _i64, _ptr, _i64, _ptr, _i64, _i32, _ptr]),
     "b200_ln_modulate_fp8": (_i32, [_ptr, _i64, _ptr, _i64, _ptr, _ptr, _ptr, _ptr, _ptr, _i64, _i32, _f32, _ptr]),
+    "b200_rms_rope_scatter": (_i32, [_ptr, _i64, _ptr, _ptr, _i64, _i32, _f32, _ptr, _i64, _ptr, _i32, _i32, _i64, _ptr]),
+    "b200_fmha_fwd_d128_scatter": (_i32, [_ptr, _i64, _ptr, _i64, _ptr, _i64, _ptr, _i32, _i64, _i64, _i32, _i64, _i64, _i32, _f32, _ptr]),
     "b200_conv3d_cl": (_i32, [_ptr, _i64, _i64, _i64, _ptr, _ptr, _ptr, _i64, _i64, _i64, _ptr, _i64, _i64, _i64, _i32, _i32, _i32, _i32, _i32,
                               _i32, _ptr, _i32, _ptr]),
     "b200_rms_silu_cl": (_i32, [_ptr, _ptr, _ptr, _i64, _i32, _i32, _ptr]),
@@ -252,3 +254,36 @@ def cl_to_video(x: torch.Tensor) -> torch.Tensor:
     rc = load().b200_cl_to_video(x.contiguous().data_ptr(), out.data_ptr(), T * H * W, CP, _stream())
     _check(rc, "b200_cl_to_video")
     return out
+
+
+# ---------------------------------------------------------------------------------------------------------------- Ulysses over peer memory
+def _ptr_table(ptrs):
+    return (ctypes.c_void_p * len(ptrs))(*[int(p) for p in ptrs])
+
+
+def rms_rope_scatter(qkv: torch.Tensor, wq: torch.Tensor, wk: torch.Tensor, cos_sin: torch.Tensor, peer_ptrs, rank: int, rows_per_rank: int,
+                     *, eps: float = 1e-6, rope_rows: Optional[int] = None) -> None:
+    """qkv [rows, 3*D] (local shard) -> RMSNorm+RoPE(q,k), copy(v), stored into each head owner's buffer peer_ptrs[r]
+    laid out [world*rows_per_rank, 3, H/world, 128]."""
+    _req(qkv, "qkv")
+    rows, D3 = qkv.shape
+    D = D3 // 3
+    tbl = _ptr_table(peer_ptrs)
+    rr = rows if rope_rows is None else rope_rows
+    rc = load().b200_rms_rope_scatter(qkv.data_ptr(), qkv.stride(0), wq.data_ptr(), wk.data_ptr(), rows, D, eps, cos_sin.data_ptr(), rr,
+                                      ctypes.cast(tbl, ctypes.c_void_p), len(peer_ptrs), rank, rows_per_rank, _stream())
+    _check(rc, "b200_rms_rope_scatter")
+
+
+def fmha_scatter(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, peer_ptrs, rows_per_rank: int, peer_stride_s: int, head_offset: int,
+                 *, softmax_scale: Optional[float] = None) -> None:
+    """Attention over all tokens for this rank's heads; output rows stored into the token owners' buffers."""
+    for n, t in (("q", q), ("k", k), ("v", v)):
+        _req(t, n)
+    sq, H, _ = q.shape
+    scale = 128 ** -0.5 if softmax_scale is None else softmax_scale
+    tbl = _ptr_table(peer_ptrs)
+    rc = load().b200_fmha_fwd_d128_scatter(q.data_ptr(), q.stride(0), k.data_ptr(), k.stride(0), v.data_ptr(), v.stride(0),
+                                           ctypes.cast(tbl, ctypes.c_void_p), len(peer_ptrs), rows_per_rank, peer_stride_s, head_offset,
+                                           sq, k.shape[0], H, scale, _stream())
+    _check(rc, "b200_fmha_fwd_d128_scatter")
