@@ -89,6 +89,13 @@ int b200_ln_modulate_fp8(const void* x, int64_t ldx, void* q8, int64_t ldq, floa
                          const void* ln_b, const void* scale, const void* shift, int64_t rows, int D, float eps,
                          b200_stream_t stream);
 
+/* In-place per-head RMSNorm of x0 (and x1) laid out [rows, H, 128] (weight [128], bf16 chain), then for rows < rope_rows
+ * x*cos + rotate_half(x)*sin in bf16 arithmetic with table cos_sin[row, 64] float2 (bf16-representable values).  HunyuanVideo's
+ * q/k path: RMSWeight over the head dim + apply_rotary_emb (lightx2v/models/networks/hunyuan/infer/transformer_infer.py:289-295,
+ * 342-347; lightx2v/models/networks/hunyuan/infer/utils_bf16.py:5-31). */
+int b200_rms_rope_heads(void* x0, int64_t ld0, const void* w0, void* x1, int64_t ld1, const void* w1, int64_t rows, int H,
+                        float eps, const void* cos_sin, int64_t rope_rows, b200_stream_t stream);
+
 /* ---- Ulysses sequence parallelism fused into the kernels (peer memory over NVLink / NVSwitch) ------------------------------ */
 
 /* q/k RMSNorm + RoPE (and a copy of v) of the local token shard qkv[rows, 3*D], every 16-byte vector stored directly into the

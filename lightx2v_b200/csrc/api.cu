@@ -37,6 +37,8 @@ int rms_rope_scatter(const void* qkv, long long ld, const void* wq, const void* 
 int fmha_fwd_d128_scatter(const void* q, long long q_stride_s, const void* k, long long k_stride_s, const void* v,
                           long long v_stride_s, void* const* peers, int world, long long rows_per_rank, long long peer_stride_s,
                           int head_offset, long long sq, long long sk, int heads, float softmax_scale, cudaStream_t stream);
+int rms_rope_heads(void* x0, long long ld0, const void* w0, void* x1, long long ld1, const void* w1, long long rows,
+                   int H, float eps, const void* cos_sin, long long rope_rows, cudaStream_t stream);
 }  // namespace b200
 
 extern "C" {
@@ -123,6 +125,11 @@ int b200_fmha_fwd_d128_scatter(const void* q, int64_t q_stride_s, const void* k,
                                int head_offset, int64_t sq, int64_t sk, int heads, float softmax_scale, b200_stream_t stream) {
   return b200::fmha_fwd_d128_scatter(q, q_stride_s, k, k_stride_s, v, v_stride_s, peers, world, rows_per_rank, peer_stride_s,
                                      head_offset, sq, sk, heads, softmax_scale, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int b200_rms_rope_heads(void* x0, int64_t ld0, const void* w0, void* x1, int64_t ld1, const void* w1, int64_t rows, int H,
+                        float eps, const void* cos_sin, int64_t rope_rows, b200_stream_t stream) {
+  return b200::rms_rope_heads(x0, ld0, w0, x1, ld1, w1, rows, H, eps, cos_sin, rope_rows, reinterpret_cast<cudaStream_t>(stream));
 }
 
 }  // extern "C"

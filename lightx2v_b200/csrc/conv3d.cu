@@ -28,12 +28,20 @@ constexpr int CONV_MAX_TAPS = 27;
 constexpr int CONV_A_CHUNK_BYTES = CONV_BLOCK_M * CONV_KC * 2;   // 8 KB
 constexpr int CONV_STAGING_BYTES = CONV_BLOCK_M * 64 * 2;        // 16 KB (64 output channels per store chunk)
 
+// M_SUB sub-tiles of 128 voxels (32 w x 4 h each, stacked along h) share one weight tile: with the narrow N of the VAE
+// (96 / 192 output channels) a 128-voxel tile gives only ~290 tensor cycles per pipeline stage, far below the TMA round trip;
+// two sub-tiles double the MMA work per byte of weight traffic and per barrier.
 template <int BLOCK_N>
 struct ConvCfg {
+  static constexpr int kMSub = (BLOCK_N <= 96) ? 2 : 1;
   static constexpr int kBChunkBytes = BLOCK_N * CONV_KC * 2;
-  static constexpr int kStageBytes = CONV_CHUNKS * (CONV_A_CHUNK_BYTES + kBChunkBytes);
-  static constexpr int kTmemCols = (2 * BLOCK_N <= 128) ? 128 : (2 * BLOCK_N <= 256 ? 256 : 512);
-  static constexpr int kSmemBytes = CONV_STAGES * kStageBytes + 2 * CONV_STAGING_BYTES + 1024 + 256;
+  static constexpr int kStageBytes = CONV_CHUNKS * (kMSub * CONV_A_CHUNK_BYTES + kBChunkBytes);
+  static constexpr int kAccCols = kMSub * BLOCK_N;                       // TMEM columns of one accumulator stage
+  static constexpr int kTmemCols = (2 * kAccCols <= 128) ? 128 : (2 * kAccCols <= 256 ? 256 : 512);
+  // epilogue staging buffers: two unless that would exceed the 227 KB of shared memory (BLOCK_N = 96 with two sub-tiles)
+  static constexpr int kNumStaging = (CONV_STAGES * kStageBytes + 2 * CONV_STAGING_BYTES + 1280 <= 232448) ? 2 : 1;
+  static constexpr int kSmemBytes = CONV_STAGES * kStageBytes + kNumStaging * CONV_STAGING_BYTES + 1024 + 256;
+  static_assert(kSmemBytes <= 232448, "shared memory budget exceeded");
 };
 
 struct ConvParams {
@@ -59,7 +67,7 @@ conv3d_igemm_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_const
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sStage = smem + CONV_STAGES * Cfg::kStageBytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sStage + 2 * CONV_STAGING_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sStage + Cfg::kNumStaging * CONV_STAGING_BYTES);
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + CONV_STAGES;
   uint64_t* tmem_full_bar = bars + 2 * CONV_STAGES;
@@ -103,7 +111,7 @@ conv3d_igemm_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_const
     int m = tile / p.num_n_blocks;
     t = m / tiles_per_frame;
     m -= t * tiles_per_frame;
-    h0 = (m / p.tiles_w) * CONV_BH;
+    h0 = (m / p.tiles_w) * (CONV_BH * Cfg::kMSub);
     w0 = (m % p.tiles_w) * CONV_BW;
   };
 
@@ -119,14 +127,16 @@ conv3d_igemm_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_const
           const int c_begin = ks * CONV_CHUNKS;
           const int c_end = min(c_begin + CONV_CHUNKS, num_chunks);
           mbar_wait(&empty_bar[stage], phase ^ 1);
-          mbar_arrive_expect_tx(&full_bar[stage], (c_end - c_begin) * (CONV_A_CHUNK_BYTES + Cfg::kBChunkBytes));
+          mbar_arrive_expect_tx(&full_bar[stage], (c_end - c_begin) * (Cfg::kMSub * CONV_A_CHUNK_BYTES + Cfg::kBChunkBytes));
           uint8_t* sA = smem + stage * Cfg::kStageBytes;
-          uint8_t* sB = sA + CONV_CHUNKS * CONV_A_CHUNK_BYTES;
+          uint8_t* sB = sA + CONV_CHUNKS * Cfg::kMSub * CONV_A_CHUNK_BYTES;
           for (int c = c_begin; c < c_end; ++c) {
             const int tap = c / chunks_per_tap;
             const int cc = (c - tap * chunks_per_tap) * CONV_KC;
-            tma_load_4d(sA + (c - c_begin) * CONV_A_CHUNK_BYTES, &tmIn, &full_bar[stage], cc, w0 + p.dw[tap], h0 + p.dh[tap],
-                        t + p.dt[tap]);
+#pragma unroll
+            for (int ms = 0; ms < Cfg::kMSub; ++ms)
+              tma_load_4d(sA + ((c - c_begin) * Cfg::kMSub + ms) * CONV_A_CHUNK_BYTES, &tmIn, &full_bar[stage], cc, w0 + p.dw[tap],
+                          h0 + ms * CONV_BH + p.dh[tap], t + p.dt[tap]);
             tma_load_2d(sB + (c - c_begin) * Cfg::kBChunkBytes, &tmW, &full_bar[stage], c * CONV_KC, n_blk * BLOCK_N);
           }
           if (++stage == CONV_STAGES) {
@@ -148,21 +158,24 @@ conv3d_igemm_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_const
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
       tc_fence_after();
-      const uint32_t d_tmem = tb + acc * BLOCK_N;
+      const uint32_t d_tmem = tb + acc * Cfg::kAccCols;
       for (int ks = 0; ks < num_stages_k; ++ks) {
         const int nch = min(CONV_CHUNKS, num_chunks - ks * CONV_CHUNKS);
         mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
         const uint32_t a_lo = s_lo0 + stage * (Cfg::kStageBytes >> 4);
-        const uint32_t b_lo = a_lo + ((CONV_CHUNKS * CONV_A_CHUNK_BYTES) >> 4);
+        const uint32_t b_lo = a_lo + ((CONV_CHUNKS * Cfg::kMSub * CONV_A_CHUNK_BYTES) >> 4);
 #pragma unroll
         for (int c = 0; c < CONV_CHUNKS; ++c) {
           if (c < nch) {
 #pragma unroll
-            for (int k = 0; k < CONV_KC / 16; ++k) {   // two K=16 MMAs per 32-channel chunk: +32 B inside the 64-byte swizzle row
-              const uint32_t accum = (ks | c | k) != 0 ? 1u : 0u;
-              mma_f16_ss_w(d_tmem, a_lo + c * (CONV_A_CHUNK_BYTES >> 4) + 2 * k, kDescHiSw64,
-                           b_lo + c * (Cfg::kBChunkBytes >> 4) + 2 * k, kDescHiSw64, idesc, accum);
+            for (int ms = 0; ms < Cfg::kMSub; ++ms) {
+#pragma unroll
+              for (int k = 0; k < CONV_KC / 16; ++k) {   // two K=16 MMAs per 32-channel chunk: +32 B inside the 64-byte swizzle row
+                const uint32_t accum = (ks | c | k) != 0 ? 1u : 0u;
+                mma_f16_ss_w(d_tmem + ms * BLOCK_N, a_lo + (c * Cfg::kMSub + ms) * (CONV_A_CHUNK_BYTES >> 4) + 2 * k, kDescHiSw64,
+                             b_lo + c * (Cfg::kBChunkBytes >> 4) + 2 * k, kDescHiSw64, idesc, accum);
+              }
             }
           }
         }
@@ -188,11 +201,15 @@ conv3d_igemm_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_const
       int n_blk, t, h0, w0;
       tile_coords(tile, n_blk, t, h0, w0);
       const int n0 = n_blk * BLOCK_N;
-      const int hh = h0 + row / CONV_BW, ww = w0 + row % CONV_BW;
-      const bool vox_ok = hh < p.H && ww < p.W;
       mbar_wait(&tmem_full_bar[acc], acc_phase);
       tc_fence_after();
-      const uint32_t t_row = tmem_base + acc * BLOCK_N + (uint32_t(ewarp * 32) << 16);
+#pragma unroll 1
+      for (int ms = 0; ms < Cfg::kMSub; ++ms) {
+      const int hs = h0 + ms * CONV_BH;                     // first image row of this sub-tile
+      if (hs >= p.H) break;                                 // uniform
+      const int hh = hs + row / CONV_BW, ww = w0 + row % CONV_BW;
+      const bool vox_ok = hh < p.H && ww < p.W;
+      const uint32_t t_row = tmem_base + acc * Cfg::kAccCols + ms * BLOCK_N + (uint32_t(ewarp * 32) << 16);
       const __nv_bfloat16* res_row =
           p.residual ? p.residual + (long long)t * p.res_st + (long long)hh * p.res_sh + (long long)ww * p.res_sw : nullptr;
 
@@ -213,7 +230,7 @@ conv3d_igemm_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_const
 #pragma unroll
           for (int i = 16; i < 64; ++i) v[i] = 0;
         }
-        if (et == 0) tma_store_wait_read<1>();
+        if (et == 0) tma_store_wait_read<Cfg::kNumStaging - 1>();
         named_bar_sync(1, 128);
         tmem_ld_wait();
         uint8_t* stg = sStage + sbuf * CONV_STAGING_BYTES;
@@ -264,12 +281,13 @@ conv3d_igemm_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_const
           // output box {64 ch, 32 w, 4 h, 1 t}: rows of the staging tile are (h, w)-ordered like the input box
           asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(
                            reinterpret_cast<uint64_t>(&tmOut)),
-                       "r"(smem_u32(stg)), "r"(ncol0), "r"(w0), "r"(h0), "r"(t)
+                       "r"(smem_u32(stg)), "r"(ncol0), "r"(w0), "r"(hs), "r"(t)
                        : "memory");
           tma_store_commit();
         }
-        sbuf ^= 1;
+        sbuf = (sbuf + 1) % Cfg::kNumStaging;
       }
+      }   // sub-tiles
       tc_fence_before();
       mbar_arrive(&tmem_empty_bar[acc]);
       acc ^= 1;
@@ -368,7 +386,8 @@ int conv3d_cl(const void* in, long long in_st, long long in_sh, long long in_sw,
     p.dw[i] = (int8_t)taps[3 * i + 2];
   }
   p.tiles_w = (W + CONV_BW - 1) / CONV_BW;
-  p.tiles_h = (H + CONV_BH - 1) / CONV_BH;
+  const int msub = (block_n <= 96) ? 2 : 1;
+  p.tiles_h = (H + CONV_BH * msub - 1) / (CONV_BH * msub);
   p.num_n_blocks = (cout + block_n - 1) / block_n;
   p.bias = reinterpret_cast<const __nv_bfloat16*>(bias);
   p.residual = reinterpret_cast<const __nv_bfloat16*>(residual);

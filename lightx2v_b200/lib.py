@@ -28,6 +28,7 @@ SIGNATURES = {
     "b200_gemm_fp8": (_i32, [_ptr, _i64, _ptr, _i64, _ptr, _i64, _ptr, _ptr, _ptr, _ptr, _i64, _i64, _i64, _i32, _i32, _i32, _ptr]),
     "b200_quant_fp8_per_token": (_i32, [_ptr, _i64, _ptr, _i64, _ptr, _i64, _i32, _ptr]),
     "b200_ln_modulate_fp8": (_i32, [_ptr, _i64, _ptr, _i64, _ptr, _ptr, _ptr, _ptr, _ptr, _i64, _i32, _f32, _ptr]),
+    "b200_rms_rope_heads": (_i32, [_ptr, _i64, _ptr, _ptr, _i64, _ptr, _i64, _i32, _f32, _ptr, _i64, _ptr]),
     "b200_rms_rope_scatter": (_i32, [_ptr, _i64, _ptr, _ptr, _i64, _i32, _f32, _ptr, _i64, _ptr, _i32, _i32, _i64, _ptr]),
     "b200_fmha_fwd_d128_scatter": (_i32, [_ptr, _i64, _ptr, _i64, _ptr, _i64, _ptr, _i32, _i64, _i64, _i32, _i64, _i64, _i32, _f32, _ptr]),
     "b200_conv3d_cl": (_i32, [_ptr, _i64, _i64, _i64, _ptr, _ptr, _ptr, _i64, _i64, _i64, _ptr, _i64, _i64, _i64, _i32, _i32, _i32, _i32, _i32,
@@ -287,3 +288,18 @@ def fmha_scatter(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, peer_ptrs, r
                                            ctypes.cast(tbl, ctypes.c_void_p), len(peer_ptrs), rows_per_rank, peer_stride_s, head_offset,
                                            sq, k.shape[0], H, scale, _stream())
     _check(rc, "b200_fmha_fwd_d128_scatter")
+
+
+# ---------------------------------------------------------------------------------------------------------------- HunyuanVideo q/k path
+def rms_rope_heads_(x0: torch.Tensor, w0: torch.Tensor, x1: Optional[torch.Tensor] = None, w1: Optional[torch.Tensor] = None, *, eps: float = 1e-6,
+                    cos_sin: Optional[torch.Tensor] = None, rope_rows: int = 0) -> None:
+    """In place: per-head RMSNorm (weight [128]) of x0/x1 [rows, H, 128] (row-strided views), bf16-chain RoPE on rows < rope_rows."""
+    _req(x0, "x0")
+    rows, H, d = x0.shape
+    if d != 128 or x0.stride(1) != 128:
+        raise B200Error("rms_rope_heads_: expected [rows, H, 128] with contiguous heads")
+    if cos_sin is not None:
+        _req(cos_sin, "cos_sin", torch.float32)
+    rc = load().b200_rms_rope_heads(x0.data_ptr(), x0.stride(0), w0.data_ptr(), _p(x1), 0 if x1 is None else x1.stride(0), _p(w1), rows, H, eps,
+                                    _p(cos_sin), rope_rows if cos_sin is not None else 0, _stream())
+    _check(rc, "b200_rms_rope_heads")

@@ -172,8 +172,45 @@ def gen_vae_fixture():
     print("wan_vae_decode_small", tuple(out.shape), "absmax", float(out.abs().max()), "frac clamped", float((out.abs() >= 1).float().mean()))
 
 
+def gen_hunyuan_fixture():
+    """Real HunyuanTransformerInfer (lightx2v/models/networks/hunyuan/infer/transformer_infer.py) on one double-stream and one
+    single-stream block at the model's true width (3072, 24 heads, MLP 12288), 96 image + 32 text tokens, torch_sdpa attention with
+    a single segment (the reference's torch_sdpa op ignores cu_seqlens; two-segment varlen is checked on the GPU against flash-attn)."""
+    from safetensors.torch import save_file
+
+    import lightx2v.common.ops  # noqa: F401
+    from lightx2v.models.networks.hunyuan.infer.transformer_infer import HunyuanTransformerInfer
+    from lightx2v.models.networks.hunyuan.weights.transformer_weights import HunyuanTransformerDoubleBlock, HunyuanTransformerSingleBlock
+
+    from oracle import hunyuan_oracle as HO
+
+    hidden, mlp, heads = 3072, 12288, 24
+    cfg = Cfg(cpu_offload=False, do_mm_calib=False, mm_config={}, attention_type="torch_sdpa", task="t2v")
+    W = HO.synth_weights(1, 1, hidden, mlp, seed=42)
+    img, txt, vec, cu, freqs = HO.synth_inputs(96, 32, 32, hidden, seed=7)
+    dbl, sgl = HunyuanTransformerDoubleBlock(0, cfg), HunyuanTransformerSingleBlock(0, cfg)
+    dbl.load(W)
+    sgl.load(W)
+    infer = HunyuanTransformerInfer(cfg)
+    cu_t = torch.tensor(cu, dtype=torch.int32)
+    max_len = img.shape[0] + txt.shape[0]
+    img1, txt1 = infer.infer_double_block(dbl, img.clone(), txt.clone(), vec, cu_t, max_len, freqs, None, None)
+    x = torch.cat((img1, txt1), 0)
+    x2 = infer.infer_single_block(sgl, x, vec, txt.shape[0], cu_t, max_len, freqs, None, None)
+    save_file({"img": img, "txt": txt, "vec": vec, "cos": freqs[0], "sin": freqs[1], "img_after_double": img1.contiguous(),
+               "txt_after_double": txt1.contiguous(), "x_after_single": x2.contiguous()},
+              os.path.join(GOLD, "hunyuan_blocks_small.safetensors"),
+              metadata={"hidden": str(hidden), "mlp": str(mlp), "heads": str(heads), "weights_seed": "42", "inputs_seed": "7", "txt_valid": "32",
+                        "generator": "oracle/gen_golden.py:gen_hunyuan_fixture", "reference": "ModelTC/lightx2v@0591c35e"})
+    print("hunyuan_blocks_small", float(x2.float().abs().max()), os.path.getsize(os.path.join(GOLD, "hunyuan_blocks_small.safetensors")))
+
+
 if __name__ == "__main__":
-    if os.environ.get("GOLDEN_ONLY", "") == "vae":
+    if os.environ.get("GOLDEN_ONLY", "") == "hunyuan":
+        install_shims()
+        os.makedirs(GOLD, exist_ok=True)
+        gen_hunyuan_fixture()
+    elif os.environ.get("GOLDEN_ONLY", "") == "vae":
         install_shims()
         os.makedirs(GOLD, exist_ok=True)
         gen_vae_fixture()
@@ -185,3 +222,4 @@ if __name__ == "__main__":
         main()
         gen_scheduler_fixture()
         gen_vae_fixture()
+        gen_hunyuan_fixture()

@@ -1,0 +1,152 @@
+"""ORACLE (test infrastructure, NOT product code): plain-torch restatement of the HunyuanVideo DiT blocks as LightX2V runs them
+(lightx2v/models/networks/hunyuan/infer/transformer_infer.py: double block :86-277 + :279-306, single block :308-384;
+rotary / rms helpers lightx2v/models/networks/hunyuan/infer/utils_bf16.py:5-31), t2v path (token_replace_vec = None).
+Weights: flat dict with the checkpoint key names of hunyuan/weights/transformer_weights.py:16-71.
+Pinned by tests/golden/hunyuan_blocks_small.safetensors, produced by the REAL HunyuanTransformerInfer (oracle/gen_golden.py)."""
+from __future__ import annotations
+
+from typing import Dict
+
+import torch
+import torch.nn.functional as F
+
+from .wan_oracle import attn_apply, mm_named
+
+
+def rms_norm(x, weight, eps=1e-6):
+    """RMSWeightSgl.apply bf16 fallback over the last (head) dim — rms_norm_weight.py:109-113 (same chain as utils_bf16.py:5-8)."""
+    x = x * torch.rsqrt(x.pow(2).mean(-1, keepdim=True) + eps)
+    return x * weight
+
+
+def rotate_half(x, s0, s1):
+    x_real, x_imag = x.reshape(s0, s1, -1, 2).unbind(-1)
+    return torch.stack([-x_imag, x_real], dim=-1).flatten(2)          # utils_bf16.py:11-13
+
+
+def apply_rotary_emb(xq, xk, freqs_cis):
+    """utils_bf16.py:21-31."""
+    s0, s1, s2 = xq.shape
+    cos = freqs_cis[0].view(s0, 1, s2)
+    sin = freqs_cis[1].view(s0, 1, s2)
+    return xq * cos + rotate_half(xq, s0, s1) * sin, xk * cos + rotate_half(xk, s0, s1) * sin
+
+
+def varlen_attention(q, k, v, cu_seqlens, impl="torch_sdpa"):
+    """ATTN op with cu_seqlens = [0, img + txt_valid, img + txt_padded] (pre_infer.py:50-58): two independent segments."""
+    bounds = [int(b) for b in cu_seqlens]
+    outs = [attn_apply(q[a:b], k[a:b], v[a:b], impl) for a, b in zip(bounds[:-1], bounds[1:]) if b > a]
+    return torch.cat(outs, dim=0)
+
+
+def _qkv_heads(qkv, heads):
+    L = qkv.shape[0]
+    return qkv.view(L, 3, heads, -1).unbind(1)                         # "L (K H D) -> K L H D"
+
+
+def infer_double_block(W: Dict[str, torch.Tensor], i: int, img, txt, vec, cu_seqlens, freqs_cis, heads: int, attn="torch_sdpa"):
+    """transformer_infer.py:234-277 (phases :86-232)."""
+    p = f"double_blocks.{i}."
+    vec_silu = F.silu(vec)
+    im = mm_named(W, p + "img_mod.linear", vec_silu).chunk(6, dim=-1)      # shift1, scale1, gate1, shift2, scale2, gate2
+    tm = mm_named(W, p + "txt_mod.linear", vec_silu).chunk(6, dim=-1)
+
+    def pre_atten(x, mod, pre, rope):
+        x_mod = F.layer_norm(x, (x.shape[1],), None, None, 1e-6) * (1 + mod[1]) + mod[0]                     # :280-286
+        q, k, v = _qkv_heads(mm_named(W, p + pre + "_attn_qkv", x_mod), heads)
+        q = rms_norm(q, W[p + pre + "_attn_q_norm.weight"])
+        k = rms_norm(k, W[p + pre + "_attn_k_norm.weight"])
+        if rope:
+            q, k = apply_rotary_emb(q, k, freqs_cis)
+        return q, k, v
+
+    iq, ik, iv = pre_atten(img, im, "img", True)
+    tq, tk, tv = pre_atten(txt, tm, "txt", False)
+    q, k, v = torch.cat((iq, tq)), torch.cat((ik, tk)), torch.cat((iv, tv))
+    attn_out = varlen_attention(q, k, v, cu_seqlens, attn)
+    img_attn, txt_attn = attn_out[: img.shape[0]], attn_out[img.shape[0]:]
+    img_out = mm_named(W, p + "img_attn_proj", img_attn)
+    txt_out = mm_named(W, p + "txt_attn_proj", txt_attn)
+
+    def mlp(x, out, mod, pre):
+        x = x + out * mod[2]                                                                                   # :192-199 / :215-216
+        h = F.layer_norm(x, (x.shape[1],), None, None, 1e-6) * (1 + mod[4]) + mod[3]
+        h = F.gelu(mm_named(W, p + pre + "_mlp.fc1", h), approximate="tanh")
+        h = mm_named(W, p + pre + "_mlp.fc2", h)
+        return x + h * mod[5]                                                                                  # phase 3 :224-232
+
+    return mlp(img, img_out, im, "img"), mlp(txt, txt_out, tm, "txt")
+
+
+def infer_single_block(W, i: int, x, vec, txt_seq_len: int, cu_seqlens, freqs_cis, heads: int, hidden: int, attn="torch_sdpa"):
+    """transformer_infer.py:308-384."""
+    p = f"single_blocks.{i}."
+    mod_shift, mod_scale, mod_gate = mm_named(W, p + "modulation.linear", F.silu(vec)).chunk(3, dim=-1)
+    x_mod = F.layer_norm(x, (x.shape[1],), None, None, 1e-6) * (1 + mod_scale) + mod_shift
+    x_mod = mm_named(W, p + "linear1", x_mod)
+    qkv, mlp = torch.split(x_mod, [3 * hidden, x_mod.shape[1] - 3 * hidden], dim=-1)
+    q, k, v = _qkv_heads(qkv, heads)
+    q = rms_norm(q, W[p + "q_norm.weight"])
+    k = rms_norm(k, W[p + "k_norm.weight"])
+    img_q, txt_q = q[:-txt_seq_len], q[-txt_seq_len:]
+    img_k, txt_k = k[:-txt_seq_len], k[-txt_seq_len:]
+    img_q, img_k = apply_rotary_emb(img_q, img_k, freqs_cis)
+    q, k = torch.cat((img_q, txt_q)), torch.cat((img_k, txt_k))
+    attn_out = varlen_attention(q, k, v, cu_seqlens, attn)
+    out = torch.cat((attn_out, F.gelu(mlp, approximate="tanh")), 1)
+    out = mm_named(W, p + "linear2", out)
+    return x + out * mod_gate                                                                                  # :371-379
+
+
+def infer_blocks(W, n_double: int, n_single: int, img, txt, vec, cu_seqlens, freqs_cis, heads: int, attn="torch_sdpa"):
+    """_infer_without_offload — transformer_infer.py:71-84."""
+    hidden = img.shape[1]
+    for i in range(n_double):
+        img, txt = infer_double_block(W, i, img, txt, vec, cu_seqlens, freqs_cis, heads, attn)
+    x = torch.cat((img, txt), 0)
+    for i in range(n_single):
+        x = infer_single_block(W, i, x, vec, txt.shape[0], cu_seqlens, freqs_cis, heads, hidden, attn)
+    return x[: img.shape[0]]
+
+
+def synth_weights(n_double: int, n_single: int, hidden: int, mlp_hidden: int, seed=42, device="cpu") -> Dict[str, torch.Tensor]:
+    g = torch.Generator().manual_seed(seed)
+    W: Dict[str, torch.Tensor] = {}
+
+    def lin(name, n, k, scale=0.02):
+        W[name + ".weight"] = (torch.randn(n, k, generator=g) * scale).to(torch.bfloat16).to(device)
+        W[name + ".bias"] = (torch.randn(n, generator=g) * 0.02).to(torch.bfloat16).to(device)
+
+    def norm(name):
+        W[name] = (1.0 + torch.randn(128, generator=g) * 0.05).to(torch.bfloat16).to(device)
+
+    for i in range(n_double):
+        p = f"double_blocks.{i}."
+        for s in ("img", "txt"):
+            lin(p + s + "_mod.linear", 6 * hidden, hidden, 0.01)
+            lin(p + s + "_attn_qkv", 3 * hidden, hidden)
+            norm(p + s + "_attn_q_norm.weight")
+            norm(p + s + "_attn_k_norm.weight")
+            lin(p + s + "_attn_proj", hidden, hidden)
+            lin(p + s + "_mlp.fc1", mlp_hidden, hidden)
+            lin(p + s + "_mlp.fc2", hidden, mlp_hidden)
+    for i in range(n_single):
+        p = f"single_blocks.{i}."
+        lin(p + "linear1", 3 * hidden + mlp_hidden, hidden)
+        lin(p + "linear2", hidden, hidden + mlp_hidden)
+        norm(p + "q_norm.weight")
+        norm(p + "k_norm.weight")
+        lin(p + "modulation.linear", 3 * hidden, hidden, 0.01)
+    return W
+
+
+def synth_inputs(img_len: int, txt_len: int, txt_valid: int, hidden: int, seed=7, device="cpu"):
+    g = torch.Generator().manual_seed(seed)
+    img = torch.randn(img_len, hidden, generator=g).to(torch.bfloat16).to(device)
+    txt = torch.randn(txt_len, hidden, generator=g).to(torch.bfloat16).to(device)
+    vec = torch.randn(1, hidden, generator=g).to(torch.bfloat16).to(device)
+    ang = torch.rand(img_len, 64, generator=g) * 6.28
+    cos = ang.cos().repeat_interleave(2, dim=1).to(torch.bfloat16).to(device)      # scheduler.py:58-59, cast :318-319
+    sin = ang.sin().repeat_interleave(2, dim=1).to(torch.bfloat16).to(device)
+    cu = [0, img_len + txt_valid, img_len + txt_len]
+    return img, txt, vec, cu, (cos, sin)

@@ -70,3 +70,20 @@ def test_vae_oracle_matches_reference_fixture(golden_dir):
     err = (out - T["images"]).abs().max().item()
     assert err <= 2e-5, err
     assert V.count_causal_convs(V.decoder_layout()[1]) == 33          # 33 CausalConv3d in the decoder
+
+
+def test_hunyuan_oracle_matches_reference_fixture(golden_dir):
+    """oracle/hunyuan_oracle.py vs the REAL HunyuanTransformerInfer double + single block at width 3072, bit for bit."""
+    from oracle import hunyuan_oracle as HO
+
+    torch.set_num_threads(8)
+    T, meta = _load(os.path.join(golden_dir, "hunyuan_blocks_small.safetensors"))
+    hidden, mlp, heads = int(meta["hidden"]), int(meta["mlp"]), int(meta["heads"])
+    W = HO.synth_weights(1, 1, hidden, mlp, seed=int(meta["weights_seed"]))
+    L_img, L_txt = T["img"].shape[0], T["txt"].shape[0]
+    cu = [0, L_img + int(meta["txt_valid"]), L_img + L_txt]
+    freqs = (T["cos"], T["sin"])
+    img1, txt1 = HO.infer_double_block(W, 0, T["img"].clone(), T["txt"].clone(), T["vec"], cu, freqs, heads)
+    assert torch.equal(img1, T["img_after_double"]) and torch.equal(txt1, T["txt_after_double"])
+    x2 = HO.infer_single_block(W, 0, torch.cat((img1, txt1)), T["vec"], L_txt, cu, freqs, heads, hidden)
+    assert torch.equal(x2, T["x_after_single"])
