@@ -28,6 +28,9 @@ WORKLOADS = {
     # name: dims of the DiT + latent shape
     "wan2.1-t2v-14b-720p-81f": dict(dim=5120, num_heads=40, ffn_dim=13824, num_layers=40, target_shape=(16, 21, 90, 160), infer_steps=50,
                                     enable_cfg=True, sample_guide_scale=5.0, sample_shift=5.0),
+    # BASELINE config 3: w8a8-fp8 linears (weights quantised per out-channel at load), 4-step distilled sampler, no CFG
+    "wan2.1-t2v-14b-fp8-distill-720p-81f": dict(dim=5120, num_heads=40, ffn_dim=13824, num_layers=40, target_shape=(16, 21, 90, 160), infer_steps=4,
+                                                enable_cfg=False, sample_guide_scale=1.0, sample_shift=5.0, fp8=True, distill=True),
     "wan2.1-t2v-1.3b-480p-17f": dict(dim=1536, num_heads=12, ffn_dim=8960, num_layers=30, target_shape=(16, 5, 60, 104), infer_steps=50,
                                      enable_cfg=True, sample_guide_scale=5.0, sample_shift=5.0),   # quick self-test of this script
 }
@@ -136,10 +139,19 @@ def run_ours(args):
 
     cfg = dict(WORKLOADS[args.workload])
     cfg.update(task="t2v", freq_dim=256, text_len=512, in_dim=16, out_dim=16, seed=42, mm_config={}, patch_size=(1, 2, 2))
+    if cfg.get("fp8"):
+        from lightx2v_b200.host.ops import FP8_MM_KEY
+        cfg["mm_config"] = {"mm_type": FP8_MM_KEY, "weight_auto_quant": True}
+    if cfg.get("distill"):
+        cfg["denoising_step_list"] = [1000, 750, 500, 250]
     S, flops_step = step_flops(cfg)
     W = synth_weights(cfg, dev)
     model = WanModel(cfg, W)
-    sched = WanScheduler(cfg, device=dev)
+    if cfg.get("distill"):
+        from lightx2v_b200.host.wan_scheduler import WanStepDistillScheduler
+        sched = WanStepDistillScheduler(cfg, device=dev)
+    else:
+        sched = WanScheduler(cfg, device=dev)
     sched.prepare()
     model.set_scheduler(sched)
     g = torch.Generator(device=dev).manual_seed(7)
@@ -151,7 +163,8 @@ def run_ours(args):
     counters = {"launches": 0}
     fmha_events = []
     timing = {"on": False}
-    native = {n: getattr(lib, n) for n in ("gemm_bf16", "ln_modulate", "rms_rope_", "fmha", "rms_rope_scatter", "fmha_scatter")}
+    native = {n: getattr(lib, n) for n in ("gemm_bf16", "ln_modulate", "rms_rope_", "fmha", "rms_rope_scatter", "fmha_scatter", "gemm_fp8",
+                                           "quant_fp8_per_token", "ln_modulate_fp8")}
 
     def counted(name):
         fn = native[name]
@@ -179,8 +192,8 @@ def run_ours(args):
             ulysses.parallelize_wan_fused(model, S)
 
     def one_step(i):
-        i = i % (cfg["infer_steps"] - 1)
-        if i == 0:
+        i = i % max(1, sched.infer_steps - 1)
+        if i == 0 and not cfg.get("distill"):
             sched.set_timesteps(sched.infer_steps, shift=sched.sample_shift)   # fresh multistep history when the 50-step grid wraps
         sched.step_pre(i)
         model.infer(inputs)
@@ -259,10 +272,11 @@ def run_ours(args):
         out = {
             "metric": METRIC, "value": round(1000.0 / ms_resident, 5), "unit": "latents/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": round(ms_resident, 2), "higher_is_better": True, "scaling": "strong",
-            "vs_baseline": None, "dtype": "bf16", "data": "synthetic latents/prompt embeddings, random-init weights of the named shapes",
+            "vs_baseline": None, "dtype": "fp8-e4m3 linears, bf16 attention" if cfg.get("fp8") else "bf16",
+            "data": "synthetic latents/prompt embeddings, random-init weights of the named shapes",
             "config": {"workload": args.workload, "tokens": S, "forwards_per_step": 2 if cfg["enable_cfg"] else 1, "blocks": cfg["num_layers"],
                        "parallelism": f"ulysses{world}" if world > 1 else "single", "l2": "activations (774 MB/tensor) and weights (28 GB) exceed the 126 MB L2",
-                       "scheduler": "UniPC order 2 (flow), 50-step sigma grid"},
+                       "scheduler": "step-distill 4-step (x0 re-noising)" if cfg.get("distill") else "UniPC order 2 (flow), 50-step sigma grid"},
             "achieved_tflops": round(flops_step / (ms_resident * 1e-3) / 1e12, 1),
             "model_tflop_per_step": round(flops_step / 1e12, 1),
             "e2e": {"value": round(1000.0 / ms_e2e, 5), "unit": "latents/s", "ms_per_step": round(ms_e2e, 2), "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},

@@ -79,7 +79,9 @@ __device__ __forceinline__ float2 exp2_poly2(float2 x) {
 
 // kSplitP: P is published to the MMA warp in two 64-column halves (two mbarriers per tile) so that the first four PV
 // MMAs run while the second half of the exponentials is still being computed.
-template <int kPolyPairs, bool kSplitP>
+// kSpecMax: the exponentials of the first half start against the previous running max while the new row max is still being
+// reduced; the result is validated (and in the rare > 2^8 jump recomputed) before P is published.
+template <int kPolyPairs, bool kSplitP, bool kSpecMax>
 __global__ void __launch_bounds__(FMHA_THREADS, 1)
 fmha_fwd_d128_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                      const __grid_constant__ CUtensorMap tmV, const FmhaParams p) {
@@ -287,83 +289,100 @@ fmha_fwd_d128_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         for (int i = 0; i < 128; ++i)
           if (i >= kv_valid) s[i] = 0xff800000u;  // -inf
       }
-      float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
-#pragma unroll
-      for (int i = 0; i < 128; i += 4) {
-        mx0 = fmaxf(mx0, __uint_as_float(s[i]));
-        mx1 = fmaxf(mx1, __uint_as_float(s[i + 1]));
-        mx2 = fmaxf(mx2, __uint_as_float(s[i + 2]));
-        mx3 = fmaxf(mx3, __uint_as_float(s[i + 3]));
-      }
-      const float m_new = fmaxf(fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)), m_used);
-
-      if (j == 0) {
-        m_used = m_new;
-      } else {
-        // lazy rescale: only when the running max moved by more than 2^8 in the exp2 domain
-        const bool need = (m_new - m_used) * sl2 > 8.0f;
-        if (__any_sync(0xffffffffu, need)) {
-          float alpha = 1.0f;
-          if (need) {
-            alpha = ex2((m_used - m_new) * sl2);
-            m_used = m_new;
-          }
-          l_sum *= alpha;
-#pragma unroll 1
-          for (int c = 0; c < 128; c += 32) {
-            uint32_t o[32];
-            tmem_ld_x32(tO + c, o);
-            tmem_ld_wait();
-#pragma unroll
-            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-            tmem_st_x32(tO + c, o);
-          }
-          tmem_st_wait();
-        }
-      }
-
-      // exp2(s * scale_log2 - m * scale_log2) on packed f32x2 lanes (FFMA2 / FADD2 halve the fma-pipe instruction count);
-      // kPolyPairs of every 4 pairs take the FMA-pipe polynomial instead of MUFU.EX2, which is the co-critical unit
-      // (16 ex2/clk/SM vs 8192 tensor FLOP/clk/SM: a 128x128 tile costs 1024 MUFU cycles and 1024 MMA cycles).
       const float2 sl2v = make_float2(sl2, sl2);
-      const float neg_m = -m_used * sl2;
-      const float2 negm = make_float2(neg_m, neg_m);
-      float2 acc[4] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
       uint32_t pk[64];
+      float2 acc[4] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
+
+      // exp2(s * scale_log2 - m * scale_log2) for 64 columns on packed f32x2 lanes (FFMA2 / FADD2 halve the fma-pipe instruction
+      // count); kPolyPairs of every 4 pairs take the FMA-pipe polynomial instead of MUFU.EX2, the co-critical unit
+      // (16 ex2/clk/SM vs 8192 tensor FLOP/clk/SM: a 128x128 tile costs 1024 MUFU cycles and 1024 MMA cycles).
+      auto exp_half = [&](int half, float neg_m_) {
+        const float2 negm = make_float2(neg_m_, neg_m_);
 #pragma unroll
-      for (int g = 0; g < 16; ++g) {
+        for (int g = 0; g < 8; ++g) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const int i = g * 4 + j;
-          const float2 x = __ffma2_rn(make_float2(__uint_as_float(s[2 * i]), __uint_as_float(s[2 * i + 1])), sl2v, negm);
-          float2 e;
-          if (j < kPolyPairs) {
-            e = exp2_poly2(x);
-          } else {
-            e.x = ex2(x.x);
-            e.y = ex2(x.y);
-          }
-          acc[j] = __fadd2_rn(acc[j], e);
-          pk[i] = pack_bf16(e.x, e.y);
-        }
-        if constexpr (kSplitP) {
-          if (g == 7) {               // columns 0..63 done: publish the first half of P
-            tmem_st_x32(tS + 0, pk + 0);
-            tmem_st_wait();
-            tc_fence_before();
-            mbar_arrive(&p_full[2 * t]);
+          for (int jj = 0; jj < 4; ++jj) {
+            const int i = half * 32 + g * 4 + jj;
+            const float2 x = __ffma2_rn(make_float2(__uint_as_float(s[2 * i]), __uint_as_float(s[2 * i + 1])), sl2v, negm);
+            float2 e;
+            if (jj < kPolyPairs) {
+              e = exp2_poly2(x);
+            } else {
+              e.x = ex2(x.x);
+              e.y = ex2(x.y);
+            }
+            acc[jj] = __fadd2_rn(acc[jj], e);
+            pk[i] = pack_bf16(e.x, e.y);
           }
         }
+      };
+      auto row_max = [&]() {
+        float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+#pragma unroll
+        for (int i = 0; i < 128; i += 4) {
+          mx0 = fmaxf(mx0, __uint_as_float(s[i]));
+          mx1 = fmaxf(mx1, __uint_as_float(s[i + 1]));
+          mx2 = fmaxf(mx2, __uint_as_float(s[i + 2]));
+          mx3 = fmaxf(mx3, __uint_as_float(s[i + 3]));
+        }
+        return fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
+      };
+      // lazy rescale: O and l follow the running max only when it moved by more than 2^8 in the exp2 domain
+      auto rescale_if_needed = [&](float m_new) -> bool {
+        const bool need = (m_new - m_used) * sl2 > 8.0f;
+        if (!__any_sync(0xffffffffu, need)) return false;
+        float alpha = 1.0f;
+        if (need) {
+          alpha = ex2((m_used - m_new) * sl2);
+          m_used = m_new;
+        }
+        l_sum *= alpha;
+#pragma unroll 1
+        for (int c = 0; c < 128; c += 32) {
+          uint32_t o[32];
+          tmem_ld_x32(tO + c, o);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+          tmem_st_x32(tO + c, o);
+        }
+        tmem_st_wait();
+        return true;
+      };
+      auto publish = [&](int half) {
+        tmem_st_x32(tS + half * 32, pk + half * 32);   // P (bf16 pairs) overwrites the first 64 columns of S
+        tmem_st_wait();
+        tc_fence_before();
+        mbar_arrive(&p_full[2 * t + half]);
+      };
+
+      if (!kSpecMax || j == 0) {
+        const float m_new = fmaxf(row_max(), m_used);
+        if (j == 0) m_used = m_new;
+        else rescale_if_needed(m_new);
+        const float neg_m = -m_used * sl2;
+        exp_half(0, neg_m);
+        if constexpr (kSplitP) publish(0);
+        exp_half(1, neg_m);
+      } else {
+        // Speculative: start the exponentials of the first half against the stale max immediately (no dependency on the row
+        // reduction, which the scheduler interleaves on the ALU pipe); validate before anything is published.
+        const float2 acc_save[4] = {acc[0], acc[1], acc[2], acc[3]};
+        exp_half(0, -m_used * sl2);
+        const float m_new = fmaxf(row_max(), m_used);
+        if (rescale_if_needed(m_new)) {               // rare: the max jumped by > 2^8 — redo the first half against the new max
+          acc[0] = acc_save[0]; acc[1] = acc_save[1]; acc[2] = acc_save[2]; acc[3] = acc_save[3];
+          exp_half(0, -m_used * sl2);
+        }
+        if constexpr (kSplitP) publish(0);
+        exp_half(1, -m_used * sl2);
       }
       const float2 a01 = __fadd2_rn(acc[0], acc[1]), a23 = __fadd2_rn(acc[2], acc[3]);
       l_sum += (a01.x + a01.y) + (a23.x + a23.y);
       if constexpr (kSplitP) {
-        tmem_st_x32(tS + 32, pk + 32);
-        tmem_st_wait();
-        tc_fence_before();
-        mbar_arrive(&p_full[2 * t + 1]);
+        publish(1);
       } else {
-        tmem_st_x32(tS + 0, pk + 0);    // P (bf16 pairs) overwrites the first 64 columns of S
+        tmem_st_x32(tS + 0, pk + 0);
         tmem_st_x32(tS + 32, pk + 32);
         tmem_st_wait();
         tc_fence_before();
@@ -767,7 +786,7 @@ int fmha_fwd_d128_impl(const void* q, long long q_stride_s, const void* k, long 
   if (ver < 0) {
     const char* e = getenv("B200_FMHA_VER");
     ver = e ? atoi(e) : 4;     // 2: one softmax warpgroup per tile (1.23 PF); 3: two per tile (1.14 PF); 4: v2 + split-P publication (1.28 PF, default)
-    if (ver < 2 || ver > 4) ver = 4;
+    if (ver < 2 || ver > 5) ver = 4;
   }
   auto launch = [&](auto kern, int threads, int smem_bytes) -> int {
     B200_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
@@ -782,18 +801,24 @@ int fmha_fwd_d128_impl(const void* q, long long q_stride_s, const void* k, long 
       case 3: rc2 = launch(fmha_fwd_d128_v3_kernel<3>, FMHA3_THREADS, FMHA3_SMEM_BYTES); break;
       default: rc2 = launch(fmha_fwd_d128_v3_kernel<1>, FMHA3_THREADS, FMHA3_SMEM_BYTES); break;
     }
+  } else if (ver == 5) {
+    switch (poly) {
+      case 0: rc2 = launch(fmha_fwd_d128_kernel<0, true, true>, FMHA_THREADS, FMHA_SMEM_BYTES); break;
+      case 2: rc2 = launch(fmha_fwd_d128_kernel<2, true, true>, FMHA_THREADS, FMHA_SMEM_BYTES); break;
+      default: rc2 = launch(fmha_fwd_d128_kernel<1, true, true>, FMHA_THREADS, FMHA_SMEM_BYTES); break;
+    }
   } else if (ver == 4) {
     switch (poly) {
-      case 0: rc2 = launch(fmha_fwd_d128_kernel<0, true>, FMHA_THREADS, FMHA_SMEM_BYTES); break;
-      case 2: rc2 = launch(fmha_fwd_d128_kernel<2, true>, FMHA_THREADS, FMHA_SMEM_BYTES); break;
-      default: rc2 = launch(fmha_fwd_d128_kernel<1, true>, FMHA_THREADS, FMHA_SMEM_BYTES); break;
+      case 0: rc2 = launch(fmha_fwd_d128_kernel<0, true, false>, FMHA_THREADS, FMHA_SMEM_BYTES); break;
+      case 2: rc2 = launch(fmha_fwd_d128_kernel<2, true, false>, FMHA_THREADS, FMHA_SMEM_BYTES); break;
+      default: rc2 = launch(fmha_fwd_d128_kernel<1, true, false>, FMHA_THREADS, FMHA_SMEM_BYTES); break;
     }
   } else {
     switch (poly) {
-      case 0: rc2 = launch(fmha_fwd_d128_kernel<0, false>, FMHA_THREADS, FMHA_SMEM_BYTES); break;
-      case 2: rc2 = launch(fmha_fwd_d128_kernel<2, false>, FMHA_THREADS, FMHA_SMEM_BYTES); break;
-      case 3: rc2 = launch(fmha_fwd_d128_kernel<3, false>, FMHA_THREADS, FMHA_SMEM_BYTES); break;
-      default: rc2 = launch(fmha_fwd_d128_kernel<1, false>, FMHA_THREADS, FMHA_SMEM_BYTES); break;
+      case 0: rc2 = launch(fmha_fwd_d128_kernel<0, false, false>, FMHA_THREADS, FMHA_SMEM_BYTES); break;
+      case 2: rc2 = launch(fmha_fwd_d128_kernel<2, false, false>, FMHA_THREADS, FMHA_SMEM_BYTES); break;
+      case 3: rc2 = launch(fmha_fwd_d128_kernel<3, false, false>, FMHA_THREADS, FMHA_SMEM_BYTES); break;
+      default: rc2 = launch(fmha_fwd_d128_kernel<1, false, false>, FMHA_THREADS, FMHA_SMEM_BYTES); break;
     }
   }
   if (rc2) return rc2;
