@@ -728,11 +728,317 @@ fmha_fwd_d128_v3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
   }
 }
 
+// =====================================================================================================================
+// v6: 64-row K/V tiles with S and P in SEPARATE TMEM columns.
+// With 128-row K/V tiles the TMEM budget (S0|S1|O0|O1 = 512 columns) forces P to alias S, so QK_{j+1} of a query tile cannot be
+// issued before PV_j has consumed P_j: the per-tile loop is serial (softmax -> PV -> QK -> softmax) and neither the tensor pipe
+// (72 %) nor the softmax warps (60 % busy) saturate.  With 64-row K/V tiles S_t (64 columns), P_t (32 columns) and O_t (128
+// columns) all fit (448 of 512 columns) without aliasing: the softmax warps hand S back right after loading it into registers
+// (s_free), so the tensor pipe runs QK_{j+1} while the exponentials of step j are still being computed, and PV_j as soon as
+// P_j lands.  The chain per tile and step is max(softmax, MMA) instead of their sum.
+//   TMEM: S0 @0, S1 @64, P0 @128, P1 @160, O0 @256, O1 @384.   smem: Q 2 x 32 KB, K/V ring 8 x 16 KB ([64 rows][128 d] tiles).
+//   barriers per tile: s_full (MMA->softmax), s_free (softmax->MMA), p_full (softmax->MMA), p_free (MMA->softmax), o_full.
+// =====================================================================================================================
+constexpr int FMHA6_BLOCK_KV = 64;
+constexpr int FMHA6_KV_STAGES = 8;
+constexpr int FMHA6_KV_TILE_BYTES = 64 * 128 * 2;      // 16 KB: two [64 rows][64 d] swizzled panels of 8 KB
+constexpr int FMHA6_KV_PANEL_BYTES = 64 * 64 * 2;      // 8 KB
+constexpr int FMHA6_SMEM_BYTES = 2 * FMHA_TILE_BYTES + FMHA6_KV_STAGES * FMHA6_KV_TILE_BYTES + 1024 + 512;
+
+template <int kPolyPairs>
+__global__ void __launch_bounds__(FMHA_THREADS, 1)
+fmha_fwd_d128_v6_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                        const __grid_constant__ CUtensorMap tmV, const FmhaParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;
+  uint8_t* sKV = smem + 2 * FMHA_TILE_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sKV + FMHA6_KV_STAGES * FMHA6_KV_TILE_BYTES);
+  uint64_t* q_full = bars;                  // [1]
+  uint64_t* kv_full = bars + 1;             // [8]
+  uint64_t* kv_empty = bars + 9;            // [8]
+  uint64_t* s_full = bars + 17;             // [2]
+  uint64_t* s_free = bars + 19;             // [2]
+  uint64_t* p_full = bars + 21;             // [2]
+  uint64_t* p_free = bars + 23;             // [2]
+  uint64_t* o_full = bars + 25;             // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 27);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int head = blockIdx.y;
+  const int q0 = blockIdx.x * (2 * FMHA_BLOCK_Q);
+  const int n_kv = (p.sk + FMHA6_BLOCK_KV - 1) / FMHA6_BLOCK_KV;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmQ);
+    prefetch_tmap(&tmK);
+    prefetch_tmap(&tmV);
+  }
+  if (warp == 1 && lane == 0) {
+    mbar_init(q_full, 1);
+    for (int i = 0; i < FMHA6_KV_STAGES; ++i) {
+      mbar_init(&kv_full[i], 1);
+      mbar_init(&kv_empty[i], 1);
+    }
+    for (int t = 0; t < 2; ++t) {
+      mbar_init(&s_full[t], 1);
+      mbar_init(&s_free[t], 128);
+      mbar_init(&p_full[t], 128);
+      mbar_init(&p_free[t], 1);
+      mbar_init(&o_full[t], 1);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  constexpr uint32_t COL_S0 = 0, COL_S1 = 64, COL_P0 = 128, COL_P1 = 160, COL_O0 = 256, COL_O1 = 384;
+
+  if (warp < 4) {
+    reg_dealloc<88>();
+    if (warp == 0) {
+      // ============================== TMA producer ==============================
+      if (lane == 0) {
+        mbar_arrive_expect_tx(q_full, 2 * FMHA_TILE_BYTES);
+        for (int t = 0; t < 2; ++t)
+          for (int h = 0; h < 2; ++h)
+            tma_load_3d(sQ + t * FMHA_TILE_BYTES + h * FMHA_PANEL_BYTES, &tmQ, q_full, h * 64, head, q0 + t * FMHA_BLOCK_Q);
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int it = 0; it < 2 * n_kv; ++it) {   // K_0, V_0, K_1, V_1, ...
+          const int j = it >> 1;
+          const CUtensorMap* tm = (it & 1) ? &tmV : &tmK;
+          mbar_wait(&kv_empty[stage], phase ^ 1);
+          mbar_arrive_expect_tx(&kv_full[stage], FMHA6_KV_TILE_BYTES);
+          for (int h = 0; h < 2; ++h)
+            tma_load_3d(sKV + stage * FMHA6_KV_TILE_BYTES + h * FMHA6_KV_PANEL_BYTES, tm, &kv_full[stage], h * 64, head,
+                        j * FMHA6_BLOCK_KV);
+          if (++stage == FMHA6_KV_STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    } else if (warp == 1) {
+      // ============================== MMA issuer (whole warp, warp-uniform) ==============================
+      constexpr uint32_t idesc_qk = make_idesc(FMT_BF16, FMT_BF16, 128, 64, 0, 0);    // S[128 q, 64 kv]
+      constexpr uint32_t idesc_pv = make_idesc(FMT_BF16, FMT_BF16, 128, 128, 0, 1);   // O[128 q, 128 d], V MN-major
+      const uint32_t tb = __shfl_sync(0xffffffffu, tmem_base, 0);
+      const uint32_t q_lo = desc_lo_kmajor(smem_u32(sQ));
+      const uint32_t kv_addr = smem_u32(sKV);
+
+      auto issue_qk = [&](int t, int kstage) {
+        const uint32_t a = q_lo + t * (FMHA_TILE_BYTES >> 4);
+        const uint32_t b = desc_lo_kmajor(kv_addr + kstage * FMHA6_KV_TILE_BYTES);
+        const uint32_t d = tb + (t ? COL_S1 : COL_S0);
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks) {   // d = 128 in steps of 16: Q panels are 16 KB apart, K panels 8 KB apart
+          const uint32_t offq = ((ks >> 2) * FMHA_PANEL_BYTES + (ks & 3) * 32) >> 4;
+          const uint32_t offk = ((ks >> 2) * FMHA6_KV_PANEL_BYTES + (ks & 3) * 32) >> 4;
+          mma_f16_ss_w(d, a + offq, kDescHiSw128, b + offk, kDescHiSw128, idesc_qk, ks != 0 ? 1u : 0u);
+        }
+      };
+      auto issue_pv = [&](int t, int vstage, uint32_t accumulate) {
+        const uint32_t b = desc_lo_mnmajor(kv_addr + vstage * FMHA6_KV_TILE_BYTES, FMHA6_KV_PANEL_BYTES);
+        const uint32_t d = tb + (t ? COL_O1 : COL_O0);
+        const uint32_t a = tb + (t ? COL_P1 : COL_P0);
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {   // kv = 64 in steps of 16 rows (2048 B); P: 8 columns per step
+          mma_f16_ts_w(d, a + ks * 8, b + ks * (2048 >> 4), kDescHiSw128, idesc_pv, ks != 0 ? 1u : accumulate);
+        }
+      };
+
+      int stage = 0;
+      uint32_t phase = 0;
+      auto advance = [&]() {
+        if (++stage == FMHA6_KV_STAGES) {
+          stage = 0;
+          phase ^= 1;
+        }
+      };
+
+      mbar_wait(q_full, 0);
+      mbar_wait(&kv_full[stage], phase);           // K_0
+      tc_fence_after();
+      issue_qk(0, stage);
+      tc_commit_w(&s_full[0]);
+      issue_qk(1, stage);
+      tc_commit_w(&s_full[1]);
+      tc_commit_w(&kv_empty[stage]);
+      advance();
+
+      for (int j = 0; j < n_kv; ++j) {
+        const bool has_next = (j + 1) < n_kv;
+        const int vstage = stage;
+        const uint32_t vphase = phase;
+        advance();
+        const int kstage = stage;
+        const uint32_t kphase = phase;
+        if (has_next) advance();
+        const uint32_t pj = j & 1;
+        const uint32_t acc = j > 0 ? 1u : 0u;
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+          if (has_next) {
+            if (t == 0) mbar_wait(&kv_full[kstage], kphase);      // K_{j+1}
+            mbar_wait(&s_free[t], pj);                             // S_j of this tile is in the softmax warps' registers
+            tc_fence_after();
+            issue_qk(t, kstage);
+            tc_commit_w(&s_full[t]);
+            if (t == 1) tc_commit_w(&kv_empty[kstage]);
+          }
+          if (t == 0) mbar_wait(&kv_full[vstage], vphase);        // V_j
+          mbar_wait(&p_full[t], pj);
+          tc_fence_after();
+          issue_pv(t, vstage, acc);
+          tc_commit_w(&p_free[t]);
+          if (!has_next) tc_commit_w(&o_full[t]);
+          if (t == 1) tc_commit_w(&kv_empty[vstage]);
+        }
+      }
+    }
+  } else {
+    // ============================== softmax / correction / epilogue ==============================
+    reg_alloc<208>();
+    const int t = (warp - 4) >> 2;
+    const int lg = warp & 3;
+    const int row = lg * 32 + lane;
+    const uint32_t lane_off = uint32_t(lg * 32) << 16;
+    const uint32_t tS = tmem_base + (t ? COL_S1 : COL_S0) + lane_off;
+    const uint32_t tP = tmem_base + (t ? COL_P1 : COL_P0) + lane_off;
+    const uint32_t tO = tmem_base + (t ? COL_O1 : COL_O0) + lane_off;
+    const float sl2 = p.scale_log2;
+    const float2 sl2v = make_float2(sl2, sl2);
+
+    float m_used = -INFINITY;
+    float l_sum = 0.f;
+
+    for (int j = 0; j < n_kv; ++j) {
+      mbar_wait(&s_full[t], j & 1);
+      tc_fence_after();
+      uint32_t s[64];
+      tmem_ld_x32(tS, s);
+      tmem_ld_x32(tS + 32, s + 32);
+      tmem_ld_wait();
+      tc_fence_before();
+      mbar_arrive(&s_free[t]);                       // the tensor pipe may overwrite S with QK_{j+1} from here on
+
+      const int kv_valid = p.sk - j * FMHA6_BLOCK_KV;
+      if (kv_valid < FMHA6_BLOCK_KV) {
+#pragma unroll
+        for (int i = 0; i < 64; ++i)
+          if (i >= kv_valid) s[i] = 0xff800000u;
+      }
+      float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+#pragma unroll
+      for (int i = 0; i < 64; i += 4) {
+        mx0 = fmaxf(mx0, __uint_as_float(s[i]));
+        mx1 = fmaxf(mx1, __uint_as_float(s[i + 1]));
+        mx2 = fmaxf(mx2, __uint_as_float(s[i + 2]));
+        mx3 = fmaxf(mx3, __uint_as_float(s[i + 3]));
+      }
+      const float m_new = fmaxf(fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)), m_used);
+      float alpha = 1.0f;
+      bool any_need = false;
+      if (j == 0) {
+        m_used = m_new;
+      } else {
+        const bool need = (m_new - m_used) * sl2 > 8.0f;     // lazy rescale threshold: 2^8 in the exp2 domain
+        any_need = __any_sync(0xffffffffu, need);
+        if (need) {
+          alpha = ex2((m_used - m_new) * sl2);
+          m_used = m_new;
+        }
+        l_sum *= alpha;
+      }
+
+      const float neg_m = -m_used * sl2;
+      const float2 negm = make_float2(neg_m, neg_m);
+      float2 acc[4] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
+      uint32_t pk[32];
+#pragma unroll
+      for (int g = 0; g < 8; ++g) {
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) {
+          const int i = g * 4 + jj;
+          const float2 x = __ffma2_rn(make_float2(__uint_as_float(s[2 * i]), __uint_as_float(s[2 * i + 1])), sl2v, negm);
+          float2 e;
+          if (jj < kPolyPairs) {
+            e = exp2_poly2(x);
+          } else {
+            e.x = ex2(x.x);
+            e.y = ex2(x.y);
+          }
+          acc[jj] = __fadd2_rn(acc[jj], e);
+          pk[i] = pack_bf16(e.x, e.y);
+        }
+      }
+      const float2 a01 = __fadd2_rn(acc[0], acc[1]), a23 = __fadd2_rn(acc[2], acc[3]);
+      l_sum += (a01.x + a01.y) + (a23.x + a23.y);
+
+      // P_{j-1} must have been consumed (and O be quiescent) before P_j is written / O is rescaled
+      if (j > 0) {
+        mbar_wait(&p_free[t], (j - 1) & 1);
+        tc_fence_after();
+        if (any_need) {
+#pragma unroll 1
+          for (int c = 0; c < 128; c += 32) {
+            uint32_t o[32];
+            tmem_ld_x32(tO + c, o);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+            tmem_st_x32(tO + c, o);
+          }
+        }
+      }
+      tmem_st_x32(tP, pk);
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive(&p_full[t]);
+    }
+
+    // ---- epilogue: O / l -> bf16 -> global (or the token owner's peer buffer)
+    mbar_wait(&o_full[t], 0);
+    tc_fence_after();
+    const float inv_l = 1.0f / l_sum;
+    const int q_row = q0 + t * FMHA_BLOCK_Q + row;
+    __nv_bfloat16* orow = q_row < p.sq ? fmha_out_row(p, q_row, head) : p.out;
+#pragma unroll 1
+    for (int c = 0; c < 128; c += 32) {
+      uint32_t o[32];
+      tmem_ld_x32(tO + c, o);
+      tmem_ld_wait();
+      if (q_row < p.sq) {
+#pragma unroll
+        for (int v = 0; v < 4; ++v) {
+          uint4 w;
+          w.x = pack_bf16(__uint_as_float(o[v * 8 + 0]) * inv_l, __uint_as_float(o[v * 8 + 1]) * inv_l);
+          w.y = pack_bf16(__uint_as_float(o[v * 8 + 2]) * inv_l, __uint_as_float(o[v * 8 + 3]) * inv_l);
+          w.z = pack_bf16(__uint_as_float(o[v * 8 + 4]) * inv_l, __uint_as_float(o[v * 8 + 5]) * inv_l);
+          w.w = pack_bf16(__uint_as_float(o[v * 8 + 6]) * inv_l, __uint_as_float(o[v * 8 + 7]) * inv_l);
+          *reinterpret_cast<uint4*>(orow + c + v * 8) = w;
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
 // q/k/v: [rows, H, 128] bf16 with arbitrary row stride (elements), heads contiguous (stride 128).
-static int encode_qkv_map(CUtensorMap* tm, const void* base, long long rows, int heads, long long stride_s) {
+static int encode_qkv_map(CUtensorMap* tm, const void* base, long long rows, int heads, long long stride_s, uint32_t box_rows = 128) {
   uint64_t dims[3] = {128, (uint64_t)heads, (uint64_t)rows};
   uint64_t strides[2] = {128 * 2, (uint64_t)stride_s * 2};
-  uint32_t box[3] = {64, 1, 128};
+  uint32_t box[3] = {64, 1, box_rows};
   return encode_tmap(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, base, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
 }
 
@@ -760,8 +1066,15 @@ int fmha_fwd_d128_impl(const void* q, long long q_stride_s, const void* k, long 
   CUtensorMap tmQ, tmK, tmV;
   int rc;
   if ((rc = encode_qkv_map(&tmQ, q, sq, heads, q_stride_s))) return rc;
-  if ((rc = encode_qkv_map(&tmK, k, sk, heads, k_stride_s))) return rc;
-  if ((rc = encode_qkv_map(&tmV, v, sk, heads, v_stride_s))) return rc;
+  static int ver = -1;
+  if (ver < 0) {
+    const char* e = getenv("B200_FMHA_VER");
+    ver = e ? atoi(e) : 4;     // 2: one softmax warpgroup per tile; 3: two per tile; 4: v2 + split-P publication; 5: 4 + speculative max; 6: 64-row K/V tiles, S/P un-aliased
+    if (ver < 2 || ver > 6) ver = 4;
+  }
+  const uint32_t kv_box_rows = (ver == 6) ? 64 : 128;
+  if ((rc = encode_qkv_map(&tmK, k, sk, heads, k_stride_s, kv_box_rows))) return rc;
+  if ((rc = encode_qkv_map(&tmV, v, sk, heads, v_stride_s, kv_box_rows))) return rc;
 
   FmhaParams p;
   p.sq = (int)sq;
@@ -782,19 +1095,19 @@ int fmha_fwd_d128_impl(const void* q, long long q_stride_s, const void* k, long 
     if (poly < 0 || poly > 3) poly = 1;
   }
   dim3 grid((unsigned)((sq + 2 * FMHA_BLOCK_Q - 1) / (2 * FMHA_BLOCK_Q)), (unsigned)heads, 1);
-  static int ver = -1;
-  if (ver < 0) {
-    const char* e = getenv("B200_FMHA_VER");
-    ver = e ? atoi(e) : 4;     // 2: one softmax warpgroup per tile (1.23 PF); 3: two per tile (1.14 PF); 4: v2 + split-P publication (1.28 PF, default)
-    if (ver < 2 || ver > 5) ver = 4;
-  }
   auto launch = [&](auto kern, int threads, int smem_bytes) -> int {
     B200_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
     kern<<<grid, threads, smem_bytes, stream>>>(tmQ, tmK, tmV, p);
     return B200_OK;
   };
   int rc2;
-  if (ver == 3) {
+  if (ver == 6) {
+    switch (poly) {
+      case 0: rc2 = launch(fmha_fwd_d128_v6_kernel<0>, FMHA_THREADS, FMHA6_SMEM_BYTES); break;
+      case 2: rc2 = launch(fmha_fwd_d128_v6_kernel<2>, FMHA_THREADS, FMHA6_SMEM_BYTES); break;
+      default: rc2 = launch(fmha_fwd_d128_v6_kernel<1>, FMHA_THREADS, FMHA6_SMEM_BYTES); break;
+    }
+  } else if (ver == 3) {
     switch (poly) {
       case 0: rc2 = launch(fmha_fwd_d128_v3_kernel<0>, FMHA3_THREADS, FMHA3_SMEM_BYTES); break;
       case 2: rc2 = launch(fmha_fwd_d128_v3_kernel<2>, FMHA3_THREADS, FMHA3_SMEM_BYTES); break;
