@@ -186,10 +186,17 @@ def run_ours(args):
         setattr(lib, n, counted(n))
     if world > 1:
         # after wrapping, so the sharded launches are counted and timed too
-        if args.sp == "nccl":
-            ulysses.parallelize_wan(model, S, lib.fmha)
+        sp_mode = args.sp
+        if sp_mode == "fused":
+            try:
+                ulysses.parallelize_wan_fused(model, S)
+            except Exception as ex:  # symmetric memory unavailable on this box: keep the run alive on the NCCL exchange and say so
+                sp_mode = f"nccl (peer-memory setup failed: {str(ex)[:120]})"
+                ulysses.parallelize_wan(model, S, lib.fmha)
         else:
-            ulysses.parallelize_wan_fused(model, S)
+            ulysses.parallelize_wan(model, S, lib.fmha)
+    else:
+        sp_mode = "none"
 
     def one_step(i):
         i = i % max(1, sched.infer_steps - 1)
@@ -266,8 +273,12 @@ def run_ours(args):
             _, sq, sk, h = fm[0]
             fl = 4.0 * sq * sk * h * 128
             ach = fl / (avg_ms * 1e-3) / 1e12
+            # DRAM bytes per launch from the committed `ncu --set full` capture of this kernel at this shape
+            # (profiles/r01_fmha_v4_h40_ncu_summary.txt: dram read 2.70 GB + write 1.09 GB; algorithmic q+k+v+o = 3.10 GB).
+            traffic = 3.787e9 if (sq, sk, h) == (75600, 75600, 40) else None
             roof = {"kernel": "fmha_fwd_d128_kernel (self-attention)", "bound": "tensor", "achieved": round(ach, 1), "peak": peak_tf,
-                    "unit": "TFLOP/s", "frac": round(ach / peak_tf, 4), "traffic": None, "launch_ms": round(avg_ms, 3),
+                    "unit": "TFLOP/s", "frac": round(ach / peak_tf, 4), "traffic": traffic, "traffic_unit": "bytes/launch (ncu dram read+write)",
+                    "launch_ms": round(avg_ms, 3),
                     "launches_timed": len(fm), "algorithmic_flop_per_launch": fl, "peak_source": peak_src}
         out = {
             "metric": METRIC, "value": round(1000.0 / ms_resident, 5), "unit": "latents/s", "n_gpus": world, "steps": args.steps,
@@ -275,7 +286,7 @@ def run_ours(args):
             "vs_baseline": None, "dtype": "fp8-e4m3 linears, bf16 attention" if cfg.get("fp8") else "bf16",
             "data": "synthetic latents/prompt embeddings, random-init weights of the named shapes",
             "config": {"workload": args.workload, "tokens": S, "forwards_per_step": 2 if cfg["enable_cfg"] else 1, "blocks": cfg["num_layers"],
-                       "parallelism": f"ulysses{world}" if world > 1 else "single", "l2": "activations (774 MB/tensor) and weights (28 GB) exceed the 126 MB L2",
+                       "parallelism": f"ulysses{world}" if world > 1 else "single", "sp_exchange": sp_mode, "l2": "activations (774 MB/tensor) and weights (28 GB) exceed the 126 MB L2",
                        "scheduler": "step-distill 4-step (x0 re-noising)" if cfg.get("distill") else "UniPC order 2 (flow), 50-step sigma grid"},
             "achieved_tflops": round(flops_step / (ms_resident * 1e-3) / 1e12, 1),
             "model_tflop_per_step": round(flops_step / 1e12, 1),
@@ -296,6 +307,70 @@ def run_ours(args):
         print(json.dumps(out))
     if world > 1:
         torch.distributed.destroy_process_group()
+
+
+def run_hunyuan_blocks(args):
+    """BASELINE config 5 (block stack only): HunyuanVideo 13B bf16, 720p x 129f = 118 800 image tokens + 256 text tokens (77 valid),
+    20 double-stream + 40 single-stream blocks, one forward per step (embedded guidance, no CFG).  Pre/post-infer and the Hunyuan VAE
+    are not part of this measurement (SURVEY.md 8a A16 only)."""
+    from lightx2v_b200 import lib
+    from lightx2v_b200.host.hunyuan_infer import HunyuanTransformerInfer, HunyuanTransformerWeights
+
+    dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
+    torch.cuda.set_device(dev)
+    lib.load()
+    D, M, H, ND, NS = 3072, 12288, 24, 20, 40
+    Li, Lt, valid = 33 * 45 * 80, 256, 77
+    g = torch.Generator(device=dev).manual_seed(42)
+
+    def rnd(*shape, scale=0.02):
+        return (torch.randn(*shape, generator=g, device=dev, dtype=torch.float32) * scale).to(torch.bfloat16)
+
+    W = {}
+    def lin(name, n, k, scale=0.02):
+        W[name + ".weight"] = rnd(n, k, scale=scale)
+        W[name + ".bias"] = rnd(n)
+    for i in range(ND):
+        p = f"double_blocks.{i}."
+        for s in ("img", "txt"):
+            lin(p + s + "_mod.linear", 6 * D, D, 0.01); lin(p + s + "_attn_qkv", 3 * D, D); lin(p + s + "_attn_proj", D, D)
+            lin(p + s + "_mlp.fc1", M, D); lin(p + s + "_mlp.fc2", D, M)
+            W[p + s + "_attn_q_norm.weight"] = (1 + rnd(128, scale=0.05).float()).to(torch.bfloat16)
+            W[p + s + "_attn_k_norm.weight"] = (1 + rnd(128, scale=0.05).float()).to(torch.bfloat16)
+    for i in range(NS):
+        p = f"single_blocks.{i}."
+        lin(p + "linear1", 3 * D + M, D); lin(p + "linear2", D, D + M); lin(p + "modulation.linear", 3 * D, D, 0.01)
+        W[p + "q_norm.weight"] = (1 + rnd(128, scale=0.05).float()).to(torch.bfloat16)
+        W[p + "k_norm.weight"] = (1 + rnd(128, scale=0.05).float()).to(torch.bfloat16)
+    cfg = dict(task="t2v", mm_config={}, double_blocks_num=ND, single_blocks_num=NS)
+    weights = HunyuanTransformerWeights(cfg)
+    weights.load(W)
+    infer = HunyuanTransformerInfer(cfg)
+    img0, txt0, vec = rnd(Li, D, scale=1.0), rnd(Lt, D, scale=1.0), rnd(1, D, scale=1.0)
+    ang = torch.rand(Li, 64, generator=g, device=dev) * 6.28
+    freqs = (ang.cos().repeat_interleave(2, 1).to(torch.bfloat16), ang.sin().repeat_interleave(2, 1).to(torch.bfloat16))
+    cu = [0, Li + valid, Li + Lt]
+
+    def step():
+        infer.infer(weights, img0.clone(), txt0.clone(), vec, cu, Li + Lt, freqs)
+
+    for _ in range(args.warmup):
+        step()
+    torch.cuda.synchronize()
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    for _ in range(args.steps):
+        step()
+    e.record()
+    torch.cuda.synchronize()
+    ms = s.elapsed_time(e) / args.steps
+    L = Li + Lt
+    flops = 60 * (4.0 * L * L * D + 24.0 * L * D * D)          # SURVEY.md 8d
+    print(json.dumps({"metric": "denoise-step latents/sec (HunyuanVideo 13B 720p x 129f, DiT block stack only)", "value": round(1000.0 / ms, 5),
+                      "unit": "latents/s", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms, 1), "higher_is_better": True,
+                      "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+                      "config": {"workload": args.workload, "img_tokens": Li, "txt_tokens": Lt, "txt_valid": valid, "blocks": "20 double + 40 single"},
+                      "achieved_tflops": round(flops / (ms * 1e-3) / 1e12, 1), "model_tflop_per_step": round(flops / 1e12, 1)}))
 
 
 def cpu_reference_sample(cfg, flops_step, budget_s=20.0):
@@ -440,14 +515,16 @@ def main():
     ap.add_argument("--steps", type=int, default=2)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="wan2.1-t2v-14b-720p-81f", choices=list(WORKLOADS))
+    ap.add_argument("--workload", default="wan2.1-t2v-14b-720p-81f", choices=list(WORKLOADS) + ["hunyuan-13b-720p-129f-blocks"])
     ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false")
     ap.add_argument("--no-gpu-reference", dest="gpu_reference", action="store_false")
     ap.add_argument("--no-vae", dest="vae", action="store_false")
     ap.add_argument("--sp", default="fused", choices=["fused", "nccl"], help="Ulysses exchange: peer-memory kernels (default) or NCCL all-to-all")
     ap.add_argument("--cpu-budget", type=float, default=20.0)
     args = ap.parse_args()
-    if args.impl == "reference":
+    if args.workload == "hunyuan-13b-720p-129f-blocks":
+        run_hunyuan_blocks(args)
+    elif args.impl == "reference":
         run_reference(args)
     else:
         run_ours(args)

@@ -81,7 +81,9 @@ __device__ __forceinline__ float2 exp2_poly2(float2 x) {
 // MMAs run while the second half of the exponentials is still being computed.
 // kSpecMax: the exponentials of the first half start against the previous running max while the new row max is still being
 // reduced; the result is validated (and in the rare > 2^8 jump recomputed) before P is published.
-template <int kPolyPairs, bool kSplitP, bool kSpecMax>
+// kEarlyQK: the upper 64 score columns of S_{j+1} do not overlap P_j (columns 0..63), so that half of QK_{j+1} is issued as soon
+// as the softmax warps have pulled S_j into registers (s_free), ahead of PV_j; only the lower half waits for PV_j to finish.
+template <int kPolyPairs, bool kSplitP, bool kSpecMax, bool kEarlyQK>
 __global__ void __launch_bounds__(FMHA_THREADS, 1)
 fmha_fwd_d128_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                      const __grid_constant__ CUtensorMap tmV, const FmhaParams p) {
@@ -96,7 +98,8 @@ fmha_fwd_d128_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
   uint64_t* s_full = bars + 9;           // [2]
   uint64_t* p_full = bars + 11;          // [2 tiles][2 halves] (the second half only with kSplitP)
   uint64_t* o_full = bars + 15;          // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 17);
+  uint64_t* s_free = bars + 17;          // [2] (kEarlyQK)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 19);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -120,6 +123,7 @@ fmha_fwd_d128_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       mbar_init(&p_full[2 * t], 128);
       mbar_init(&p_full[2 * t + 1], 128);
       mbar_init(&o_full[t], 1);
+      mbar_init(&s_free[t], 128);
     }
     fence_mbar_init();
   }
@@ -181,6 +185,18 @@ fmha_fwd_d128_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
           mma_f16_ss_w(d, a + off, kDescHiSw128, b + off, kDescHiSw128, idesc_qk, ks != 0 ? 1u : 0u);
         }
       };
+      // one 64-column half of S: K rows [64 half, 64 half + 64) (8192 B into each panel), TMEM columns 64 half ..
+      auto issue_qk_half = [&](int t, int kstage, int half) {
+        constexpr uint32_t idesc_qk64 = make_idesc(FMT_BF16, FMT_BF16, 128, 64, 0, 0);
+        const uint32_t a = q_lo + t * (FMHA_TILE_BYTES >> 4);
+        const uint32_t b = desc_lo_kmajor(kv_addr + kstage * FMHA_TILE_BYTES + half * 8192);
+        const uint32_t d = (t ? tS1 : tS0) + half * 64;
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks) {
+          const uint32_t off = ((ks >> 2) * FMHA_PANEL_BYTES + (ks & 3) * 32) >> 4;
+          mma_f16_ss_w(d, a + off, kDescHiSw128, b + off, kDescHiSw128, idesc_qk64, ks != 0 ? 1u : 0u);
+        }
+      };
       // kv = 128 in steps of 16 rows (16 x 128 B = 2048 B); P: 8 columns per step; ks in [ks0, ks1)
       auto issue_pv_range = [&](int t, int vstage, uint32_t accumulate, int ks0, int ks1) {
         const uint32_t b = desc_lo_mnmajor(kv_addr + vstage * FMHA_TILE_BYTES, FMHA_PANEL_BYTES);
@@ -239,18 +255,34 @@ fmha_fwd_d128_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         const uint32_t pj = j & 1;
         const uint32_t acc = j > 0 ? 1u : 0u;
         // ---- tile 0
+        if constexpr (kEarlyQK) {
+          if (has_next) {
+            mbar_wait(&s_free[0], pj);
+            tc_fence_after();
+            issue_qk_half(0, kstage, 1);
+          }
+        }
         issue_pv(0, vstage, acc, pj);
         if (has_next) {
-          issue_qk(0, kstage);
+          if constexpr (kEarlyQK) issue_qk_half(0, kstage, 0);
+          else issue_qk(0, kstage);
           tc_commit_w(&s_full[0]);
         } else {
           tc_commit_w(&o_full[0]);
         }
         // ---- tile 1
+        if constexpr (kEarlyQK) {
+          if (has_next) {
+            mbar_wait(&s_free[1], pj);
+            tc_fence_after();
+            issue_qk_half(1, kstage, 1);
+          }
+        }
         issue_pv(1, vstage, acc, pj);
         tc_commit_w(&kv_empty[vstage]);
         if (has_next) {
-          issue_qk(1, kstage);
+          if constexpr (kEarlyQK) issue_qk_half(1, kstage, 0);
+          else issue_qk(1, kstage);
           tc_commit_w(&s_full[1]);
           tc_commit_w(&kv_empty[kstage]);
         } else {
@@ -282,6 +314,10 @@ fmha_fwd_d128_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       tmem_ld_x32(tS + 64, s + 64);
       tmem_ld_x32(tS + 96, s + 96);
       tmem_ld_wait();
+      if constexpr (kEarlyQK) {
+        tc_fence_before();
+        mbar_arrive(&s_free[t]);          // S_j is in registers: the upper half of S may be overwritten by QK_{j+1}
+      }
 
       const int kv_valid = p.sk - j * FMHA_BLOCK_KV;   // >= 1
       if (kv_valid < FMHA_BLOCK_KV) {
@@ -1070,7 +1106,7 @@ int fmha_fwd_d128_impl(const void* q, long long q_stride_s, const void* k, long 
   if (ver < 0) {
     const char* e = getenv("B200_FMHA_VER");
     ver = e ? atoi(e) : 4;     // 2: one softmax warpgroup per tile; 3: two per tile; 4: v2 + split-P publication; 5: 4 + speculative max; 6: 64-row K/V tiles, S/P un-aliased
-    if (ver < 2 || ver > 6) ver = 4;
+    if (ver < 2 || ver > 7) ver = 4;
   }
   const uint32_t kv_box_rows = (ver == 6) ? 64 : 128;
   if ((rc = encode_qkv_map(&tmK, k, sk, heads, k_stride_s, kv_box_rows))) return rc;
@@ -1114,24 +1150,30 @@ int fmha_fwd_d128_impl(const void* q, long long q_stride_s, const void* k, long 
       case 3: rc2 = launch(fmha_fwd_d128_v3_kernel<3>, FMHA3_THREADS, FMHA3_SMEM_BYTES); break;
       default: rc2 = launch(fmha_fwd_d128_v3_kernel<1>, FMHA3_THREADS, FMHA3_SMEM_BYTES); break;
     }
+  } else if (ver == 7) {
+    switch (poly) {
+      case 0: rc2 = launch(fmha_fwd_d128_kernel<0, true, false, true>, FMHA_THREADS, FMHA_SMEM_BYTES); break;
+      case 2: rc2 = launch(fmha_fwd_d128_kernel<2, true, false, true>, FMHA_THREADS, FMHA_SMEM_BYTES); break;
+      default: rc2 = launch(fmha_fwd_d128_kernel<1, true, false, true>, FMHA_THREADS, FMHA_SMEM_BYTES); break;
+    }
   } else if (ver == 5) {
     switch (poly) {
-      case 0: rc2 = launch(fmha_fwd_d128_kernel<0, true, true>, FMHA_THREADS, FMHA_SMEM_BYTES); break;
-      case 2: rc2 = launch(fmha_fwd_d128_kernel<2, true, true>, FMHA_THREADS, FMHA_SMEM_BYTES); break;
-      default: rc2 = launch(fmha_fwd_d128_kernel<1, true, true>, FMHA_THREADS, FMHA_SMEM_BYTES); break;
+      case 0: rc2 = launch(fmha_fwd_d128_kernel<0, true, true, false>, FMHA_THREADS, FMHA_SMEM_BYTES); break;
+      case 2: rc2 = launch(fmha_fwd_d128_kernel<2, true, true, false>, FMHA_THREADS, FMHA_SMEM_BYTES); break;
+      default: rc2 = launch(fmha_fwd_d128_kernel<1, true, true, false>, FMHA_THREADS, FMHA_SMEM_BYTES); break;
     }
   } else if (ver == 4) {
     switch (poly) {
-      case 0: rc2 = launch(fmha_fwd_d128_kernel<0, true, false>, FMHA_THREADS, FMHA_SMEM_BYTES); break;
-      case 2: rc2 = launch(fmha_fwd_d128_kernel<2, true, false>, FMHA_THREADS, FMHA_SMEM_BYTES); break;
-      default: rc2 = launch(fmha_fwd_d128_kernel<1, true, false>, FMHA_THREADS, FMHA_SMEM_BYTES); break;
+      case 0: rc2 = launch(fmha_fwd_d128_kernel<0, true, false, false>, FMHA_THREADS, FMHA_SMEM_BYTES); break;
+      case 2: rc2 = launch(fmha_fwd_d128_kernel<2, true, false, false>, FMHA_THREADS, FMHA_SMEM_BYTES); break;
+      default: rc2 = launch(fmha_fwd_d128_kernel<1, true, false, false>, FMHA_THREADS, FMHA_SMEM_BYTES); break;
     }
   } else {
     switch (poly) {
-      case 0: rc2 = launch(fmha_fwd_d128_kernel<0, false, false>, FMHA_THREADS, FMHA_SMEM_BYTES); break;
-      case 2: rc2 = launch(fmha_fwd_d128_kernel<2, false, false>, FMHA_THREADS, FMHA_SMEM_BYTES); break;
-      case 3: rc2 = launch(fmha_fwd_d128_kernel<3, false, false>, FMHA_THREADS, FMHA_SMEM_BYTES); break;
-      default: rc2 = launch(fmha_fwd_d128_kernel<1, false, false>, FMHA_THREADS, FMHA_SMEM_BYTES); break;
+      case 0: rc2 = launch(fmha_fwd_d128_kernel<0, false, false, false>, FMHA_THREADS, FMHA_SMEM_BYTES); break;
+      case 2: rc2 = launch(fmha_fwd_d128_kernel<2, false, false, false>, FMHA_THREADS, FMHA_SMEM_BYTES); break;
+      case 3: rc2 = launch(fmha_fwd_d128_kernel<3, false, false, false>, FMHA_THREADS, FMHA_SMEM_BYTES); break;
+      default: rc2 = launch(fmha_fwd_d128_kernel<1, false, false, false>, FMHA_THREADS, FMHA_SMEM_BYTES); break;
     }
   }
   if (rc2) return rc2;
