@@ -125,6 +125,30 @@ int b200_conv3d_cl(const void* in, int64_t in_st, int64_t in_sh, int64_t in_sw, 
                    int64_t res_sw, int T, int H, int W, int cin, int cout, int ntaps, const int32_t* taps, int clamp_out,
                    b200_stream_t stream);
 
+/* ---- HunyuanVideo causal 3-D VAE decoder ------------------------------------------------------------------------------ */
+
+/* b200_conv3d_cl with a separate extent (in_T, in_H, in_W) for the input view: the producer has already written the
+ * convolution's border into the tensor (replicate padding of CausalConv3d.forward,
+ * lightx2v/models/video_encoders/hf/autoencoder_kl_causal_3d/unet_causal_3d_blocks.py:88-91), so `taps` are non-negative
+ * offsets into the padded view and the output extent (T, H, W) is smaller than the input's.  cin multiple of 64 with
+ * cout multiple of 128 / 256 selects the 128-byte-swizzle tiles used by the 128 / 256 / 512-channel stages. */
+int b200_conv3d_cl_padded(const void* in, int64_t in_st, int64_t in_sh, int64_t in_sw, int in_T, int in_H, int in_W, const void* wt,
+                          const void* bias, void* out, int64_t out_st, int64_t out_sh, int64_t out_sw, const void* residual,
+                          int64_t res_st, int64_t res_sh, int64_t res_sw, int T, int H, int W, int cin, int cout, int ntaps,
+                          const int32_t* taps, int clamp_out, b200_stream_t stream);
+
+/* sums[0:32] = per-group sum, sums[32:64] = per-group sum of squares (fp64, device; zeroed by the call) of a channels-last bf16
+ * tensor [voxels, C], 32 groups of C/32 consecutive channels, C in {64,128,256,512}.  First half of torch.nn.GroupNorm as used by
+ * ResnetBlockCausal3D.norm1/norm2, Attention.group_norm and DecoderCausal3D.conv_norm_out (unet_causal_3d_blocks.py:313,332;
+ * vae.py:209). */
+int b200_gn_stats_cl(const void* x, int64_t voxels, int C, double* sums, b200_stream_t stream);
+
+/* y[T+pt, H+2ph, W+2pw, C] = replicate_pad( [silu]( (x - mean_g) * rsqrt(var_g + eps) * gamma + beta ) ), statistics from
+ * b200_gn_stats_cl; sums == NULL -> plain replicate-pad copy.  GroupNorm -> SiLU -> F.pad(mode="replicate") of
+ * ResnetBlockCausal3D.forward + CausalConv3d.forward (unet_causal_3d_blocks.py:364-412, 88-91). */
+int b200_gn_apply_pad_cl(const void* x, void* y, const double* sums, const float* gamma, const float* beta, float eps, int T, int H,
+                         int W, int C, int pt, int ph, int pw, int apply_silu, b200_stream_t stream);
+
 /* y[v, :] = [silu] ( x[v, :] / max(||x[v, :]||_2, 1e-12) * sqrt(C) * gamma ) over `voxels` channels-last rows of C in {96,192,384}.
  * Replaces RMS_norm.forward + nn.SiLU (vae.py:47-59, 192-195, 430-433). */
 int b200_rms_silu_cl(const void* x, void* y, const float* gamma, int64_t voxels, int C, int apply_silu, b200_stream_t stream);

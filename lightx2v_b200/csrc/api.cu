@@ -23,10 +23,13 @@ int quant_fp8_per_token(const void* x, long long ldx, void* q8, long long ldq, f
 int ln_modulate_fp8(const void* x, long long ldx, void* q8, long long ldq, float* q_scale, const void* ln_w,
                     const void* ln_b, const void* scale, const void* shift, long long rows, int D, float eps,
                     cudaStream_t stream);
-int conv3d_cl(const void* in, long long in_st, long long in_sh, long long in_sw, const void* wt, const void* bias,
-              void* out, long long out_st, long long out_sh, long long out_sw, const void* residual, long long res_st,
-              long long res_sh, long long res_sw, int T, int H, int W, int cin, int cout, int ntaps, const int* taps,
-              int clamp_out, cudaStream_t stream);
+int conv3d_cl(const void* in, long long in_st, long long in_sh, long long in_sw, int in_T, int in_H, int in_W, const void* wt,
+              const void* bias, void* out, long long out_st, long long out_sh, long long out_sw, const void* residual,
+              long long res_st, long long res_sh, long long res_sw, int T, int H, int W, int cin, int cout, int ntaps,
+              const int* taps, int clamp_out, cudaStream_t stream);
+int gn_stats_cl(const void* x, long long voxels, int C, double* sums, cudaStream_t stream);
+int gn_apply_pad_cl(const void* x, void* y, const double* sums, const float* gamma, const float* beta, float eps, int T, int H, int W,
+                    int C, int pt, int ph, int pw, int apply_silu, cudaStream_t stream);
 int rms_silu_cl(const void* x, void* y, const float* gamma, long long voxels, int C, int apply_silu, cudaStream_t stream);
 int latent_to_cl(const float* z, void* out, const float* mean, const float* inv_std, long long voxels, int CZ, int CP,
                  cudaStream_t stream);
@@ -96,8 +99,25 @@ int b200_conv3d_cl(const void* in, int64_t in_st, int64_t in_sh, int64_t in_sw, 
                    int64_t out_st, int64_t out_sh, int64_t out_sw, const void* residual, int64_t res_st, int64_t res_sh,
                    int64_t res_sw, int T, int H, int W, int cin, int cout, int ntaps, const int32_t* taps, int clamp_out,
                    b200_stream_t stream) {
-  return b200::conv3d_cl(in, in_st, in_sh, in_sw, wt, bias, out, out_st, out_sh, out_sw, residual, res_st, res_sh, res_sw, T,
-                         H, W, cin, cout, ntaps, taps, clamp_out, reinterpret_cast<cudaStream_t>(stream));
+  return b200::conv3d_cl(in, in_st, in_sh, in_sw, T, H, W, wt, bias, out, out_st, out_sh, out_sw, residual, res_st, res_sh, res_sw,
+                         T, H, W, cin, cout, ntaps, taps, clamp_out, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int b200_conv3d_cl_padded(const void* in, int64_t in_st, int64_t in_sh, int64_t in_sw, int in_T, int in_H, int in_W, const void* wt,
+                          const void* bias, void* out, int64_t out_st, int64_t out_sh, int64_t out_sw, const void* residual,
+                          int64_t res_st, int64_t res_sh, int64_t res_sw, int T, int H, int W, int cin, int cout, int ntaps,
+                          const int32_t* taps, int clamp_out, b200_stream_t stream) {
+  return b200::conv3d_cl(in, in_st, in_sh, in_sw, in_T, in_H, in_W, wt, bias, out, out_st, out_sh, out_sw, residual, res_st, res_sh,
+                         res_sw, T, H, W, cin, cout, ntaps, taps, clamp_out, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int b200_gn_stats_cl(const void* x, int64_t voxels, int C, double* sums, b200_stream_t stream) {
+  return b200::gn_stats_cl(x, voxels, C, sums, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int b200_gn_apply_pad_cl(const void* x, void* y, const double* sums, const float* gamma, const float* beta, float eps, int T, int H,
+                         int W, int C, int pt, int ph, int pw, int apply_silu, b200_stream_t stream) {
+  return b200::gn_apply_pad_cl(x, y, sums, gamma, beta, eps, T, H, W, C, pt, ph, pw, apply_silu, reinterpret_cast<cudaStream_t>(stream));
 }
 
 int b200_rms_silu_cl(const void* x, void* y, const float* gamma, int64_t voxels, int C, int apply_silu, b200_stream_t stream) {

@@ -20,33 +20,38 @@ namespace b200 {
 
 constexpr int CONV_BLOCK_M = 128;            // voxels per tile: 32 (w) x 4 (h)
 constexpr int CONV_BW = 32, CONV_BH = 4;
-constexpr int CONV_KC = 32;                  // channels per K-chunk: 64-byte rows, SWIZZLE_64B
-constexpr int CONV_CHUNKS = 3;               // chunks per pipeline stage (3 x 32 = 96 channels: one tap of the 96-channel stage)
-constexpr int CONV_STAGES = 3;
 constexpr int CONV_THREADS = 256;
 constexpr int CONV_MAX_TAPS = 27;
-constexpr int CONV_A_CHUNK_BYTES = CONV_BLOCK_M * CONV_KC * 2;   // 8 KB
 constexpr int CONV_STAGING_BYTES = CONV_BLOCK_M * 64 * 2;        // 16 KB (64 output channels per store chunk)
 
 // M_SUB sub-tiles of 128 voxels (32 w x 4 h each, stacked along h) share one weight tile: with the narrow N of the VAE
 // (96 / 192 output channels) a 128-voxel tile gives only ~290 tensor cycles per pipeline stage, far below the TMA round trip;
 // two sub-tiles double the MMA work per byte of weight traffic and per barrier.
+//
+// Two K-chunk geometries: the Wan widths (96 / 192 / 384 channels) use 32-channel chunks (64-byte rows, SWIZZLE_64B), three per
+// pipeline stage (= one tap of the 96-channel stage); the power-of-two widths of the HunyuanVideo decoder (128 / 256 / 512) use
+// 64-channel chunks (128-byte rows, SWIZZLE_128B), one per stage, four stages.
 template <int BLOCK_N>
 struct ConvCfg {
-  static constexpr int kMSub = (BLOCK_N <= 96) ? 2 : 1;
-  static constexpr int kBChunkBytes = BLOCK_N * CONV_KC * 2;
-  static constexpr int kStageBytes = CONV_CHUNKS * (kMSub * CONV_A_CHUNK_BYTES + kBChunkBytes);
+  static constexpr bool kWide = (BLOCK_N == 128 || BLOCK_N == 256);
+  static constexpr int kKC = kWide ? 64 : 32;                  // channels per K-chunk
+  static constexpr int kChunks = kWide ? 1 : 3;                // chunks per pipeline stage
+  static constexpr int kStages = kWide ? 4 : 3;
+  static constexpr int kMSub = (BLOCK_N <= 128) ? 2 : 1;
+  static constexpr int kAChunkBytes = CONV_BLOCK_M * kKC * 2;  // 8 KB / 16 KB
+  static constexpr int kBChunkBytes = BLOCK_N * kKC * 2;
+  static constexpr int kStageBytes = kChunks * (kMSub * kAChunkBytes + kBChunkBytes);
   static constexpr int kAccCols = kMSub * BLOCK_N;                       // TMEM columns of one accumulator stage
   static constexpr int kTmemCols = (2 * kAccCols <= 128) ? 128 : (2 * kAccCols <= 256 ? 256 : 512);
   // epilogue staging buffers: two unless that would exceed the 227 KB of shared memory (BLOCK_N = 96 with two sub-tiles)
-  static constexpr int kNumStaging = (CONV_STAGES * kStageBytes + 2 * CONV_STAGING_BYTES + 1280 <= 232448) ? 2 : 1;
-  static constexpr int kSmemBytes = CONV_STAGES * kStageBytes + kNumStaging * CONV_STAGING_BYTES + 1024 + 256;
+  static constexpr int kNumStaging = (kStages * kStageBytes + 2 * CONV_STAGING_BYTES + 1280 <= 232448) ? 2 : 1;
+  static constexpr int kSmemBytes = kStages * kStageBytes + kNumStaging * CONV_STAGING_BYTES + 1024 + 256;
   static_assert(kSmemBytes <= 232448, "shared memory budget exceeded");
 };
 
 struct ConvParams {
-  int T, H, W;                 // output extent in tiles' coordinate system (== input view extent)
-  int cin, cout;               // cin multiple of 32, cout multiple of 16
+  int T, H, W;                 // output extent (tile coordinate system); the input view may be larger (pre-padded input)
+  int cin, cout;               // cin multiple of the K-chunk, cout multiple of 16
   int ntaps;
   int8_t dt[CONV_MAX_TAPS], dh[CONV_MAX_TAPS], dw[CONV_MAX_TAPS];
   int tiles_w, tiles_h, num_n_blocks;
@@ -66,6 +71,8 @@ conv3d_igemm_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_const
   using Cfg = ConvCfg<BLOCK_N>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  constexpr int CONV_KC = Cfg::kKC, CONV_CHUNKS = Cfg::kChunks, CONV_STAGES = Cfg::kStages, CONV_A_CHUNK_BYTES = Cfg::kAChunkBytes;
+  constexpr uint32_t kDescHi = Cfg::kWide ? kDescHiSw128 : kDescHiSw64;
   uint8_t* sStage = smem + CONV_STAGES * Cfg::kStageBytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(sStage + Cfg::kNumStaging * CONV_STAGING_BYTES);
   uint64_t* full_bar = bars;
@@ -171,10 +178,10 @@ conv3d_igemm_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_const
 #pragma unroll
             for (int ms = 0; ms < Cfg::kMSub; ++ms) {
 #pragma unroll
-              for (int k = 0; k < CONV_KC / 16; ++k) {   // two K=16 MMAs per 32-channel chunk: +32 B inside the 64-byte swizzle row
+              for (int k = 0; k < CONV_KC / 16; ++k) {   // K=16 MMAs per chunk: +32 B inside the swizzled row
                 const uint32_t accum = (ks | c | k) != 0 ? 1u : 0u;
-                mma_f16_ss_w(d_tmem + ms * BLOCK_N, a_lo + (c * Cfg::kMSub + ms) * (CONV_A_CHUNK_BYTES >> 4) + 2 * k, kDescHiSw64,
-                             b_lo + c * (Cfg::kBChunkBytes >> 4) + 2 * k, kDescHiSw64, idesc, accum);
+                mma_f16_ss_w(d_tmem + ms * BLOCK_N, a_lo + (c * Cfg::kMSub + ms) * (CONV_A_CHUNK_BYTES >> 4) + 2 * k, kDescHi,
+                             b_lo + c * (Cfg::kBChunkBytes >> 4) + 2 * k, kDescHi, idesc, accum);
               }
             }
           }
@@ -325,13 +332,16 @@ static int launch_conv(const CUtensorMap& tmIn, const CUtensorMap& tmW, const CU
 // out : channels-last view  [T, H, W, cout] bf16, element strides (out_st, out_sh, out_sw)
 // wt  : [cout, ntaps * cin] bf16 row-major (tap-major K order)
 // taps: ntaps x (dt, dh, dw) input offsets
-int conv3d_cl(const void* in, long long in_st, long long in_sh, long long in_sw, const void* wt, const void* bias,
-              void* out, long long out_st, long long out_sh, long long out_sw, const void* residual, long long res_st,
-              long long res_sh, long long res_sw, int T, int H, int W, int cin, int cout, int ntaps, const int* taps,
-              int clamp_out, cudaStream_t stream) {
+// in_T / in_H / in_W : extent of the input view (>= the output extent when the producer wrote a pre-padded tensor, e.g. the
+//                       replicate padding of the HunyuanVideo CausalConv3d; taps are then non-negative offsets into it).
+//                       Reads outside the input view return zero.
+int conv3d_cl(const void* in, long long in_st, long long in_sh, long long in_sw, int in_T, int in_H, int in_W, const void* wt,
+              const void* bias, void* out, long long out_st, long long out_sh, long long out_sw, const void* residual,
+              long long res_st, long long res_sh, long long res_sw, int T, int H, int W, int cin, int cout, int ntaps,
+              const int* taps, int clamp_out, cudaStream_t stream) {
   B200_CHECK_ARG(in && wt && out && taps, "b200_conv3d_cl: null pointer");
-  B200_CHECK_ARG(T > 0 && H > 0 && W > 0, "b200_conv3d_cl: empty extent");
-  B200_CHECK_ARG(cin % CONV_KC == 0 && cin > 0, "b200_conv3d_cl: cin (%d) must be a multiple of 32 (pad with zero channels)", cin);
+  B200_CHECK_ARG(T > 0 && H > 0 && W > 0 && in_T > 0 && in_H > 0 && in_W > 0, "b200_conv3d_cl: empty extent");
+  B200_CHECK_ARG(cin % 32 == 0 && cin > 0, "b200_conv3d_cl: cin (%d) must be a multiple of 32 (pad with zero channels)", cin);
   B200_CHECK_ARG(cout % 16 == 0 && cout > 0, "b200_conv3d_cl: cout (%d) must be a multiple of 16 (pad with zero filters)", cout);
   B200_CHECK_ARG(ntaps >= 1 && ntaps <= CONV_MAX_TAPS, "b200_conv3d_cl: ntaps %d out of range", ntaps);
   B200_CHECK_ARG(in_sw % 8 == 0 && in_sh % 8 == 0 && in_st % 8 == 0 && out_sw % 8 == 0 && out_sh % 8 == 0 && out_st % 8 == 0,
@@ -340,7 +350,9 @@ int conv3d_cl(const void* in, long long in_st, long long in_sh, long long in_sw,
                  "b200_conv3d_cl: pointers must be 16-byte aligned");
 
   int block_n;
-  if (cout % 192 == 0) block_n = 192;
+  if (cout % 256 == 0 && cin % 64 == 0) block_n = 256;
+  else if (cout % 128 == 0 && cin % 64 == 0) block_n = 128;
+  else if (cout % 192 == 0) block_n = 192;
   else if (cout % 96 == 0) block_n = 96;
   else if (cout <= 16) block_n = 16;
   else if (cout % 64 == 0) block_n = 64;
@@ -349,19 +361,22 @@ int conv3d_cl(const void* in, long long in_st, long long in_sh, long long in_sw,
     return B200_ERR_UNSUPPORTED;
   }
 
+  const bool wide = block_n == 128 || block_n == 256;
+  const int kc = wide ? 64 : 32;
+  const CUtensorMapSwizzle swz = wide ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
   CUtensorMap tmIn, tmW, tmOut;
   int rc;
   {
-    uint64_t dims[4] = {(uint64_t)cin, (uint64_t)W, (uint64_t)H, (uint64_t)T};
+    uint64_t dims[4] = {(uint64_t)cin, (uint64_t)in_W, (uint64_t)in_H, (uint64_t)in_T};
     uint64_t strides[3] = {(uint64_t)in_sw * 2, (uint64_t)in_sh * 2, (uint64_t)in_st * 2};
-    uint32_t box[4] = {CONV_KC, CONV_BW, CONV_BH, 1};
-    if ((rc = encode_tmap(&tmIn, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, in, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_64B))) return rc;
+    uint32_t box[4] = {(uint32_t)kc, CONV_BW, CONV_BH, 1};
+    if ((rc = encode_tmap(&tmIn, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, in, dims, strides, box, swz))) return rc;
   }
   {
     uint64_t dims[2] = {(uint64_t)ntaps * cin, (uint64_t)cout};
     uint64_t strides[1] = {(uint64_t)ntaps * cin * 2};
-    uint32_t box[2] = {CONV_KC, (uint32_t)block_n};
-    if ((rc = encode_tmap(&tmW, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, wt, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_64B))) return rc;
+    uint32_t box[2] = {(uint32_t)kc, (uint32_t)block_n};
+    if ((rc = encode_tmap(&tmW, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, wt, dims, strides, box, swz))) return rc;
   }
   {
     uint64_t dims[4] = {(uint64_t)cout, (uint64_t)W, (uint64_t)H, (uint64_t)T};
@@ -386,7 +401,7 @@ int conv3d_cl(const void* in, long long in_st, long long in_sh, long long in_sw,
     p.dw[i] = (int8_t)taps[3 * i + 2];
   }
   p.tiles_w = (W + CONV_BW - 1) / CONV_BW;
-  const int msub = (block_n <= 96) ? 2 : 1;
+  const int msub = (block_n <= 128) ? 2 : 1;
   p.tiles_h = (H + CONV_BH * msub - 1) / (CONV_BH * msub);
   p.num_n_blocks = (cout + block_n - 1) / block_n;
   p.bias = reinterpret_cast<const __nv_bfloat16*>(bias);
@@ -396,6 +411,8 @@ int conv3d_cl(const void* in, long long in_st, long long in_sh, long long in_sw,
   p.res_sw = res_sw;
   p.clamp_out = clamp_out;
   switch (block_n) {
+    case 256: return launch_conv<256>(tmIn, tmW, tmOut, p, stream);
+    case 128: return launch_conv<128>(tmIn, tmW, tmOut, p, stream);
     case 192: return launch_conv<192>(tmIn, tmW, tmOut, p, stream);
     case 96: return launch_conv<96>(tmIn, tmW, tmOut, p, stream);
     case 64: return launch_conv<64>(tmIn, tmW, tmOut, p, stream);

@@ -1,0 +1,170 @@
+// GroupNorm(32 groups) + SiLU + replicate padding for the HunyuanVideo causal 3-D VAE decoder, channels-last bf16 [T, H, W, C].
+//
+// Replaces, per ResnetBlockCausal3D half (lightx2v/models/video_encoders/hf/autoencoder_kl_causal_3d/unet_causal_3d_blocks.py
+// :364-412): torch.nn.GroupNorm -> SiLU -> F.pad(mode="replicate") of CausalConv3d.forward (:88-91).  Two HBM-bound passes:
+//   gn_stats     : one read of the tensor -> per-group sum / sum of squares (fp32 per thread, fp64 across threads)
+//   gn_apply_pad : one read + one write: y = silu((x - mean) * rstd * gamma + beta) written into a tensor that already carries
+//                  the convolution's replicate border (pt frames in front, ph / pw pixels around), so that the implicit-GEMM
+//                  convolution (conv3d.cu) reads it with plain non-negative tap offsets and no padding logic of its own.
+// With sums == nullptr gn_apply_pad is a pure replicate-pad copy (input of the phase-decomposed UpsampleCausal3D, :146-200).
+#include "host_util.cuh"
+#include "ptx.cuh"
+
+namespace b200 {
+
+constexpr int GN_GROUPS = 32;
+
+template <int C>
+__global__ void __launch_bounds__(256)
+gn_stats_kernel(const __nv_bfloat16* __restrict__ x, long long voxels, double* __restrict__ sums) {
+  constexpr int LPV = C / 8;                    // threads per voxel (each owns 8 consecutive channels)
+  constexpr int VPB = 256 / LPV;                // voxels per block pass
+  constexpr int CPG = C / GN_GROUPS;            // channels per group
+  constexpr int GPT = (CPG >= 8) ? 1 : 8 / CPG; // groups touched by one thread
+  constexpr int EPG = 8 / GPT;                  // of its 8 elements, how many fall in one group
+  __shared__ float s_sum[GN_GROUPS], s_sq[GN_GROUPS];
+  if (threadIdx.x < GN_GROUPS) {
+    s_sum[threadIdx.x] = 0.f;
+    s_sq[threadIdx.x] = 0.f;
+  }
+  __syncthreads();
+  const int l = threadIdx.x % LPV, sub = threadIdx.x / LPV;
+  float s[GPT], q[GPT];
+#pragma unroll
+  for (int g = 0; g < GPT; ++g) s[g] = q[g] = 0.f;
+  for (long long v = (long long)blockIdx.x * VPB + sub; v < voxels; v += (long long)gridDim.x * VPB) {
+    const uint4 raw = *reinterpret_cast<const uint4*>(x + v * C + l * 8);
+    const float f[8] = {bf16_lo(raw.x), bf16_hi(raw.x), bf16_lo(raw.y), bf16_hi(raw.y), bf16_lo(raw.z), bf16_hi(raw.z), bf16_lo(raw.w), bf16_hi(raw.w)};
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      s[e / EPG] += f[e];
+      q[e / EPG] += f[e] * f[e];
+    }
+  }
+  // lanes of a warp that own the same channel slice (LPV < 32) are folded by shuffles before touching shared memory
+#pragma unroll
+  for (int g = 0; g < GPT; ++g) {
+#pragma unroll
+    for (int o = 16; o >= LPV; o >>= 1) {
+      s[g] += __shfl_xor_sync(0xffffffffu, s[g], o);
+      q[g] += __shfl_xor_sync(0xffffffffu, q[g], o);
+    }
+  }
+  if (LPV >= 32 || (threadIdx.x & 31) < LPV) {
+#pragma unroll
+    for (int g = 0; g < GPT; ++g) {
+      const int grp = (l * 8) / CPG + g;
+      atomicAdd(&s_sum[grp], s[g]);
+      atomicAdd(&s_sq[grp], q[g]);
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < GN_GROUPS) {
+    atomicAdd(&sums[threadIdx.x], (double)s_sum[threadIdx.x]);
+    atomicAdd(&sums[GN_GROUPS + threadIdx.x], (double)s_sq[threadIdx.x]);
+  }
+}
+
+int gn_stats_cl(const void* x, long long voxels, int C, double* sums, cudaStream_t stream) {
+  B200_CHECK_ARG(x && sums && voxels > 0, "b200_gn_stats_cl: bad arguments");
+  B200_CHECK_CUDA(cudaMemsetAsync(sums, 0, 2 * GN_GROUPS * sizeof(double), stream));
+  const auto* xp = reinterpret_cast<const __nv_bfloat16*>(x);
+  const int lpv = C / 8;
+  const long long passes = (voxels + (256 / (lpv > 0 ? lpv : 1)) - 1) / (256 / (lpv > 0 ? lpv : 1));
+  const int max_blocks = num_sms() * 8;
+  const int blocks = (int)(passes < max_blocks ? passes : max_blocks);
+  switch (C) {
+    case 64: gn_stats_kernel<64><<<blocks, 256, 0, stream>>>(xp, voxels, sums); break;
+    case 128: gn_stats_kernel<128><<<blocks, 256, 0, stream>>>(xp, voxels, sums); break;
+    case 256: gn_stats_kernel<256><<<blocks, 256, 0, stream>>>(xp, voxels, sums); break;
+    case 512: gn_stats_kernel<512><<<blocks, 256, 0, stream>>>(xp, voxels, sums); break;
+    default:
+      set_last_error("b200_gn_stats_cl: unsupported channel count %d (64 / 128 / 256 / 512)", C);
+      return B200_ERR_UNSUPPORTED;
+  }
+  B200_CHECK_CUDA(cudaGetLastError());
+  return B200_OK;
+}
+
+template <int C>
+__global__ void __launch_bounds__(256)
+gn_apply_pad_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, const double* __restrict__ sums,
+                    const float* __restrict__ gamma, const float* __restrict__ beta, float eps, double inv_count, int T, int H, int W,
+                    int pt, int ph, int pw, int apply_silu) {
+  constexpr int LPV = C / 8;
+  constexpr int VPB = 256 / LPV;
+  constexpr int CPG = C / GN_GROUPS;
+  const int l = threadIdx.x % LPV, sub = threadIdx.x / LPV;
+  float a[8], b[8];
+  if (sums != nullptr) {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int c = l * 8 + e;
+      const int grp = c / CPG;
+      const double mean = sums[grp] * inv_count;
+      const double var = fmax(sums[GN_GROUPS + grp] * inv_count - mean * mean, 0.0);
+      const float rstd = rsqrtf((float)var + eps);
+      a[e] = rstd * gamma[c];
+      b[e] = beta[c] - (float)mean * a[e];
+    }
+  } else {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      a[e] = 1.f;
+      b[e] = 0.f;
+    }
+  }
+  const int Hp = H + 2 * ph, Wp = W + 2 * pw;
+  const long long pvox = (long long)(T + pt) * Hp * Wp;
+  for (long long v = (long long)blockIdx.x * VPB + sub; v < pvox; v += (long long)gridDim.x * VPB) {
+    const int wp = (int)(v % Wp);
+    const long long r = v / Wp;
+    const int hp = (int)(r % Hp);
+    const int tp = (int)(r / Hp);
+    const int t = max(tp - pt, 0), h = min(max(hp - ph, 0), H - 1), w = min(max(wp - pw, 0), W - 1);
+    const uint4 raw = *reinterpret_cast<const uint4*>(x + (((long long)t * H + h) * W + w) * C + l * 8);
+    float f[8] = {bf16_lo(raw.x), bf16_hi(raw.x), bf16_lo(raw.y), bf16_hi(raw.y), bf16_lo(raw.z), bf16_hi(raw.z), bf16_lo(raw.w), bf16_hi(raw.w)};
+    if (sums != nullptr) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        float u = fmaf(f[e], a[e], b[e]);
+        if (apply_silu) u = u / (1.0f + __expf(-u));
+        f[e] = u;
+      }
+    }
+    uint4 o;
+    o.x = pack_bf16(f[0], f[1]); o.y = pack_bf16(f[2], f[3]); o.z = pack_bf16(f[4], f[5]); o.w = pack_bf16(f[6], f[7]);
+    *reinterpret_cast<uint4*>(y + v * C + l * 8) = o;
+  }
+}
+
+int gn_apply_pad_cl(const void* x, void* y, const double* sums, const float* gamma, const float* beta, float eps, int T, int H, int W,
+                    int C, int pt, int ph, int pw, int apply_silu, cudaStream_t stream) {
+  B200_CHECK_ARG(x && y && T > 0 && H > 0 && W > 0, "b200_gn_apply_pad_cl: bad arguments");
+  B200_CHECK_ARG(sums == nullptr || (gamma && beta), "b200_gn_apply_pad_cl: gamma / beta required with sums");
+  B200_CHECK_ARG(pt >= 0 && ph >= 0 && pw >= 0, "b200_gn_apply_pad_cl: negative padding");
+  const auto* xp = reinterpret_cast<const __nv_bfloat16*>(x);
+  auto* yp = reinterpret_cast<__nv_bfloat16*>(y);
+  const double inv_count = 1.0 / ((double)T * H * W * (C / GN_GROUPS));
+  const long long pvox = (long long)(T + pt) * (H + 2 * ph) * (W + 2 * pw);
+  const int vpb = 256 / (C / 8 > 0 ? C / 8 : 1);
+  const long long passes = (pvox + vpb - 1) / vpb;
+  const int max_blocks = num_sms() * 8;
+  const int blocks = (int)(passes < max_blocks ? passes : max_blocks);
+#define B200_GN_LAUNCH(CC) \
+  gn_apply_pad_kernel<CC><<<blocks, 256, 0, stream>>>(xp, yp, sums, gamma, beta, eps, inv_count, T, H, W, pt, ph, pw, apply_silu)
+  switch (C) {
+    case 64: B200_GN_LAUNCH(64); break;
+    case 128: B200_GN_LAUNCH(128); break;
+    case 256: B200_GN_LAUNCH(256); break;
+    case 512: B200_GN_LAUNCH(512); break;
+    default:
+      set_last_error("b200_gn_apply_pad_cl: unsupported channel count %d (64 / 128 / 256 / 512)", C);
+      return B200_ERR_UNSUPPORTED;
+  }
+#undef B200_GN_LAUNCH
+  B200_CHECK_CUDA(cudaGetLastError());
+  return B200_OK;
+}
+
+}  // namespace b200

@@ -33,6 +33,10 @@ SIGNATURES = {
     "b200_fmha_fwd_d128_scatter": (_i32, [_ptr, _i64, _ptr, _i64, _ptr, _i64, _ptr, _i32, _i64, _i64, _i32, _i64, _i64, _i32, _f32, _ptr]),
     "b200_conv3d_cl": (_i32, [_ptr, _i64, _i64, _i64, _ptr, _ptr, _ptr, _i64, _i64, _i64, _ptr, _i64, _i64, _i64, _i32, _i32, _i32, _i32, _i32,
                               _i32, _ptr, _i32, _ptr]),
+    "b200_conv3d_cl_padded": (_i32, [_ptr, _i64, _i64, _i64, _i32, _i32, _i32, _ptr, _ptr, _ptr, _i64, _i64, _i64, _ptr, _i64, _i64, _i64, _i32, _i32,
+                                     _i32, _i32, _i32, _i32, _ptr, _i32, _ptr]),
+    "b200_gn_stats_cl": (_i32, [_ptr, _i64, _i32, _ptr, _ptr]),
+    "b200_gn_apply_pad_cl": (_i32, [_ptr, _ptr, _ptr, _ptr, _ptr, _f32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _ptr]),
     "b200_rms_silu_cl": (_i32, [_ptr, _ptr, _ptr, _i64, _i32, _i32, _ptr]),
     "b200_latent_to_cl": (_i32, [_ptr, _ptr, _ptr, _ptr, _i64, _i32, _i32, _ptr]),
     "b200_cl_to_video": (_i32, [_ptr, _ptr, _i64, _i32, _ptr]),
@@ -224,6 +228,54 @@ def conv3d_cl(x: torch.Tensor, wt: torch.Tensor, bias: Optional[torch.Tensor], o
                                out.stride(1), out.stride(2), _p(residual), rs[0], rs[1], rs[2], T, H, W, cin, cout, len(taps),
                                ctypes.cast(tp, ctypes.c_void_p), 1 if clamp_out else 0, _stream())
     _check(rc, "b200_conv3d_cl")
+    return out
+
+
+def conv3d_cl_padded(xp: torch.Tensor, wt: torch.Tensor, bias: Optional[torch.Tensor], out: torch.Tensor, taps, *,
+                     residual: Optional[torch.Tensor] = None, clamp_out: bool = False) -> torch.Tensor:
+    """xp: pre-padded channels-last view [Tp, Hp, Wp, cin]; out: view [T, H, W, cout]; taps: non-negative (dt, dh, dw) offsets into xp."""
+    _req(xp, "xp"); _req(wt, "wt"); _req(out, "out")
+    Tp, Hp, Wp, cin = xp.shape
+    T, H, W, cout = out.shape
+    if wt.shape[0] != cout or wt.shape[1] != len(taps) * cin:
+        raise B200Error(f"conv3d_cl_padded: shape mismatch xp{tuple(xp.shape)} wt{tuple(wt.shape)} out{tuple(out.shape)} taps {len(taps)}")
+    tp = (ctypes.c_int32 * (3 * len(taps)))(*[int(v) for t3 in taps for v in t3])
+    rs = (0, 0, 0) if residual is None else (residual.stride(0), residual.stride(1), residual.stride(2))
+    rc = load().b200_conv3d_cl_padded(xp.data_ptr(), xp.stride(0), xp.stride(1), xp.stride(2), Tp, Hp, Wp, wt.data_ptr(), _p(bias), out.data_ptr(),
+                                      out.stride(0), out.stride(1), out.stride(2), _p(residual), rs[0], rs[1], rs[2], T, H, W, cin, cout, len(taps),
+                                      ctypes.cast(tp, ctypes.c_void_p), 1 if clamp_out else 0, _stream())
+    _check(rc, "b200_conv3d_cl_padded")
+    return out
+
+
+def gn_stats_cl(x: torch.Tensor, sums: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Per-group (32 groups) sum / sum-of-squares of a contiguous channels-last tensor [..., C] -> fp64 [64]."""
+    _req(x, "x")
+    if not x.is_contiguous():
+        raise B200Error("gn_stats_cl: x must be contiguous channels-last")
+    C = x.shape[-1]
+    if sums is None:
+        sums = torch.empty(64, dtype=torch.float64, device=x.device)
+    rc = load().b200_gn_stats_cl(x.data_ptr(), x.numel() // C, C, sums.data_ptr(), _stream())
+    _check(rc, "b200_gn_stats_cl")
+    return sums
+
+
+def gn_apply_pad_cl(x: torch.Tensor, sums: Optional[torch.Tensor], gamma: Optional[torch.Tensor], beta: Optional[torch.Tensor], *, eps: float = 1e-6,
+                    pad=(0, 0, 0), silu: bool = True, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """x [T, H, W, C] -> [T + pt, H + 2 ph, W + 2 pw, C]: GroupNorm(32) affine [+ SiLU] with a replicate border (sums None: copy)."""
+    _req(x, "x")
+    if not x.is_contiguous():
+        raise B200Error("gn_apply_pad_cl: x must be contiguous channels-last")
+    T, H, W, C = x.shape
+    pt, ph, pw = pad
+    if out is None:
+        out = torch.empty((T + pt, H + 2 * ph, W + 2 * pw, C), dtype=torch.bfloat16, device=x.device)
+    if sums is not None:
+        _req(gamma, "gamma", torch.float32); _req(beta, "beta", torch.float32)
+    rc = load().b200_gn_apply_pad_cl(x.data_ptr(), out.data_ptr(), _p(sums), _p(gamma), _p(beta), float(eps), T, H, W, C, pt, ph, pw, 1 if silu else 0,
+                                     _stream())
+    _check(rc, "b200_gn_apply_pad_cl")
     return out
 
 

@@ -205,7 +205,139 @@ def gen_hunyuan_fixture():
     print("hunyuan_blocks_small", float(x2.float().abs().max()), os.path.getsize(os.path.join(GOLD, "hunyuan_blocks_small.safetensors")))
 
 
+def install_diffusers_shim():
+    """`diffusers` is not installed in this image.  The reference's HunyuanVideo VAE files import it for (a) config / model mixins
+    and (b) ONE compute layer, `Attention` (mid-block, `_from_deprecated_attn_block=True`).  This shim supplies inert mixins and a
+    restatement of that layer's published algorithm (diffusers 0.31 `AttnProcessor2_0`): GroupNorm -> q/k/v Linear -> SDPA with the
+    additive mask -> to_out -> + residual -> / rescale.  Everything else on the decode path is the reference's own code."""
+    import inspect
+    from dataclasses import dataclass  # noqa: F401
+
+    import torch.nn as nn
+    import torch.nn.functional as F
+
+    def mod(name):
+        m = types.ModuleType(name)
+        sys.modules[name] = m
+        return m
+
+    d = mod("diffusers")
+    cu = mod("diffusers.configuration_utils")
+    ld = mod("diffusers.loaders")
+    ut = mod("diffusers.utils")
+    au = mod("diffusers.utils.accelerate_utils")
+    tu = mod("diffusers.utils.torch_utils")
+    md = mod("diffusers.models")
+    ap = mod("diffusers.models.attention_processor")
+    mo = mod("diffusers.models.modeling_outputs")
+    mu = mod("diffusers.models.modeling_utils")
+    ac = mod("diffusers.models.activations")
+    nm = mod("diffusers.models.normalization")
+    d.models = md
+
+    class ConfigMixin:
+        pass
+
+    def register_to_config(init):
+        def wrapped(self, *a, **k):
+            sig = inspect.signature(init)
+            bound = sig.bind(self, *a, **k)
+            bound.apply_defaults()
+            self.config = Cfg({n: v for n, v in bound.arguments.items() if n != "self"})
+            init(self, *a, **k)
+        return wrapped
+
+    cu.ConfigMixin, cu.register_to_config = ConfigMixin, register_to_config
+    ld.FromOriginalVAEMixin = type("FromOriginalVAEMixin", (), {})
+    au.apply_forward_hook = lambda f: f
+
+    class BaseOutput:
+        pass
+
+    class _Log:
+        def warn(self, *a, **k):
+            pass
+        warning = info = debug = warn
+
+    ut.BaseOutput = BaseOutput
+    ut.is_torch_version = lambda op, v: True
+    ut.logging = types.SimpleNamespace(get_logger=lambda name: _Log())
+    tu.randn_tensor = lambda shape, generator=None, device=None, dtype=None: torch.randn(shape, generator=generator, device=device, dtype=dtype)
+
+    class Attention(nn.Module):
+        def __init__(self, query_dim, heads=8, dim_head=64, rescale_output_factor=1.0, eps=1e-5, norm_num_groups=None, spatial_norm_dim=None,
+                     residual_connection=False, bias=False, upcast_softmax=False, _from_deprecated_attn_block=False, **kw):
+            super().__init__()
+            assert heads == 1 and spatial_norm_dim is None and _from_deprecated_attn_block
+            inner = heads * dim_head
+            self.group_norm = nn.GroupNorm(num_channels=query_dim, num_groups=norm_num_groups, eps=eps, affine=True)
+            self.to_q, self.to_k, self.to_v = nn.Linear(query_dim, inner, bias=bias), nn.Linear(query_dim, inner, bias=bias), nn.Linear(query_dim, inner, bias=bias)
+            self.to_out = nn.ModuleList([nn.Linear(inner, query_dim, bias=True), nn.Dropout(0.0)])
+            self.residual_connection, self.rescale_output_factor = residual_connection, rescale_output_factor
+
+        def forward(self, hidden_states, temb=None, attention_mask=None, **kw):
+            residual = hidden_states
+            h = self.group_norm(hidden_states.transpose(1, 2)).transpose(1, 2)
+            q, k, v = self.to_q(h).unsqueeze(1), self.to_k(h).unsqueeze(1), self.to_v(h).unsqueeze(1)
+            m = attention_mask.unsqueeze(1) if attention_mask is not None else None
+            o = F.scaled_dot_product_attention(q, k, v, attn_mask=m, dropout_p=0.0, is_causal=False).squeeze(1)
+            o = self.to_out[1](self.to_out[0](o))
+            if self.residual_connection:
+                o = o + residual
+            return o / self.rescale_output_factor
+
+    ap.Attention = Attention
+    for n in ("AttentionProcessor", "AttnAddedKVProcessor", "AttnProcessor", "SpatialNorm"):
+        setattr(ap, n, type(n, (nn.Module,), {}))
+    ap.ADDED_KV_ATTENTION_PROCESSORS, ap.CROSS_ATTENTION_PROCESSORS = (), ()
+    mo.AutoencoderKLOutput = type("AutoencoderKLOutput", (BaseOutput,), {})
+    mu.ModelMixin = type("ModelMixin", (nn.Module,), {})
+    ac.get_activation = lambda name: {"swish": nn.SiLU, "silu": nn.SiLU}[name]()
+    nm.AdaGroupNorm = type("AdaGroupNorm", (nn.Module,), {})
+    nm.RMSNorm = type("RMSNorm", (nn.Module,), {})
+
+
+def gen_hunyuan_vae_fixture():
+    """Real AutoencoderKLCausal3D (lightx2v/models/video_encoders/hf/autoencoder_kl_causal_3d/) decode with tiling enabled, exactly
+    the calls of VideoEncoderKLCausal3DModel.decode (model.py:33-44), fp32 on CPU, narrow widths (64, 64, 128, 128), sample_size 64 /
+    sample_tsize 16 so that a [16, 6, 12, 10] latent exercises temporal tiles (2), spatial tiles (2 x 2) and all three blends."""
+    from safetensors.torch import save_file
+
+    install_diffusers_shim()
+    from lightx2v.models.video_encoders.hf.autoencoder_kl_causal_3d.autoencoder_kl_causal_3d import AutoencoderKLCausal3D
+
+    from oracle import hunyuan_vae_oracle as HV
+
+    cfg = dict(HV.HUNYUAN_VAE_CFG, block_out_channels=(64, 64, 128, 128), sample_size=64, sample_tsize=16)
+    W = HV.synth_vae_weights(cfg, seed=3)
+    model = AutoencoderKLCausal3D(in_channels=3, out_channels=3, down_block_types=("DownEncoderBlockCausal3D",) * 4, up_block_types=("UpDecoderBlockCausal3D",) * 4,
+                                  block_out_channels=cfg["block_out_channels"], layers_per_block=2, act_fn="silu", latent_channels=16, norm_num_groups=32,
+                                  sample_size=cfg["sample_size"], sample_tsize=cfg["sample_tsize"], scaling_factor=cfg["scaling_factor"],
+                                  time_compression_ratio=4, spatial_compression_ratio=8, mid_block_add_attention=True).eval()
+    res = model.load_state_dict(W, strict=False)
+    assert not res.unexpected_keys, res.unexpected_keys
+    assert all(k.startswith("encoder.") or k.startswith("quant_conv.") for k in res.missing_keys), res.missing_keys
+    g = torch.Generator().manual_seed(11)
+    latents = torch.randn(1, 16, 6, 12, 10, generator=g)
+    with torch.no_grad():
+        z = latents / model.config.scaling_factor
+        model.enable_tiling()
+        image = model.decode(z, return_dict=False, generator=None)[0]
+        image = (image / 2 + 0.5).clamp(0, 1).float()
+        one = model.decoder(model.post_quant_conv(z[:, :, :3, :8, :8]))          # a single un-tiled tile, before the clamp
+    save_file({"latents": latents, "images": image.contiguous(), "tile_raw": one.contiguous()}, os.path.join(GOLD, "hunyuan_vae_decode_small.safetensors"),
+              metadata={"weights_seed": "3", "block_out_channels": "64,64,128,128", "sample_size": "64", "sample_tsize": "16",
+                        "generator": "oracle/gen_golden.py:gen_hunyuan_vae_fixture", "reference": "ModelTC/lightx2v@0591c35e"})
+    print("hunyuan_vae_decode_small", tuple(image.shape), "mean", float(image.mean()), "frac clamped", float(((image <= 0) | (image >= 1)).float().mean()),
+          "tile_raw absmax", float(one.abs().max()))
+
+
 if __name__ == "__main__":
+    if os.environ.get("GOLDEN_ONLY", "") == "hunyuan_vae":
+        install_shims()
+        os.makedirs(GOLD, exist_ok=True)
+        gen_hunyuan_vae_fixture()
+        sys.exit(0)
     if os.environ.get("GOLDEN_ONLY", "") == "hunyuan":
         install_shims()
         os.makedirs(GOLD, exist_ok=True)
@@ -223,3 +355,4 @@ if __name__ == "__main__":
         gen_scheduler_fixture()
         gen_vae_fixture()
         gen_hunyuan_fixture()
+        gen_hunyuan_vae_fixture()

@@ -1,0 +1,135 @@
+"""GPU parity of the HunyuanVideo causal 3-D VAE decode path (A17): GroupNorm kernels against torch.group_norm, the pre-padded
+implicit-GEMM convolution (128-byte-swizzle tiles for 128 / 256 / 512 channels) against F.conv3d with the reference's replicate
+padding, the phase-decomposed UpsampleCausal3D+conv against the oracle's upsample, one tile of the decoder at the TRUE widths
+(128, 256, 512, 512) against the oracle on the GPU, and the tiled decode (temporal + spatial tiles, three blends) against the fixture
+produced by the REAL AutoencoderKLCausal3D on CPU in fp32.  The reference computes in fp16; this path keeps bf16 activations with fp32
+accumulation and fp32/fp64 norm statistics, so results are PSNR with a stated floor plus max-abs caps on the [0, 1] image."""
+import os
+
+import pytest
+import torch
+import torch.nn.functional as F
+from safetensors import safe_open
+
+from oracle import hunyuan_vae_oracle as HV
+from oracle.wan_oracle import psnr
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from lightx2v_b200 import lib as L
+
+    L.load()
+    return L
+
+
+def _cl(x):      # [C, T, H, W] -> channels-last bf16 [T, H, W, C]
+    return x.permute(1, 2, 3, 0).contiguous().to(torch.bfloat16)
+
+
+def _cf(x):      # channels-last -> [C, T, H, W] fp32
+    return x.permute(3, 0, 1, 2).float()
+
+
+@pytest.mark.parametrize("C,T,H,W,pad,silu", [(64, 3, 9, 11, (2, 1, 1), True), (128, 2, 16, 33, (2, 1, 1), True), (256, 5, 8, 8, (0, 0, 0), False),
+                                              (512, 3, 7, 20, (2, 1, 1), True)])
+def test_group_norm_silu_pad(lib, C, T, H, W, pad, silu):
+    g = torch.Generator(device="cuda").manual_seed(C)
+    x = (torch.randn(C, T, H, W, generator=g, device="cuda") * 1.5 + 0.7).to(torch.bfloat16)
+    gamma = 1 + 0.2 * torch.randn(C, generator=g, device="cuda")
+    beta = 0.1 * torch.randn(C, generator=g, device="cuda")
+    xc = _cl(x)
+    sums = lib.gn_stats_cl(xc)
+    xf = x.float().view(32, -1).double()
+    assert torch.allclose(sums[:32], xf.sum(1), rtol=1e-5, atol=1e-3)
+    assert torch.allclose(sums[32:], (xf * xf).sum(1), rtol=1e-5, atol=1e-3)
+    got = _cf(lib.gn_apply_pad_cl(xc, sums, gamma, beta, eps=1e-6, pad=pad, silu=silu))
+    ref = F.group_norm(x.float().unsqueeze(0), 32, gamma, beta, 1e-6)
+    if silu:
+        ref = F.silu(ref)
+    if pad != (0, 0, 0):
+        ref = F.pad(ref, (pad[2], pad[2], pad[1], pad[1], pad[0], 0), mode="replicate")
+    assert got.shape == ref[0].shape
+    assert (got - ref[0]).abs().max() <= 1e-2 + 8e-3 * ref.abs().max()
+    # pure replicate-pad copy
+    cp = _cf(lib.gn_apply_pad_cl(xc, None, None, None, pad=(2, 1, 1)))
+    assert torch.equal(cp, F.pad(x.float().unsqueeze(0), (1, 1, 1, 1, 2, 0), mode="replicate")[0])
+
+
+@pytest.mark.parametrize("cin,cout,T,H,W", [(128, 128, 3, 12, 40), (256, 128, 2, 9, 33), (512, 256, 2, 8, 32), (512, 512, 3, 6, 16), (64, 512, 2, 8, 8),
+                                            (64, 64, 3, 10, 34), (128, 16, 2, 9, 70)])
+def test_conv3d_padded_vs_causal_replicate_conv(lib, cin, cout, T, H, W):
+    from lightx2v_b200.host.hunyuan_vae import PAD, _conv333
+
+    g = torch.Generator(device="cuda").manual_seed(cin + cout)
+    x = torch.randn(cin, T, H, W, generator=g, device="cuda").to(torch.bfloat16)
+    w = (torch.randn(cout, cin, 3, 3, 3, generator=g, device="cuda") / (cin * 27) ** 0.5).to(torch.bfloat16)
+    b = (torch.randn(cout, generator=g, device="cuda") * 0.1).to(torch.bfloat16)
+    torch.backends.cudnn.allow_tf32 = False
+    ref = HV.causal_conv3d({"c.conv.weight": w.float(), "c.conv.bias": b.float()}, "c", x.float().unsqueeze(0))[0]
+    conv = _conv333(w, b, "cuda")
+    xp = lib.gn_apply_pad_cl(_cl(x), None, None, None, pad=PAD)
+    got = _cf(conv(xp))[:cout]
+    assert (got - ref).abs().max() <= 2e-2 + 1e-2 * ref.abs().max()
+    assert psnr(got, ref) > 45
+    if cout >= 64:
+        res = torch.randn(T, H, W, cout, generator=g, device="cuda").to(torch.bfloat16)
+        got2 = _cf(conv(xp, residual=res))
+        assert psnr(got2, ref + _cf(res)) > 45
+
+
+@pytest.mark.parametrize("ft,C,T,H,W", [(2, 128, 4, 9, 20), (1, 128, 3, 8, 33), (2, 256, 2, 6, 8), (2, 64, 1, 5, 9)])
+def test_upsample_conv3d_phase_decomposition(lib, ft, C, T, H, W):
+    from lightx2v_b200.host.hunyuan_vae import _UpsampleConv3d
+
+    g = torch.Generator(device="cuda").manual_seed(3 + C + T)
+    x = torch.randn(C, T, H, W, generator=g, device="cuda").to(torch.bfloat16)
+    w = (torch.randn(C, C, 3, 3, 3, generator=g, device="cuda") / (C * 27) ** 0.5).to(torch.bfloat16)
+    b = (torch.randn(C, generator=g, device="cuda") * 0.1).to(torch.bfloat16)
+    torch.backends.cudnn.allow_tf32 = False
+    ref = HV.upsample({"u.conv.conv.weight": w.float(), "u.conv.conv.bias": b.float()}, "u", x.float().unsqueeze(0), (ft, 2, 2))[0]
+    got = _cf(_UpsampleConv3d(w, b, "cuda", ft)(_cl(x)))
+    assert got.shape == ref.shape
+    assert (got - ref).abs().max() <= 3e-2 + 1e-2 * ref.abs().max()
+    assert psnr(got, ref) > 42
+
+
+def test_decoder_tile_true_widths_vs_oracle_on_gpu():
+    """One un-tiled tile through the full-width decoder (128, 256, 512, 512): [16, 3, 12, 10] latent -> 9 frames of 96 x 80."""
+    from lightx2v_b200.host.hunyuan_vae import HunyuanVAEDecoderB200
+
+    cfg = dict(HV.HUNYUAN_VAE_CFG)
+    W = {k: v.cuda() for k, v in HV.synth_vae_weights(cfg, seed=5).items()}
+    g = torch.Generator(device="cuda").manual_seed(9)
+    lat = torch.randn(1, 16, 3, 12, 10, generator=g, device="cuda")
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    with torch.no_grad():
+        ref = HV.tile_decode(W, lat / cfg["scaling_factor"], cfg)[0]
+    out = HunyuanVAEDecoderB200(W, device="cuda").decode_tile(lat[0])
+    assert out.shape == ref.shape == (3, 9, 96, 80)
+    p = psnr(out, ref)
+    err = (out - ref).abs()
+    print(f"Hunyuan VAE tile (true widths) vs oracle on GPU: PSNR {p:.1f} dB, max abs err {err.max():.4f} of range {ref.abs().max():.2f}")
+    assert p > 35 and err.max() < 0.08 * ref.abs().max()
+
+
+def test_tiled_decode_vs_reference_fixture(golden_dir):
+    from lightx2v_b200.host.hunyuan_vae import HunyuanVAEB200
+
+    with safe_open(os.path.join(golden_dir, "hunyuan_vae_decode_small.safetensors"), framework="pt") as f:
+        lat, ref, tile_raw = f.get_tensor("latents"), f.get_tensor("images"), f.get_tensor("tile_raw")
+    cfg = dict(HV.HUNYUAN_VAE_CFG, block_out_channels=(64, 64, 128, 128), sample_size=64, sample_tsize=16)
+    vae = HunyuanVAEB200(HV.synth_vae_weights(cfg, seed=3), device="cuda", config=cfg)
+    one = vae.decoder.decode_tile(lat[0, :, :3, :8, :8].cuda()).cpu()
+    p1 = psnr(one, tile_raw[0])
+    print(f"Hunyuan VAE single tile vs real reference: PSNR {p1:.1f} dB, max abs err {(one - tile_raw[0]).abs().max():.4f}")
+    assert p1 > 35
+    out = vae.decode(lat.cuda(), None, None)
+    assert out.shape == ref.shape and out.device.type == "cpu" and out.dtype == torch.float32
+    p = psnr(out, ref)
+    err = (out - ref).abs()
+    print(f"Hunyuan VAE tiled decode vs real reference (fp32 CPU): PSNR {p:.1f} dB, max abs err {err.max():.4f}, mean {err.mean():.5f}")
+    assert p > 35 and err.max() < 0.1 and err.mean() < 1e-2

@@ -87,3 +87,23 @@ def test_hunyuan_oracle_matches_reference_fixture(golden_dir):
     assert torch.equal(img1, T["img_after_double"]) and torch.equal(txt1, T["txt_after_double"])
     x2 = HO.infer_single_block(W, 0, torch.cat((img1, txt1)), T["vec"], L_txt, cu, freqs, heads, hidden)
     assert torch.equal(x2, T["x_after_single"])
+
+
+def test_hunyuan_vae_oracle_matches_reference_fixture(golden_dir):
+    """oracle/hunyuan_vae_oracle.py vs the REAL AutoencoderKLCausal3D tiled decode (2 temporal x 2 x 2 spatial tiles, all three blends)
+    and one raw un-tiled decoder tile; fp32 convolutions -> tolerance 2e-5 (observed 1.5e-6 / 3.2e-6)."""
+    from oracle import hunyuan_vae_oracle as HV
+
+    T, meta = _load(os.path.join(golden_dir, "hunyuan_vae_decode_small.safetensors"))
+    cfg = dict(HV.HUNYUAN_VAE_CFG, block_out_channels=tuple(int(c) for c in meta["block_out_channels"].split(",")),
+               sample_size=int(meta["sample_size"]), sample_tsize=int(meta["sample_tsize"]))
+    W = HV.synth_vae_weights(cfg, seed=int(meta["weights_seed"]))
+    with torch.no_grad():
+        out = HV.decode(W, T["latents"], cfg)
+        one = HV.tile_decode(W, (T["latents"] / cfg["scaling_factor"])[:, :, :3, :8, :8], cfg)
+    assert out.shape == T["images"].shape == (1, 3, 21, 96, 80)
+    assert (out - T["images"]).abs().max().item() <= 2e-5
+    assert (one - T["tile_raw"]).abs().max().item() <= 5e-5
+    # frame-causal mask of the mid-block attention: token of frame i sees frames <= i only
+    m = HV.causal_frame_mask(3, 2, torch.float32, "cpu")
+    assert m.shape == (6, 6) and m[0, 2] == float("-inf") and m[2, 1] == 0 and m[5, 0] == 0 and m[3, 4] == float("-inf")

@@ -8,7 +8,7 @@ def child(kind):
     import torch
     from lightx2v_b200 import lib
     from tools.bringup import _time_cuda
-    if kind in ("fmha", "fmha3", "fmha4", "fmha5", "fmha6"):
+    if kind in ("fmha", "fmha3", "fmha4", "fmha5", "fmha6", "fmha7"):
         for (S, H) in ((75600, 40),):
             q = torch.randn(S, H, 128, device="cuda").bfloat16(); k = torch.randn(S, H, 128, device="cuda").bfloat16(); v = torch.randn(S, H, 128, device="cuda").bfloat16()
             o = torch.empty_like(q)
@@ -39,7 +39,7 @@ if __name__ == "__main__":
         child(sys.argv[1])
     else:
         kind = sys.argv[1]
-        var, vals = {"fmha": ("B200_FMHA_POLY", ["0", "1", "2"]), "fmha3": ("B200_FMHA_POLY", ["0", "1", "2"]), "fmha4": ("B200_FMHA_POLY", ["1"]), "fmha5": ("B200_FMHA_POLY", ["0", "1", "2"]), "fmha6": ("B200_FMHA_POLY", ["0", "1", "2"]), "gemm": ("B200_GEMM_GROUP_M", ["16"]), "gemm8": ("B200_X", ["0"])}[kind]
+        var, vals = {"fmha": ("B200_FMHA_POLY", ["0", "1", "2"]), "fmha3": ("B200_FMHA_POLY", ["0", "1", "2"]), "fmha4": ("B200_FMHA_POLY", ["1"]), "fmha5": ("B200_FMHA_POLY", ["0", "1", "2"]), "fmha6": ("B200_FMHA_POLY", ["0", "1", "2"]), "fmha7": ("B200_FMHA_POLY", ["0", "1"]), "gemm": ("B200_GEMM_GROUP_M", ["16"]), "gemm8": ("B200_X", ["0"])}[kind]
         for v in vals:
             env = dict(os.environ); env[var] = v
             if kind == "fmha": env["B200_FMHA_VER"] = "2"
@@ -47,4 +47,5 @@ if __name__ == "__main__":
             if kind == "fmha4": env["B200_FMHA_VER"] = "4"
             if kind == "fmha5": env["B200_FMHA_VER"] = "5"
             if kind == "fmha6": env["B200_FMHA_VER"] = "6"
+            if kind == "fmha7": env["B200_FMHA_VER"] = "7"
             subprocess.run([sys.executable, os.path.abspath(__file__), kind, "child"], env=env, cwd=ROOT)
