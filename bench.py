@@ -31,6 +31,9 @@ WORKLOADS = {
     # BASELINE config 3: w8a8-fp8 linears (weights quantised per out-channel at load), 4-step distilled sampler, no CFG
     "wan2.1-t2v-14b-fp8-distill-720p-81f": dict(dim=5120, num_heads=40, ffn_dim=13824, num_layers=40, target_shape=(16, 21, 90, 160), infer_steps=4,
                                                 enable_cfg=False, sample_guide_scale=1.0, sample_shift=5.0, fp8=True, distill=True),
+    # north_star's w4a4-nvfp4 weight path on the same distilled sampler (the reference ships the kernels but no model wiring for it)
+    "wan2.1-t2v-14b-nvfp4-distill-720p-81f": dict(dim=5120, num_heads=40, ffn_dim=13824, num_layers=40, target_shape=(16, 21, 90, 160), infer_steps=4,
+                                                  enable_cfg=False, sample_guide_scale=1.0, sample_shift=5.0, nvfp4=True, distill=True),
     "wan2.1-t2v-1.3b-480p-17f": dict(dim=1536, num_heads=12, ffn_dim=8960, num_layers=30, target_shape=(16, 5, 60, 104), infer_steps=50,
                                      enable_cfg=True, sample_guide_scale=5.0, sample_shift=5.0),   # quick self-test of this script
 }
@@ -142,6 +145,9 @@ def run_ours(args):
     if cfg.get("fp8"):
         from lightx2v_b200.host.ops import FP8_MM_KEY
         cfg["mm_config"] = {"mm_type": FP8_MM_KEY, "weight_auto_quant": True}
+    if cfg.get("nvfp4"):
+        from lightx2v_b200.host.ops import NVFP4_MM_KEY
+        cfg["mm_config"] = {"mm_type": NVFP4_MM_KEY}
     if cfg.get("distill"):
         cfg["denoising_step_list"] = [1000, 750, 500, 250]
     S, flops_step = step_flops(cfg)
@@ -164,7 +170,7 @@ def run_ours(args):
     fmha_events = []
     timing = {"on": False}
     native = {n: getattr(lib, n) for n in ("gemm_bf16", "ln_modulate", "rms_rope_", "fmha", "rms_rope_scatter", "fmha_scatter", "gemm_fp8",
-                                           "quant_fp8_per_token", "ln_modulate_fp8")}
+                                           "quant_fp8_per_token", "ln_modulate_fp8", "gemm_nvfp4", "quant_nvfp4", "nvfp4_act_scale")}
 
     def counted(name):
         fn = native[name]
@@ -283,7 +289,7 @@ def run_ours(args):
         out = {
             "metric": METRIC, "value": round(1000.0 / ms_resident, 5), "unit": "latents/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": round(ms_resident, 2), "higher_is_better": True, "scaling": "strong",
-            "vs_baseline": None, "dtype": "fp8-e4m3 linears, bf16 attention" if cfg.get("fp8") else "bf16",
+            "vs_baseline": None, "dtype": "fp8-e4m3 linears, bf16 attention" if cfg.get("fp8") else ("nvfp4 (e2m1 + ue4m3/16) linears, bf16 attention" if cfg.get("nvfp4") else "bf16"),
             "data": "synthetic latents/prompt embeddings, random-init weights of the named shapes",
             "config": {"workload": args.workload, "tokens": S, "forwards_per_step": 2 if cfg["enable_cfg"] else 1, "blocks": cfg["num_layers"],
                        "parallelism": f"ulysses{world}" if world > 1 else "single", "sp_exchange": sp_mode, "l2": "activations (774 MB/tensor) and weights (28 GB) exceed the 126 MB L2",
@@ -370,7 +376,60 @@ def run_hunyuan_blocks(args):
                       "unit": "latents/s", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms, 1), "higher_is_better": True,
                       "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
                       "config": {"workload": args.workload, "img_tokens": Li, "txt_tokens": Lt, "txt_valid": valid, "blocks": "20 double + 40 single"},
-                      "achieved_tflops": round(flops / (ms * 1e-3) / 1e12, 1), "model_tflop_per_step": round(flops / 1e12, 1)}))
+                      "achieved_tflops": round(flops / (ms * 1e-3) / 1e12, 1), "model_tflop_per_step": round(flops / 1e12, 1),
+                      "vae_decode": hunyuan_vae_decode_bench(dev) if args.vae else None}))
+
+
+def hunyuan_vae_decode_bench(dev):
+    """HunyuanVideo VAE decode of the 720p x 129f latent [1,16,33,90,160] with the reference's tiling (3 temporal x 28 spatial tiles),
+    through HunyuanVAEB200.decode (device->host copy of the fp32 video included in `wall_s`), next to the torch restatement of the
+    reference's fp16 cuDNN path on ONE full tile [16,17,32,32] of the same GPU (bounded sample; diffusers is absent on the box, so the
+    reference classes themselves cannot be imported there)."""
+    import time
+
+    from oracle import hunyuan_vae_oracle as HV
+    from lightx2v_b200.host.hunyuan_vae import HunyuanVAEB200
+
+    cfg = dict(HV.HUNYUAN_VAE_CFG)
+    W = {k: v.to(dev) for k, v in HV.synth_vae_weights(cfg, seed=5).items()}
+    vae = HunyuanVAEB200(W, device=dev)
+    g = torch.Generator(device=dev).manual_seed(1)
+    lat = torch.randn(1, 16, 33, 90, 160, generator=g, device=dev)
+    vae.decode_device(lat[:, :, :5, :32, :32])                                   # warm-up (kernel attribute setup, allocator)
+    torch.cuda.synchronize()
+    torch.cuda.reset_peak_memory_stats()
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.time()
+    s.record()
+    img = vae.decode_device(lat)
+    e.record()
+    out = img.cpu().float()
+    wall = time.time() - t0
+    ms = s.elapsed_time(e)
+    mpix = out.shape[2] * out.shape[3] * out.shape[4] / 1e6
+    res = {"unit": "MPix/s", "output": list(out.shape[1:]), "mpix": round(mpix, 2), "value": round(mpix / (ms * 1e-3), 1), "ms": round(ms, 1),
+           "wall_s_with_d2h": round(wall, 2), "tiles": "3 temporal x 4 x 7 spatial (25 % overlap, linear blends)",
+           "dtype": "bf16 activations, fp32 accumulate, fp32/fp64 GroupNorm statistics", "peak_mem_gb": round(torch.cuda.max_memory_allocated() / 2 ** 30, 1)}
+    tile = lat[:, :, :17, :32, :32]
+    s.record()
+    vae.decoder.decode_tile(tile[0])
+    e.record()
+    torch.cuda.synchronize()
+    ms_tile = s.elapsed_time(e)
+    Wh = {k: v.half() for k, v in W.items()}
+    with torch.no_grad():
+        zt = (tile / cfg["scaling_factor"]).half()
+        HV.tile_decode(Wh, zt[:, :, :3, :8, :8], cfg)                            # cuDNN warm-up
+        torch.cuda.synchronize()
+        s.record()
+        HV.tile_decode(Wh, zt, cfg)
+        e.record()
+        torch.cuda.synchronize()
+    ms_ref = s.elapsed_time(e)
+    res["gpu_reference"] = {"sample": "one full tile [16,17,32,32] -> [3,65,256,256], torch fp16 (cuDNN) restatement of the reference decoder",
+                            "ms_tile_reference": round(ms_ref, 1), "ms_tile_ours": round(ms_tile, 1), "speedup": round(ms_ref / ms_tile, 2),
+                            "value": round(mpix / (ms * 1e-3) * ms_tile / ms_ref, 1), "unit": "MPix/s (extrapolated by the tile ratio)"}
+    return res
 
 
 def cpu_reference_sample(cfg, flops_step, budget_s=20.0):

@@ -125,6 +125,29 @@ int b200_conv3d_cl(const void* in, int64_t in_st, int64_t in_sh, int64_t in_sw, 
                    int64_t res_sw, int T, int H, int W, int cin, int cout, int ntaps, const int32_t* taps, int clamp_out,
                    b200_stream_t stream);
 
+/* ---- w4a4 NVFP4 linears ------------------------------------------------------------------------------------------------- */
+
+/* bf16 x[rows, K] -> packed e2m1 q[rows, K/2] (two values per byte, low nibble = even element) + ue4m3 scale factors, one per 16
+ * elements, in the 128x4 layout of the block-scaled MMA: byte ((m/128)*(K/64) + g/4)*512 + (m%32)*16 + ((m%128)/32)*4 + g%4 for row m,
+ * group g; sf must hold roundup(rows,128)*K/16 bytes (padding rows are written as 0).  *global_scale (device fp32) = 448*6/amax(x).
+ * Replaces scaled_fp4_quant (lightx2v_kernel/python/lightx2v_kernel/gemm.py:11-52, csrc/gemm/nvfp4_quant_kernels_sm120.cu:118-290);
+ * arithmetic of lightx2v_kernel/test/nvfp4_nvfp4/fake_quant.py:37-51, bit for bit.  K multiple of 64. */
+int b200_quant_nvfp4(const void* x, int64_t ldx, int64_t rows, int K, const float* global_scale, void* q, int64_t ldq, void* sf,
+                     b200_stream_t stream);
+
+/* Dynamic per-tensor scales on the device: *global_scale = 448*6 / max|x| (lightx2v_kernel/docs/en_US/nvfp4_quantization_basics.md:52,
+ * test_bench1.py:120-121), *alpha = 1 / (*global_scale * *weight_global_scale) (test_bench1.py:126; alpha may be NULL).  scratch: 4 bytes. */
+int b200_nvfp4_act_scale(const void* x, int64_t ldx, int64_t rows, int K, const float* weight_global_scale, float* global_scale,
+                         float* alpha, void* scratch, b200_stream_t stream);
+
+/* C[M,N] = epilogue( (*alpha) * sum_k (A_q[m,k] sfa[m,k/16]) (B_q[n,k] sfb[n,k/16]) + bias[n] ), bf16 out, fp32 accumulate in TMEM
+ * (tcgen05.mma kind::mxf4nvf4.block_scale).  A [M,K/2], B [N,K/2] packed e2m1 (lda / ldb in bytes), scale factors as written by
+ * b200_quant_nvfp4, *alpha = 1 / (global_scale_a * global_scale_b) (device fp32).  Epilogues as b200_gemm_bf16.  K multiple of 64.
+ * Replaces cutlass_scaled_fp4_mm (lightx2v_kernel/python/lightx2v_kernel/gemm.py:4-8, csrc/gemm/nvfp4_scaled_mm_kernels_sm120.cu). */
+int b200_gemm_nvfp4(const void* A, int64_t lda, const void* B, int64_t ldb, const void* sfa, const void* sfb, const float* alpha, void* C,
+                    int64_t ldc, const void* bias, const void* gate, int64_t M, int64_t N, int64_t K, int epilogue, int block_n,
+                    int max_ctas, b200_stream_t stream);
+
 /* ---- HunyuanVideo causal 3-D VAE decoder ------------------------------------------------------------------------------ */
 
 /* b200_conv3d_cl with a separate extent (in_T, in_H, in_W) for the input view: the producer has already written the

@@ -27,6 +27,13 @@ int conv3d_cl(const void* in, long long in_st, long long in_sh, long long in_sw,
               const void* bias, void* out, long long out_st, long long out_sh, long long out_sw, const void* residual,
               long long res_st, long long res_sh, long long res_sw, int T, int H, int W, int cin, int cout, int ntaps,
               const int* taps, int clamp_out, cudaStream_t stream);
+int gemm_nvfp4(const void* A, long long lda, const void* B, long long ldb, const void* sfa, const void* sfb, const float* alpha,
+               void* C, long long ldc, const void* bias, const void* gate, long long M, long long N, long long K, int epilogue,
+               int block_n, int max_ctas, cudaStream_t stream);
+int quant_nvfp4(const void* x, long long ldx, long long rows, int K, const float* global_scale, void* q, long long ldq, void* sf,
+                cudaStream_t stream);
+int nvfp4_act_scale(const void* x, long long ldx, long long rows, int K, const float* weight_global_scale, float* global_scale,
+                    float* alpha, void* scratch, cudaStream_t stream);
 int gn_stats_cl(const void* x, long long voxels, int C, double* sums, cudaStream_t stream);
 int gn_apply_pad_cl(const void* x, void* y, const double* sums, const float* gamma, const float* beta, float eps, int T, int H, int W,
                     int C, int pt, int ph, int pw, int apply_silu, cudaStream_t stream);
@@ -109,6 +116,23 @@ int b200_conv3d_cl_padded(const void* in, int64_t in_st, int64_t in_sh, int64_t 
                           const int32_t* taps, int clamp_out, b200_stream_t stream) {
   return b200::conv3d_cl(in, in_st, in_sh, in_sw, in_T, in_H, in_W, wt, bias, out, out_st, out_sh, out_sw, residual, res_st, res_sh,
                          res_sw, T, H, W, cin, cout, ntaps, taps, clamp_out, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int b200_gemm_nvfp4(const void* A, int64_t lda, const void* B, int64_t ldb, const void* sfa, const void* sfb, const float* alpha, void* C,
+                    int64_t ldc, const void* bias, const void* gate, int64_t M, int64_t N, int64_t K, int epilogue, int block_n,
+                    int max_ctas, b200_stream_t stream) {
+  return b200::gemm_nvfp4(A, lda, B, ldb, sfa, sfb, alpha, C, ldc, bias, gate, M, N, K, epilogue, block_n, max_ctas,
+                          reinterpret_cast<cudaStream_t>(stream));
+}
+
+int b200_quant_nvfp4(const void* x, int64_t ldx, int64_t rows, int K, const float* global_scale, void* q, int64_t ldq, void* sf,
+                     b200_stream_t stream) {
+  return b200::quant_nvfp4(x, ldx, rows, K, global_scale, q, ldq, sf, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int b200_nvfp4_act_scale(const void* x, int64_t ldx, int64_t rows, int K, const float* weight_global_scale, float* global_scale,
+                         float* alpha, void* scratch, b200_stream_t stream) {
+  return b200::nvfp4_act_scale(x, ldx, rows, K, weight_global_scale, global_scale, alpha, scratch, reinterpret_cast<cudaStream_t>(stream));
 }
 
 int b200_gn_stats_cl(const void* x, int64_t voxels, int C, double* sums, b200_stream_t stream) {

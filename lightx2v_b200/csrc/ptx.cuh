@@ -294,6 +294,43 @@ __device__ __forceinline__ void mma_f8_ss_w(uint32_t d_tmem, uint32_t a_lo, uint
       "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// Block-scaled NVFP4 MMA (e2m1 x e2m1, one ue4m3 scale per 16 elements along K, K = 64 per instruction).  The scale factors
+// live in TMEM (4 bytes = 4 K-blocks per 32-bit column; rows r + 32 q of the operand in lane r, column q), put there by tcgen05.cp.
+__device__ __forceinline__ void mma_f4_bs_w(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                            uint32_t idesc, uint32_t sfa_tmem, uint32_t sfb_tmem, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p, e;\n\t"
+      ".reg .b64 da, db;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "setp.ne.b32 p, %6, 0;\n\t"
+      "mov.b64 da, {%1, %2};\n\t"
+      "mov.b64 db, {%3, %4};\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::mxf4nvf4.block_scale.scale_vec::4X [%0], da, db, %5, [%7], [%8], p;\n\t"
+      "}\n" ::"r"(d_tmem),
+      "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate), "r"(sfa_tmem), "r"(sfb_tmem)
+      : "memory");
+}
+// smem -> TMEM copy of 32 rows x 16 bytes, replicated into the four 32-lane sub-partitions (scale-factor staging).
+// Source: no-swizzle K-major core matrices (8 rows x 16 B contiguous), 8-row groups `SBO` bytes apart.
+__device__ __forceinline__ void tmem_cp_32x128b_w(uint32_t taddr, uint32_t desc_lo, uint32_t desc_hi) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred e;\n\t"
+      ".reg .b64 d;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "mov.b64 d, {%1, %2};\n\t"
+      "@e tcgen05.cp.cta_group::1.32x128b.warpx4 [%0], d;\n\t"
+      "}\n" ::"r"(taddr),
+      "r"(desc_lo), "r"(desc_hi)
+      : "memory");
+}
+// descriptor hi word for the scale-factor copy: SBO = 128 B (8-row groups are contiguous), version 1, no swizzle
+constexpr uint32_t kDescHiSfNoSwz = (128u >> 4) | (1u << 14);
+// instruction descriptor of kind::mxf4nvf4 (cute InstrDescriptorBlockScaled): a/b format E2M1 = 1, scale format ue4m3 = 0, K = 64
+__host__ __device__ constexpr uint32_t make_idesc_f4(uint32_t M, uint32_t N) {
+  return (1u << 7) | (1u << 10) | ((N >> 3) << 17) | (0u << 23) | ((M >> 4) << 24);
+}
 __device__ __forceinline__ void mma_f16_ts_w(uint32_t d_tmem, uint32_t a_tmem, uint32_t b_lo, uint32_t b_hi, uint32_t idesc,
                                              uint32_t accumulate) {
   asm volatile(

@@ -171,6 +171,109 @@ class MMWeightFp8B200(_WeightOp):
         return destination
 
 
+NVFP4_MM_KEY = "W-nvfp4-group16-A-nvfp4-group16-dynamic-B200"
+
+
+def quantize_weight_nvfp4(w: torch.Tensor):
+    """bf16 [N, K] (CUDA) -> (packed e2m1 uint8 [N, K/2], ue4m3 scale bytes uint8 [roundup(N,128), K/16] in the MMA layout,
+    global_scale fp32 [1] = 448 * 6 / max|w|) - the recipe of lightx2v_kernel/docs/en_US/nvfp4_quantization_basics.md:34-80 with the
+    arithmetic of test/nvfp4_nvfp4/fake_quant.py.  Runs on the GPU (the quantiser is a CUDA kernel; there is no CPU path)."""
+    w = w.to(torch.bfloat16).contiguous()
+    gs, _ = lib.nvfp4_act_scale(w)
+    q, sf = lib.quant_nvfp4(w, gs)
+    return q, sf, gs.clone()
+
+
+def quantize_checkpoint_nvfp4(weight_dict: Dict[str, torch.Tensor], names, device="cuda") -> Dict[str, torch.Tensor]:
+    """Offline converter for the w4a4 path: for every `<name>.weight` in `names` emit
+    `<name>.weight` (packed e2m1), `<name>.weight_scale` (swizzled ue4m3 bytes) and `<name>.weight_global_scale`;
+    everything else is passed through unchanged."""
+    out = dict(weight_dict)
+    for n in names:
+        q, sf, gs = quantize_weight_nvfp4(weight_dict[n].to(device))
+        base = n.removesuffix(".weight")
+        out[n], out[base + ".weight_scale"], out[base + ".weight_global_scale"] = q.cpu(), sf.cpu(), gs.cpu()
+    return out
+
+
+@MM_WEIGHT_REGISTER(NVFP4_MM_KEY)
+class MMWeightNvfp4B200(_WeightOp):
+    """w4a4 NVFP4 linear: packed e2m1 weight [N, K/2] + ue4m3 group scales + per-tensor global scale, dynamic per-tensor activation
+    scale computed on the device, `y = alpha * (xq @ wq^T) + b` with alpha = 1 / (gs_x * gs_w)  (cutlass_scaled_fp4_mm semantics,
+    lightx2v_kernel/python/lightx2v_kernel/gemm.py:4-52, test/nvfp4_nvfp4/test_bench1.py:106-138).  The reference has the kernels but
+    no MM_WEIGHT class or checkpoint loader for nvfp4; this class follows the fp8 template's contract:
+    a bf16 `<name>.weight` is quantised when it first reaches the GPU, a uint8 one must come with `weight_scale` and
+    `weight_global_scale` (see quantize_checkpoint_nvfp4)."""
+
+    is_nvfp4 = True
+    _attrs = ("weight", "weight_scale", "weight_global_scale", "bias")
+
+    def __init__(self, weight_name, bias_name, lazy_load=False, lazy_load_file=None):
+        self.weight_name = weight_name
+        self.bias_name = bias_name
+        base = weight_name.removesuffix(".weight")
+        self.weight_scale_name = base + ".weight_scale"
+        self.weight_global_scale_name = base + ".weight_global_scale"
+        self.lazy_load = lazy_load
+        self.lazy_load_file = lazy_load_file
+        self.config = {}
+        self.weight = self.weight_scale = self.weight_global_scale = self.bias = None
+        self._raw = None
+
+    def load(self, weight_dict):
+        w = weight_dict[self.weight_name]
+        if w.dtype == torch.uint8:
+            self.weight = w.contiguous()
+            self.weight_scale = weight_dict[self.weight_scale_name].view(torch.uint8).contiguous()
+            self.weight_global_scale = weight_dict[self.weight_global_scale_name].float().reshape(1)
+        else:
+            self._raw = w
+            if w.is_cuda:
+                self._quantize_raw()
+        self.bias = weight_dict[self.bias_name] if self.bias_name is not None else None
+
+    def _quantize_raw(self):
+        self.weight, self.weight_scale, self.weight_global_scale = quantize_weight_nvfp4(self._raw.cuda())
+        self._raw = None
+
+    @property
+    def out_features(self):
+        return (self.weight if self.weight is not None else self._raw).shape[0]
+
+    def to_cuda(self, non_blocking=False):
+        if self._raw is not None:
+            self._quantize_raw()
+        super().to_cuda(non_blocking)
+
+    def quantize_input(self, x: torch.Tensor):
+        """-> (packed activations, scale factors, global_scale): reusable across several weights that share the input."""
+        gs, _ = lib.nvfp4_act_scale(x)
+        xq, sfx = lib.quant_nvfp4(x, gs)
+        return xq, sfx, gs
+
+    def apply_q(self, xq3, *, out=None, epilogue: int = lib.EPI_BIAS, gate=None, block_n: int = 0):
+        xq, sfx, gs = xq3
+        alpha = torch.reciprocal(gs * self.weight_global_scale)
+        return lib.gemm_nvfp4(xq, self.weight, sfx, self.weight_scale, alpha, self.bias, out=out, epilogue=epilogue, gate=gate, block_n=block_n)
+
+    def apply(self, input_tensor, *, out=None, epilogue: int = lib.EPI_BIAS, gate=None):
+        if self.weight is None:
+            raise lib.B200Error(f"{self.weight_name}: weight not on the GPU yet (call to_cuda(); nvfp4 has no CPU path)")
+        gs, alpha = lib.nvfp4_act_scale(input_tensor, self.weight_global_scale)
+        xq, sfx = lib.quant_nvfp4(input_tensor, gs)
+        return lib.gemm_nvfp4(xq, self.weight, sfx, self.weight_scale, alpha, self.bias, out=out, epilogue=epilogue, gate=gate)
+
+    def state_dict(self, destination=None):
+        if destination is None:
+            destination = {}
+        destination[self.weight_name] = self.weight.cpu().detach().clone()
+        destination[self.weight_scale_name] = self.weight_scale.cpu().detach().clone()
+        destination[self.weight_global_scale_name] = self.weight_global_scale.cpu().detach().clone()
+        if self.bias is not None:
+            destination[self.bias_name] = self.bias.cpu().detach().clone()
+        return destination
+
+
 class RMSWeightB200(_WeightOp):
     """Full-row RMSNorm with the reference's bf16 rounding points (rms_norm_weight.py:111-113)."""
 

@@ -71,6 +71,9 @@ def install_into_lightx2v() -> bool:
 
     if MM_KEY not in rf.MM_WEIGHT_REGISTER:
         rf.MM_WEIGHT_REGISTER.register(ops.MMWeightB200, key=MM_KEY)
+    for key, cls in ((ops.FP8_MM_KEY, ops.MMWeightFp8B200), (ops.NVFP4_MM_KEY, ops.MMWeightNvfp4B200)):
+        if key not in rf.MM_WEIGHT_REGISTER:
+            rf.MM_WEIGHT_REGISTER.register(cls, key=key)
     if ATTN_KEY not in rf.ATTN_WEIGHT_REGISTER:
         rf.ATTN_WEIGHT_REGISTER.register(ops.FmhaWeightB200, key=ATTN_KEY)
     rf.RMS_WEIGHT_REGISTER["sgl-kernel"] = ops.RMSWeightB200

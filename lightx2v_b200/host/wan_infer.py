@@ -145,7 +145,11 @@ class WanTransformerInfer:
     # ------------------------------------------------------------------ bf16 / w8a8-fp8 dispatch
     @staticmethod
     def _is_fp8(mm) -> bool:
-        return getattr(mm, "weight_scale", None) is not None
+        return getattr(mm, "weight_scale", None) is not None and not getattr(mm, "is_nvfp4", False)
+
+    @staticmethod
+    def _is_f4(mm) -> bool:
+        return getattr(mm, "is_nvfp4", False)
 
     def _ln(self, x, fp8, name, **kw):
         """LayerNorm(+modulate) into the bf16 scratch buffer, or (fp8 mode) straight into e4m3 + per-token scale."""
@@ -158,6 +162,8 @@ class WanTransformerInfer:
 
     def _linear(self, mm, a, *, w=None, b=None, ws=None, out=None, epilogue=lib.EPI_BIAS, gate=None, qname="q8"):
         """y = epilogue(a @ W^T + b).  `a` is a bf16 tensor, or an (e4m3, scale) pair when the producer already quantised."""
+        if mm is not None and self._is_f4(mm):                     # w4a4: the op owns its packed weight and scale factors
+            return mm.apply(a, out=out, epilogue=epilogue, gate=gate)
         w = self._nk(mm) if w is None else w
         b = mm.bias if b is None and mm is not None else b
         if mm is not None and self._is_fp8(mm) or ws is not None:
@@ -193,14 +199,20 @@ class WanTransformerInfer:
         dev = x.device
         c = self._cache(weights)
         fp8 = self._is_fp8(weights.self_attn_q)
-        if c.wqkv is None:
+        f4 = self._is_f4(weights.self_attn_q)
+        if c.wqkv is None and not f4:
             c.wqkv = torch.cat([self._nk(weights.self_attn_q), self._nk(weights.self_attn_k), self._nk(weights.self_attn_v)], dim=0).contiguous()
             c.bqkv = torch.cat([weights.self_attn_q.bias, weights.self_attn_k.bias, weights.self_attn_v.bias]).contiguous()
             if fp8:
                 c.sqkv = torch.cat([m.weight_scale.reshape(-1) for m in (weights.self_attn_q, weights.self_attn_k, weights.self_attn_v)]).contiguous()
         n1 = self._ln(x, fp8, "a", scale=scale_msa, shift=shift_msa, eps=weights.norm1.eps)
         qkv = self._buf("qkv", (S, 3 * D), dev)
-        self._linear(None, n1, w=c.wqkv, b=c.bqkv, ws=c.sqkv, out=qkv)
+        if f4:      # one activation quantisation shared by the three projections (each weight has its own global scale)
+            xq3 = weights.self_attn_q.quantize_input(n1)
+            for i, mm in enumerate((weights.self_attn_q, weights.self_attn_k, weights.self_attn_v)):
+                mm.apply_q(xq3, out=qkv[:, i * D:(i + 1) * D])
+        else:
+            self._linear(None, n1, w=c.wqkv, b=c.bqkv, ws=c.sqkv, out=qkv)
         q, k, v = qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:]
         cs = self._rope_table(grid_sizes, freqs, S, dev)
         H, d = self.num_heads, self.head_dim
@@ -275,8 +287,9 @@ class WanTransformerInfer:
             x.add_(attn_out)
         fp8 = self._is_fp8(weights.ffn_0)
         n2 = self._ln(x, fp8, "a", scale=c_scale_msa, shift=c_shift_msa, eps=weights.norm2.eps)
-        w0 = self._nk(weights.ffn_0)
-        hidden = self._buf("h", (S, w0.shape[0]), dev)
+        f4 = self._is_f4(weights.ffn_0)
+        w0 = None if f4 else self._nk(weights.ffn_0)
+        hidden = self._buf("h", (S, weights.ffn_0.out_features if f4 else w0.shape[0]), dev)
         self._linear(weights.ffn_0, n2, w=w0, out=hidden, epilogue=lib.EPI_BIAS_GELU)
         if c_gate_msa is None:
             return self._linear(weights.ffn_2, hidden, qname="h8")

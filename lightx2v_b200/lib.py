@@ -35,6 +35,9 @@ SIGNATURES = {
                               _i32, _ptr, _i32, _ptr]),
     "b200_conv3d_cl_padded": (_i32, [_ptr, _i64, _i64, _i64, _i32, _i32, _i32, _ptr, _ptr, _ptr, _i64, _i64, _i64, _ptr, _i64, _i64, _i64, _i32, _i32,
                                      _i32, _i32, _i32, _i32, _ptr, _i32, _ptr]),
+    "b200_quant_nvfp4": (_i32, [_ptr, _i64, _i64, _i32, _ptr, _ptr, _i64, _ptr, _ptr]),
+    "b200_nvfp4_act_scale": (_i32, [_ptr, _i64, _i64, _i32, _ptr, _ptr, _ptr, _ptr, _ptr]),
+    "b200_gemm_nvfp4": (_i32, [_ptr, _i64, _ptr, _i64, _ptr, _ptr, _ptr, _ptr, _i64, _ptr, _ptr, _i64, _i64, _i64, _i32, _i32, _i32, _ptr]),
     "b200_gn_stats_cl": (_i32, [_ptr, _i64, _i32, _ptr, _ptr]),
     "b200_gn_apply_pad_cl": (_i32, [_ptr, _ptr, _ptr, _ptr, _ptr, _f32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _ptr]),
     "b200_rms_silu_cl": (_i32, [_ptr, _ptr, _ptr, _i64, _i32, _i32, _ptr]),
@@ -228,6 +231,49 @@ def conv3d_cl(x: torch.Tensor, wt: torch.Tensor, bias: Optional[torch.Tensor], o
                                out.stride(1), out.stride(2), _p(residual), rs[0], rs[1], rs[2], T, H, W, cin, cout, len(taps),
                                ctypes.cast(tp, ctypes.c_void_p), 1 if clamp_out else 0, _stream())
     _check(rc, "b200_conv3d_cl")
+    return out
+
+
+def quant_nvfp4(x: torch.Tensor, global_scale: torch.Tensor):
+    """bf16 [rows, K] -> (packed e2m1 uint8 [rows, K/2], ue4m3 scale factors uint8 [roundup(rows,128), K/16] in the 128x4 MMA layout)."""
+    _req(x, "x"); _req(global_scale, "global_scale", torch.float32)
+    rows, K = x.shape
+    q = torch.empty((rows, K // 2), dtype=torch.uint8, device=x.device)
+    sf = torch.empty(((rows + 127) // 128 * 128, K // 16), dtype=torch.uint8, device=x.device)
+    rc = load().b200_quant_nvfp4(x.data_ptr(), x.stride(0), rows, K, global_scale.data_ptr(), q.data_ptr(), q.stride(0), sf.data_ptr(), _stream())
+    _check(rc, "b200_quant_nvfp4")
+    return q, sf
+
+
+def nvfp4_act_scale(x: torch.Tensor, weight_global_scale: Optional[torch.Tensor] = None):
+    """-> (global_scale fp32 [1] = 2688 / max|x|, alpha fp32 [1] = 1 / (global_scale * weight_global_scale)), computed on the device."""
+    _req(x, "x")
+    rows, K = x.shape
+    buf = torch.empty(3, dtype=torch.float32, device=x.device)          # [global_scale, alpha, scratch]
+    rc = load().b200_nvfp4_act_scale(x.data_ptr(), x.stride(0), rows, K, _p(weight_global_scale), buf[0:1].data_ptr(), buf[1:2].data_ptr(),
+                                     buf[2:3].data_ptr(), _stream())
+    _check(rc, "b200_nvfp4_act_scale")
+    return buf[0:1], buf[1:2]
+
+
+def gemm_nvfp4(a_q: torch.Tensor, b_q: torch.Tensor, sfa: torch.Tensor, sfb: torch.Tensor, alpha: torch.Tensor, bias: Optional[torch.Tensor] = None, *,
+               out: Optional[torch.Tensor] = None, epilogue: int = EPI_BIAS, gate: Optional[torch.Tensor] = None, block_n: int = 0,
+               max_ctas: int = 0) -> torch.Tensor:
+    """out[M,N] = epilogue(alpha * dequant(a_q, sfa) @ dequant(b_q, sfb)^T + bias)  (cutlass_scaled_fp4_mm semantics)."""
+    _req(a_q, "a_q", torch.uint8); _req(b_q, "b_q", torch.uint8); _req(sfa, "sfa", torch.uint8); _req(sfb, "sfb", torch.uint8)
+    _req(alpha, "alpha", torch.float32)
+    M, K2 = a_q.shape
+    N, K2b = b_q.shape
+    if K2 != K2b:
+        raise B200Error(f"gemm_nvfp4: K mismatch {K2 * 2} vs {K2b * 2}")
+    if out is None:
+        if epilogue in (EPI_GATE_RESIDUAL, EPI_RESIDUAL):
+            raise B200Error("gemm_nvfp4: residual epilogues need out= (the residual stream, updated in place)")
+        out = torch.empty((M, N), dtype=torch.bfloat16, device=a_q.device)
+    _req(out, "out")
+    rc = load().b200_gemm_nvfp4(a_q.data_ptr(), a_q.stride(0), b_q.data_ptr(), b_q.stride(0), sfa.data_ptr(), sfb.data_ptr(), alpha.data_ptr(),
+                                out.data_ptr(), out.stride(0), _p(bias), _p(gate), M, N, K2 * 2, epilogue, block_n, max_ctas, _stream())
+    _check(rc, "b200_gemm_nvfp4")
     return out
 
 

@@ -332,11 +332,44 @@ def gen_hunyuan_vae_fixture():
           "tile_raw absmax", float(one.abs().max()))
 
 
+def gen_nvfp4_fixture():
+    """The reference's own NVFP4 golden model (lightx2v_kernel/test/nvfp4_nvfp4/fake_quant.py, imported unmodified) on a seeded
+    [200, 256] activation and [96, 256] weight: e2m1 grid values, e4m3 scale values, and the dequantised-matmul result the reference's
+    GEMM test compares against (test_bench1.py:75-103); pins oracle/nvfp4_oracle.py."""
+    from safetensors.torch import save_file
+
+    sys.path.insert(0, os.path.join(REF, "lightx2v_kernel", "test", "nvfp4_nvfp4"))
+    import fake_quant as FQ
+
+    g = torch.Generator().manual_seed(21)
+    a = (torch.randn(200, 256, generator=g) * 1.7).to(torch.bfloat16)
+    b = (torch.randn(96, 256, generator=g) * 0.05).to(torch.bfloat16)
+    a[5, 32:48] = 0                                                     # an all-zero group: scale 0, reciprocal guarded
+    a[7, 0] = 40.0                                                      # an outlier: other groups get small scales
+    bias = torch.randn(96, generator=g).to(torch.bfloat16)
+    gs_a = (448.0 * 6.0 / a.float().abs().max()).to(torch.float32)
+    gs_b = (448.0 * 6.0 / b.float().abs().max()).to(torch.float32)
+    qa, sa = FQ.ref_nvfp4_quant(a.clone(), gs_a)
+    qb, sb = FQ.ref_nvfp4_quant(b.clone(), gs_b)
+    da = (qa.reshape(200, 16, 16) * (sa / gs_a).unsqueeze(-1)).reshape(200, 256)
+    db = (qb.reshape(96, 16, 16) * (sb / gs_b).unsqueeze(-1)).reshape(96, 256)
+    out = da @ db.t() + bias.float()
+    save_file({"a": a, "b": b, "bias": bias, "gs_a": gs_a.reshape(1), "gs_b": gs_b.reshape(1), "qa": qa.contiguous(), "sa": sa.contiguous(),
+               "qb": qb.contiguous(), "sb": sb.contiguous(), "out": out.contiguous()}, os.path.join(GOLD, "nvfp4_quant_small.safetensors"),
+              metadata={"generator": "oracle/gen_golden.py:gen_nvfp4_fixture", "reference": "ModelTC/lightx2v@0591c35e"})
+    print("nvfp4_quant_small", float(out.abs().max()), "zero-scale groups", int((sa == 0).sum()))
+
+
 if __name__ == "__main__":
+    if os.environ.get("GOLDEN_ONLY", "") == "nvfp4":
+        os.makedirs(GOLD, exist_ok=True)
+        gen_nvfp4_fixture()
+        sys.exit(0)
     if os.environ.get("GOLDEN_ONLY", "") == "hunyuan_vae":
         install_shims()
         os.makedirs(GOLD, exist_ok=True)
         gen_hunyuan_vae_fixture()
+        gen_nvfp4_fixture()
         sys.exit(0)
     if os.environ.get("GOLDEN_ONLY", "") == "hunyuan":
         install_shims()
@@ -356,3 +389,4 @@ if __name__ == "__main__":
         gen_vae_fixture()
         gen_hunyuan_fixture()
         gen_hunyuan_vae_fixture()
+        gen_nvfp4_fixture()

@@ -66,9 +66,42 @@ def mm_fp8_apply(x: torch.Tensor, wq: torch.Tensor, wscale: torch.Tensor, bias: 
 def mm_named(W: Dict[str, torch.Tensor], name: str, x: torch.Tensor) -> torch.Tensor:
     """Linear `name` of a checkpoint-named dict: bf16 MMWeight, or the w8a8-fp8 class when `<name>.weight_scale` is present
     (the reference picks the class from mm_config.mm_type, transformer_weights.py:20-23; the quantised checkpoint carries the scales)."""
+    if name + ".weight_global_scale" in W:
+        return mm_nvfp4_apply(x, W[name + ".weight"], W.get(name + ".bias"))
     if name + ".weight_scale" in W:
         return mm_fp8_apply(x, W[name + ".weight"], W[name + ".weight_scale"], W.get(name + ".bias"))
     return mm_apply(x, W[name + ".weight"], W.get(name + ".bias"))
+
+
+def nvfp4_fake_quant(x: torch.Tensor) -> torch.Tensor:
+    """x -> dequantise(quantise(x)) in fp32 with the dynamic per-tensor global scale 448*6/max|x| - the reference's NVFP4 golden
+    model (lightx2v_kernel/test/nvfp4_nvfp4/fake_quant.py:34-51 + test_bench1.py:57-72), see oracle/nvfp4_oracle.py."""
+    from . import nvfp4_oracle as NV
+
+    gs = (NV.E4M3_MAX * NV.E2M1_MAX / x.float().abs().max()).to(torch.float32)
+    vals, scale = NV.quant(x, gs)
+    m, k = x.shape
+    return (vals.reshape(m, k // 16, 16) * (scale / gs).unsqueeze(-1)).reshape(m, k)
+
+
+def mm_nvfp4_apply(x: torch.Tensor, w_dq: torch.Tensor, bias) -> torch.Tensor:
+    """w4a4 linear as the reference's GEMM test defines it (test_bench1.py:75-103,134): dequantised operands, fp32 matmul, + bias, -> bf16.
+    `w_dq` is the already fake-quantised fp32 weight (quantize_checkpoint_nvfp4)."""
+    y = nvfp4_fake_quant(x) @ w_dq.t()
+    if bias is not None:
+        y = y + bias.float()
+    return y.to(torch.bfloat16)
+
+
+def quantize_checkpoint_nvfp4(W: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
+    """Oracle-side w4a4 conversion of the block linears: `<name>.weight` -> fake-quantised fp32 values + a `<name>.weight_global_scale`
+    marker (the product-side converter, lightx2v_b200.host.ops.quantize_checkpoint_nvfp4, emits the packed format instead)."""
+    out = dict(W)
+    for k, v in W.items():
+        if k.endswith(".weight") and v.dim() == 2 and ("attn." in k or "ffn." in k) and "norm" not in k:
+            out[k] = nvfp4_fake_quant(v)
+            out[k[: -len(".weight")] + ".weight_global_scale"] = (448.0 * 6.0 / v.float().abs().max()).reshape(1)
+    return out
 
 
 def quantize_checkpoint_fp8(W: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:

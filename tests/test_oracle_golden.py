@@ -107,3 +107,25 @@ def test_hunyuan_vae_oracle_matches_reference_fixture(golden_dir):
     # frame-causal mask of the mid-block attention: token of frame i sees frames <= i only
     m = HV.causal_frame_mask(3, 2, torch.float32, "cpu")
     assert m.shape == (6, 6) and m[0, 2] == float("-inf") and m[2, 1] == 0 and m[5, 0] == 0 and m[3, 4] == float("-inf")
+
+
+def test_nvfp4_oracle_matches_reference_fixture(golden_dir):
+    """oracle/nvfp4_oracle.py vs the reference's own fake_quant.py golden model, bit for bit; layout helpers round-trip."""
+    from oracle import nvfp4_oracle as NV
+
+    T, _ = _load(os.path.join(golden_dir, "nvfp4_quant_small.safetensors"))
+    gs_a, gs_b = T["gs_a"][0], T["gs_b"][0]
+    qa, sa = NV.quant(T["a"], gs_a)
+    qb, sb = NV.quant(T["b"], gs_b)
+    assert torch.equal(qa, T["qa"]) and torch.equal(sa, T["sa"]) and torch.equal(qb, T["qb"]) and torch.equal(sb, T["sb"])
+    assert int((sa == 0).sum()) == 1                                            # the all-zero group
+    pa, sfa = NV.scaled_fp4_quant(T["a"], gs_a)
+    pb, sfb = NV.scaled_fp4_quant(T["b"], gs_b)
+    assert pa.shape == (200, 128) and sfa.shape == (256, 16) and sfb.shape == (128, 16)
+    assert torch.equal(NV.unpack_e2m1(pa), qa) and torch.equal(NV.unswizzle_sf(sfa, 200, 256).view(torch.float8_e4m3fn).float(), sa)
+    # scale-factor layout: byte offset formula of nvfp4_quant_kernels_sm120.cu:127-152
+    m, g = 137, 9
+    off = ((m // 128) * (256 // 64) + g // 4) * 512 + (m % 32) * 16 + ((m % 128) // 32) * 4 + g % 4
+    assert sfa.reshape(-1)[off] == sa.to(torch.float8_e4m3fn).view(torch.uint8)[m, g]
+    out = NV.scaled_fp4_mm(pa, pb, sfa, sfb, gs_a, gs_b, T["bias"])
+    assert torch.allclose(out, T["out"], rtol=1e-5, atol=1e-4)

@@ -17,6 +17,21 @@ def child(kind):
             ref = torch.nn.functional.scaled_dot_product_attention(q[:2048].float().transpose(0, 1), k[:4096].float().transpose(0, 1), v[:4096].float().transpose(0, 1)).transpose(0, 1)
             got = lib.fmha(q[:2048], k[:4096], v[:4096])
             print(json.dumps({"case": "fmha_err", "env": os.environ.get("B200_FMHA_POLY"), "max_abs_err": float((got.float() - ref).abs().max())}))
+    elif kind == "gemm4":
+        for (M, N, K) in ((75600, 5120, 5120), (75600, 13824, 5120), (75600, 5120, 13824), (75600, 15360, 5120)):
+            a = torch.randn(M, K, device="cuda").bfloat16(); w = (torch.randn(N, K, device="cuda") * 0.05).bfloat16(); b = torch.randn(N, device="cuda").bfloat16()
+            o = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+            gw, _ = lib.nvfp4_act_scale(w)
+            wq, sw = lib.quant_nvfp4(w, gw)
+            ga, alpha = lib.nvfp4_act_scale(a, gw)
+            aq, sa = lib.quant_nvfp4(a, ga)
+            for bn in (128, 256):
+                ms = _time_cuda(lambda: lib.gemm_nvfp4(aq, wq, sa, sw, alpha, b, out=o, block_n=bn))
+                print(json.dumps({"case": f"gemm_nvfp4_{M}x{N}x{K}_bn{bn}", "ms": ms, "tflops": 2 * M * N * K / ms / 1e9}))
+            ms = _time_cuda(lambda: lib.quant_nvfp4(a, ga))
+            print(json.dumps({"case": f"quant_nvfp4_{M}x{K}", "ms": ms, "gbs": M * K * (2 + 0.5 + 1 / 16) / ms / 1e6}))
+            ms = _time_cuda(lambda: lib.nvfp4_act_scale(a, gw))
+            print(json.dumps({"case": f"nvfp4_act_scale_{M}x{K}", "ms": ms, "gbs": M * K * 2 / ms / 1e6}))
     elif kind == "gemm8":
         for (M, N, K) in ((75600, 5120, 5120), (75600, 13824, 5120), (75600, 5120, 13824), (75600, 15360, 5120)):
             a = torch.randn(M, K, device="cuda").bfloat16(); w = (torch.randn(N, K, device="cuda") * 0.05).bfloat16(); b = torch.randn(N, device="cuda").bfloat16()
@@ -39,7 +54,7 @@ if __name__ == "__main__":
         child(sys.argv[1])
     else:
         kind = sys.argv[1]
-        var, vals = {"fmha": ("B200_FMHA_POLY", ["0", "1", "2"]), "fmha3": ("B200_FMHA_POLY", ["0", "1", "2"]), "fmha4": ("B200_FMHA_POLY", ["1"]), "fmha5": ("B200_FMHA_POLY", ["0", "1", "2"]), "fmha6": ("B200_FMHA_POLY", ["0", "1", "2"]), "fmha7": ("B200_FMHA_POLY", ["0", "1"]), "gemm": ("B200_GEMM_GROUP_M", ["16"]), "gemm8": ("B200_X", ["0"])}[kind]
+        var, vals = {"fmha": ("B200_FMHA_POLY", ["0", "1", "2"]), "fmha3": ("B200_FMHA_POLY", ["0", "1", "2"]), "fmha4": ("B200_FMHA_POLY", ["1"]), "fmha5": ("B200_FMHA_POLY", ["0", "1", "2"]), "fmha6": ("B200_FMHA_POLY", ["0", "1", "2"]), "fmha7": ("B200_FMHA_POLY", ["0", "1"]), "gemm": ("B200_GEMM_GROUP_M", ["16"]), "gemm8": ("B200_X", ["0"]), "gemm4": ("B200_X", ["0"])}[kind]
         for v in vals:
             env = dict(os.environ); env[var] = v
             if kind == "fmha": env["B200_FMHA_VER"] = "2"
