@@ -128,9 +128,15 @@ class HunyuanTransformerInfer:
         w = mm.weight.t()
         return w if w.is_contiguous() else w.contiguous()
 
-    def _attention(self, qkv3, bounds, out, o_cols):
-        """qkv3: [L, 3, H, 128] view; out: [L, *] buffer whose columns o_cols hold the attention output [L, H*128]."""
+    def _attention(self, qkv3, bounds, out, o_cols, txt_len=None):
+        """qkv3: [L, 3, H, 128] view; out: [L, *] buffer whose columns o_cols hold the attention output [L, H*128].
+        With `parallel_attention` set (Ulysses, host/ulysses.py:HunyuanUlyssesAttention) the image rows are this rank's shard,
+        the text rows are replicated and `bounds` are the GLOBAL cu_seqlens [0, img_total + txt_valid, img_total + txt_len]."""
         H = self.heads_num
+        if self.parallel_attention is not None:
+            L = qkv3.shape[0]
+            self.parallel_attention(qkv3, L - txt_len, bounds, out[:, o_cols[0]:o_cols[1]].unflatten(1, (H, 128)))
+            return
         for a, b in zip(bounds[:-1], bounds[1:]):
             if b > a:
                 o = out[a:b, o_cols[0]:o_cols[1]].unflatten(1, (H, 128))
@@ -157,7 +163,7 @@ class HunyuanTransformerInfer:
         lib.rms_rope_heads_(q3[Li:, 0], weights.txt_attn_q_norm.weight, q3[Li:, 1], weights.txt_attn_k_norm.weight,
                             eps=weights.txt_attn_q_norm.eps)
         attn = self._buf("attn", (L, D), dev)
-        self._attention(q3, self._bounds(cu_seqlens_qkv), attn, (0, D))
+        self._attention(q3, self._bounds(cu_seqlens_qkv), attn, (0, D), txt_len=Lt)
         # x = x + proj(attn) * gate1  -> GEMM epilogue, in place on the stream tensors (the reference makes new tensors, same values)
         lib.gemm_bf16(attn[:Li], self._nk(weights.img_attn_proj), weights.img_attn_proj.bias, out=img, epilogue=lib.EPI_GATE_RESIDUAL, gate=im[2])
         lib.gemm_bf16(attn[Li:], self._nk(weights.txt_attn_proj), weights.txt_attn_proj.bias, out=txt, epilogue=lib.EPI_GATE_RESIDUAL, gate=tm[2])
@@ -182,7 +188,7 @@ class HunyuanTransformerInfer:
         Li = L - txt_seq_len
         cs = self._cs(freqs_cis)
         lib.rms_rope_heads_(q3[:, 0], weights.q_norm.weight, q3[:, 1], weights.k_norm.weight, eps=weights.q_norm.eps, cos_sin=cs, rope_rows=Li)
-        self._attention(q3, self._bounds(cu_seqlens_qkv), buf, (3 * D, 4 * D))
+        self._attention(q3, self._bounds(cu_seqlens_qkv), buf, (3 * D, 4 * D), txt_len=txt_seq_len)
         # x = x + linear2([attn | gelu(mlp)]) * gate
         lib.gemm_bf16(buf[:, 3 * D:], self._nk(weights.linear2), weights.linear2.bias, out=x, epilogue=lib.EPI_GATE_RESIDUAL, gate=mod[2])
         return x

@@ -201,6 +201,28 @@ class HunyuanVAEB200:
         self.tile_tsample = c["sample_tsize"]
         self.tile_tlatent = c["sample_tsize"] // 4
         self.overlap = c["tile_overlap_factor"]
+        self._dist = None
+        self._tile_counter = 0
+
+    # ------------------------------------------------------------------ tile scheduling (single GPU: every tile is local)
+    def _decode_tile(self, z: torch.Tensor) -> torch.Tensor:
+        """Decode one tile here, or - in a tile-parallel decode (decode_dist) - on the rank that owns it, then broadcast the result.
+        Tiles are independent units of work (the reference decodes them one after another), so sharding them needs no collective on
+        the compute path; the only exchange is the hand-over of finished tiles for the blends."""
+        if self._dist is None:
+            return self.decoder.decode_tile(z)
+        import torch.distributed as dist
+
+        world, rank, group = self._dist
+        owner = self._tile_counter % world
+        self._tile_counter += 1
+        _, t, h, w = z.shape
+        if owner == rank:
+            out = self.decoder.decode_tile(z)
+        else:
+            out = torch.empty((3, 1 + 4 * (t - 1), 8 * h, 8 * w), dtype=torch.float32, device=self.device)
+        dist.broadcast(out, src=dist.get_global_rank(group, owner) if group is not None else owner, group=group)
+        return out
 
     def _spatial_tiled(self, z: torch.Tensor) -> torch.Tensor:
         step = int(self.tile_latent * (1 - self.overlap))
@@ -208,7 +230,7 @@ class HunyuanVAEB200:
         limit = self.tile_sample - extent
         rows = []
         for i in range(0, z.shape[-2], step):
-            rows.append([self.decoder.decode_tile(z[:, :, i:i + self.tile_latent, j:j + self.tile_latent]) for j in range(0, z.shape[-1], step)])
+            rows.append([self._decode_tile(z[:, :, i:i + self.tile_latent, j:j + self.tile_latent]) for j in range(0, z.shape[-1], step)])
         out_rows = []
         for i, row in enumerate(rows):
             out = []
@@ -231,7 +253,7 @@ class HunyuanVAEB200:
             if tile.shape[-1] > self.tile_latent or tile.shape[-2] > self.tile_latent:
                 dec = self._spatial_tiled(tile)
             else:
-                dec = self.decoder.decode_tile(tile)
+                dec = self._decode_tile(tile)
             if i > 0:
                 dec = dec[:, 1:]
             row.append(dec)
@@ -253,8 +275,24 @@ class HunyuanVAEB200:
         elif z.shape[-1] > self.tile_latent or z.shape[-2] > self.tile_latent:
             img = self._spatial_tiled(z)
         else:
-            img = self.decoder.decode_tile(z)
+            img = self._decode_tile(z)
         return img.mul_(0.5).add_(0.5).clamp_(0, 1).unsqueeze(0)
+
+    @torch.no_grad()
+    def decode_dist(self, latents: torch.Tensor, group=None, to_cpu: bool = True) -> torch.Tensor:
+        """Tile-parallel decode over the ranks of `group`: tile k of the reference's (temporal, row, column) tile order is decoded by
+        rank k mod P and broadcast; every rank then performs the same blends and returns the same video (bit-identical to `decode`,
+        since each tile is computed by the same kernels on the same inputs).  The reference has no parallel Hunyuan VAE (its Wan VAE has
+        `parallel_vae`, hf/wan/vae.py:883-929); with 84 independent tiles at 720p x 129f this is the natural B200 sharding."""
+        import torch.distributed as dist
+
+        self._dist = (dist.get_world_size(group), dist.get_rank(group), group)
+        self._tile_counter = 0
+        try:
+            img = self.decode_device(latents)
+        finally:
+            self._dist = None
+        return img.cpu().float() if to_cpu else img
 
     @torch.no_grad()
     def decode(self, latents: torch.Tensor, generator=None, config=None) -> torch.Tensor:

@@ -170,3 +170,59 @@ def parallelize_wan(model, total_rows: int, attention_fn: Callable, group=None):
     model.pre_process = lambda x: pre_process(x, rank, world)
     model.post_process = lambda x: post_process(x, total_rows, group)
     return model
+
+
+class HunyuanUlyssesAttention:
+    """parallel_attention hook for HunyuanTransformerInfer (reference: ulysses_attn with img_qkv_len / cu_seqlens_qkv,
+    lightx2v/attentions/distributed/ulysses/attn.py:7-91; installed by parallelize_hunyuan, ulysses/wrap.py:5-50).
+
+    Image tokens are sharded along the token axis (s rows per rank), text tokens are replicated.  One packed all-to-all gives every
+    rank ALL image tokens for its H/P heads (:44-48); text q/k/v are sliced to the same heads locally (:51-53); attention runs over
+    [image ; text] with the two varlen segments [0, img + txt_valid) and [img + txt_valid, img + txt_len) (:60-70); image outputs go
+    back through the inverse all-to-all (:84-86), text outputs are all-gathered along heads (:80-81, 89)."""
+
+    def __init__(self, attention_fn: Callable, group=None):
+        self.attn = attention_fn
+        self.group = group
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        self._bufs = {}
+
+    _buf = UlyssesAttention._buf
+
+    def __call__(self, qkv3: torch.Tensor, img_len: int, bounds, out: torch.Tensor) -> torch.Tensor:
+        """qkv3 [s + Lt, 3, H, d] (any row stride); bounds = global cu_seqlens; out [s + Lt, H, d] view."""
+        P, r = self.world, self.rank
+        L, _, H, d = qkv3.shape
+        s, Lt = img_len, L - img_len
+        if H % P != 0:
+            raise ValueError(f"Ulysses needs num_heads ({H}) divisible by world size ({P})")
+        hp = H // P
+        img_total = P * s
+        if bounds[-1] != img_total + Lt:
+            raise ValueError(f"cu_seqlens {bounds} do not describe {img_total} image + {Lt} text tokens")
+        send = self._buf("h_send", (P, s, 3, hp, d), qkv3)
+        send.copy_(qkv3[:s].reshape(s, 3, P, hp, d).permute(2, 0, 1, 3, 4))
+        full = self._buf("h_full", (img_total + Lt, 3, hp, d), qkv3)               # [all image tokens ; text], this rank's heads
+        dist.all_to_all_single(full[:img_total].view(P, s, 3, hp, d), send, group=self.group)
+        full[img_total:].copy_(qkv3[s:, :, r * hp:(r + 1) * hp])
+        oall = self._buf("h_oall", (img_total + Lt, hp, d), qkv3)
+        for a, b in zip(bounds[:-1], bounds[1:]):
+            if b > a:
+                self.attn(full[a:b, 0], full[a:b, 1], full[a:b, 2], out=oall[a:b])
+        orecv = self._buf("h_orecv", (P, s, hp, d), qkv3)
+        dist.all_to_all_single(orecv, oall[:img_total].view(P, s, hp, d), group=self.group)
+        out[:s].copy_(orecv.permute(1, 0, 2, 3).reshape(s, H, d))
+        tg = self._buf("h_txt", (P * Lt, hp, d), qkv3)
+        dist.all_gather_into_tensor(tg, oall[img_total:].contiguous(), group=self.group)
+        out[s:].copy_(tg.view(P, Lt, hp, d).permute(1, 0, 2, 3).reshape(Lt, H, d))
+        return out
+
+
+def parallelize_hunyuan(transformer_infer, attention_fn: Callable, group=None):
+    """Install the Ulysses hook on a HunyuanTransformerInfer (wrap.py:5-50).  The caller shards the image tokens and the RoPE rows
+    (contiguous chunks of the token axis; the reference splits the latent along H or W before patchify, utils/hunyuan/processor.py:5-50,
+    which is the same thing up to the token order inside the shard) and all-gathers the image output."""
+    transformer_infer.parallel_attention = HunyuanUlyssesAttention(attention_fn, group)
+    return transformer_infer
+

@@ -89,3 +89,44 @@ def test_heads_must_divide_world():
 
     with pytest.raises(ValueError):
         FakeAtt()(q=torch.zeros(4, 4, 128), k=torch.zeros(4, 4, 128), v=torch.zeros(4, 4, 128))
+
+
+def _hunyuan_worker(rank, world, port, Li, Lt, valid, H, results):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from lightx2v_b200.host import ulysses as U
+
+        torch.manual_seed(1)
+        d = 128
+        img = torch.randn(Li, 3, H, d).to(torch.bfloat16)           # post-norm/rope q, k, v of all image tokens
+        txt = torch.randn(Lt, 3, H, d).to(torch.bfloat16)           # text tokens: replicated on every rank
+        s = Li // world
+        local = torch.cat((img[rank * s:(rank + 1) * s], txt), 0)
+        bounds = [0, Li + valid, Li + Lt]
+        att = U.HunyuanUlyssesAttention(_oracle_attn)
+        out = torch.empty(s + Lt, H, d, dtype=torch.bfloat16)
+        att(local, s, bounds, out)
+        # reference: joint attention over [all image ; text] with the two varlen segments (hunyuan_oracle.varlen_attention)
+        full = torch.cat((img, txt), 0)
+        ref = torch.empty(Li + Lt, H, d, dtype=torch.bfloat16)
+        for a, b in zip(bounds[:-1], bounds[1:]):
+            ref[a:b] = _oracle_attn(full[a:b, 0], full[a:b, 1], full[a:b, 2])
+        ok_img = torch.equal(out[:s], ref[rank * s:(rank + 1) * s])
+        ok_txt = torch.equal(out[s:], ref[Li:])
+        results[rank] = (ok_img and ok_txt, float((out[:s].float() - ref[rank * s:(rank + 1) * s].float()).abs().max()))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_hunyuan_ulysses_matches_joint_attention_world2():
+    """Image tokens sharded, text replicated, heads scattered: equals the joint [image ; text] attention with the padded-text segment."""
+    world = 2
+    port = _free_port()
+    with mp.Manager() as m:
+        results = m.dict()
+        mp.spawn(_hunyuan_worker, args=(world, port, 48, 8, 5, 4, results), nprocs=world, join=True)
+        for r in range(world):
+            ok, err = results[r]
+            assert ok, (r, err)
