@@ -193,7 +193,9 @@ def run_ours(args):
     if world > 1:
         # after wrapping, so the sharded launches are counted and timed too
         sp_mode = args.sp
-        if sp_mode == "fused":
+        if args.parallel == "cfg" and cfg["enable_cfg"] and world % 2 == 0:
+            sp_mode = ulysses.parallelize_wan_cfg(model, S, lib.fmha, sp=args.sp)
+        elif sp_mode == "fused":
             try:
                 ulysses.parallelize_wan_fused(model, S)
             except Exception as ex:  # symmetric memory unavailable on this box: keep the run alive on the NCCL exchange and say so
@@ -292,7 +294,7 @@ def run_ours(args):
             "vs_baseline": None, "dtype": "fp8-e4m3 linears, bf16 attention" if cfg.get("fp8") else ("nvfp4 (e2m1 + ue4m3/16) linears, bf16 attention" if cfg.get("nvfp4") else "bf16"),
             "data": "synthetic latents/prompt embeddings, random-init weights of the named shapes",
             "config": {"workload": args.workload, "tokens": S, "forwards_per_step": 2 if cfg["enable_cfg"] else 1, "blocks": cfg["num_layers"],
-                       "parallelism": f"ulysses{world}" if world > 1 else "single", "sp_exchange": sp_mode, "l2": "activations (774 MB/tensor) and weights (28 GB) exceed the 126 MB L2",
+                       "parallelism": (sp_mode if sp_mode.startswith("cfg2") else f"ulysses{world}") if world > 1 else "single", "sp_exchange": sp_mode, "l2": "activations (774 MB/tensor) and weights (28 GB) exceed the 126 MB L2",
                        "scheduler": "step-distill 4-step (x0 re-noising)" if cfg.get("distill") else "UniPC order 2 (flow), 50-step sigma grid"},
             "achieved_tflops": round(flops_step / (ms_resident * 1e-3) / 1e12, 1),
             "model_tflop_per_step": round(flops_step / 1e12, 1),
@@ -579,6 +581,8 @@ def main():
     ap.add_argument("--no-gpu-reference", dest="gpu_reference", action="store_false")
     ap.add_argument("--no-vae", dest="vae", action="store_false")
     ap.add_argument("--sp", default="fused", choices=["fused", "nccl"], help="Ulysses exchange: peer-memory kernels (default) or NCCL all-to-all")
+    ap.add_argument("--parallel", default="ulysses", choices=["ulysses", "cfg"],
+                    help="N > 1: Ulysses over all ranks, or CFG-parallel (cond / uncond on rank halves) x Ulysses inside each half")
     ap.add_argument("--cpu-budget", type=float, default=20.0)
     args = ap.parse_args()
     if args.workload == "hunyuan-13b-720p-129f-blocks":

@@ -160,7 +160,11 @@ int b200_conv3d_cl_padded(const void* in, int64_t in_st, int64_t in_sh, int64_t 
                           int64_t res_st, int64_t res_sh, int64_t res_sw, int T, int H, int W, int cin, int cout, int ntaps,
                           const int32_t* taps, int clamp_out, b200_stream_t stream);
 
-/* sums[0:32] = per-group sum, sums[32:64] = per-group sum of squares (fp64, device; zeroed by the call) of a channels-last bf16
+/* Size (in doubles) of the device workspace b200_gn_stats_cl needs: 64 result entries + room for the per-block partial sums. */
+int64_t b200_gn_stats_workspace_doubles(void);
+
+/* sums[0:32] = per-group sum, sums[32:64] = per-group sum of squares (fp64, device; `sums` is a workspace of
+ * b200_gn_stats_workspace_doubles() entries, deterministic fixed-order reduction, no atomics) of a channels-last bf16
  * tensor [voxels, C], 32 groups of C/32 consecutive channels, C in {64,128,256,512}.  First half of torch.nn.GroupNorm as used by
  * ResnetBlockCausal3D.norm1/norm2, Attention.group_norm and DecoderCausal3D.conv_norm_out (unet_causal_3d_blocks.py:313,332;
  * vae.py:209). */

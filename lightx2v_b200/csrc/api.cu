@@ -35,6 +35,7 @@ int quant_nvfp4(const void* x, long long ldx, long long rows, int K, const float
 int nvfp4_act_scale(const void* x, long long ldx, long long rows, int K, const float* weight_global_scale, float* global_scale,
                     float* alpha, void* scratch, cudaStream_t stream);
 int gn_stats_cl(const void* x, long long voxels, int C, double* sums, cudaStream_t stream);
+long long gn_stats_workspace_doubles();
 int gn_apply_pad_cl(const void* x, void* y, const double* sums, const float* gamma, const float* beta, float eps, int T, int H, int W,
                     int C, int pt, int ph, int pw, int apply_silu, cudaStream_t stream);
 int rms_silu_cl(const void* x, void* y, const float* gamma, long long voxels, int C, int apply_silu, cudaStream_t stream);
@@ -134,6 +135,8 @@ int b200_nvfp4_act_scale(const void* x, int64_t ldx, int64_t rows, int K, const 
                          float* alpha, void* scratch, b200_stream_t stream) {
   return b200::nvfp4_act_scale(x, ldx, rows, K, weight_global_scale, global_scale, alpha, scratch, reinterpret_cast<cudaStream_t>(stream));
 }
+
+int64_t b200_gn_stats_workspace_doubles(void) { return b200::gn_stats_workspace_doubles(); }
 
 int b200_gn_stats_cl(const void* x, int64_t voxels, int C, double* sums, b200_stream_t stream) {
   return b200::gn_stats_cl(x, voxels, C, sums, reinterpret_cast<cudaStream_t>(stream));

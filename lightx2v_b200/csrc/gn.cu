@@ -2,7 +2,7 @@
 //
 // Replaces, per ResnetBlockCausal3D half (lightx2v/models/video_encoders/hf/autoencoder_kl_causal_3d/unet_causal_3d_blocks.py
 // :364-412): torch.nn.GroupNorm -> SiLU -> F.pad(mode="replicate") of CausalConv3d.forward (:88-91).  Two HBM-bound passes:
-//   gn_stats     : one read of the tensor -> per-group sum / sum of squares (fp32 per thread, fp64 across threads)
+//   gn_stats     : one read of the tensor -> per-group sum / sum of squares (fp32 inside a block, fp64 across blocks, fixed order)
 //   gn_apply_pad : one read + one write: y = silu((x - mean) * rstd * gamma + beta) written into a tensor that already carries
 //                  the convolution's replicate border (pt frames in front, ph / pw pixels around), so that the implicit-GEMM
 //                  convolution (conv3d.cu) reads it with plain non-negative tap offsets and no padding logic of its own.
@@ -14,21 +14,22 @@ namespace b200 {
 
 constexpr int GN_GROUPS = 32;
 
+// Deterministic two-level reduction (no atomics: the decode must be reproducible run to run and across tile-parallel ranks):
+// thread -> warp shuffles -> fixed-order sum over the 8 warps -> one partial per block; a second tiny kernel sums the block
+// partials in block order in fp64.
 template <int C>
 __global__ void __launch_bounds__(256)
-gn_stats_kernel(const __nv_bfloat16* __restrict__ x, long long voxels, double* __restrict__ sums) {
+gn_stats_kernel(const __nv_bfloat16* __restrict__ x, long long voxels, float* __restrict__ partials) {
   constexpr int LPV = C / 8;                    // threads per voxel (each owns 8 consecutive channels)
   constexpr int VPB = 256 / LPV;                // voxels per block pass
   constexpr int CPG = C / GN_GROUPS;            // channels per group
   constexpr int GPT = (CPG >= 8) ? 1 : 8 / CPG; // groups touched by one thread
   constexpr int EPG = 8 / GPT;                  // of its 8 elements, how many fall in one group
-  __shared__ float s_sum[GN_GROUPS], s_sq[GN_GROUPS];
-  if (threadIdx.x < GN_GROUPS) {
-    s_sum[threadIdx.x] = 0.f;
-    s_sq[threadIdx.x] = 0.f;
-  }
+  __shared__ float part[2][8][GN_GROUPS];
+  for (int i = threadIdx.x; i < 2 * 8 * GN_GROUPS; i += 256) (&part[0][0][0])[i] = 0.f;
   __syncthreads();
   const int l = threadIdx.x % LPV, sub = threadIdx.x / LPV;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   float s[GPT], q[GPT];
 #pragma unroll
   for (int g = 0; g < GPT; ++g) s[g] = q[g] = 0.f;
@@ -41,47 +42,64 @@ gn_stats_kernel(const __nv_bfloat16* __restrict__ x, long long voxels, double* _
       q[e / EPG] += f[e] * f[e];
     }
   }
-  // lanes of a warp that own the same channel slice (LPV < 32) are folded by shuffles before touching shared memory
 #pragma unroll
   for (int g = 0; g < GPT; ++g) {
+    // lanes of a warp that own the same channel slice (LPV < 32)
 #pragma unroll
     for (int o = 16; o >= LPV; o >>= 1) {
       s[g] += __shfl_xor_sync(0xffffffffu, s[g], o);
       q[g] += __shfl_xor_sync(0xffffffffu, q[g], o);
     }
+    if constexpr (CPG == 16) {   // two neighbouring threads share a group
+      s[g] += __shfl_xor_sync(0xffffffffu, s[g], 1);
+      q[g] += __shfl_xor_sync(0xffffffffu, q[g], 1);
+    }
   }
-  if (LPV >= 32 || (threadIdx.x & 31) < LPV) {
+  if (CPG == 16 ? (lane & 1) == 0 : lane < LPV) {
 #pragma unroll
     for (int g = 0; g < GPT; ++g) {
       const int grp = (l * 8) / CPG + g;
-      atomicAdd(&s_sum[grp], s[g]);
-      atomicAdd(&s_sq[grp], q[g]);
+      part[0][warp][grp] = s[g];
+      part[1][warp][grp] = q[g];
     }
   }
   __syncthreads();
-  if (threadIdx.x < GN_GROUPS) {
-    atomicAdd(&sums[threadIdx.x], (double)s_sum[threadIdx.x]);
-    atomicAdd(&sums[GN_GROUPS + threadIdx.x], (double)s_sq[threadIdx.x]);
+  if (threadIdx.x < 2 * GN_GROUPS) {
+    const int which = threadIdx.x / GN_GROUPS, grp = threadIdx.x % GN_GROUPS;
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += part[which][w][grp];
+    partials[(long long)blockIdx.x * 2 * GN_GROUPS + threadIdx.x] = t;
   }
 }
 
+__global__ void gn_stats_finalize_kernel(const float* __restrict__ partials, int blocks, double* __restrict__ sums) {
+  double t = 0.0;
+  for (int b = 0; b < blocks; ++b) t += (double)partials[(long long)b * 2 * GN_GROUPS + threadIdx.x];
+  sums[threadIdx.x] = t;
+}
+
+// sums: fp64 workspace of gn_stats_workspace_doubles() entries; the first 64 hold the result (sum[32], sum of squares[32]).
+long long gn_stats_workspace_doubles() { return 2 * GN_GROUPS + (long long)num_sms() * 8 * GN_GROUPS; }   // 64 + float partials
+
 int gn_stats_cl(const void* x, long long voxels, int C, double* sums, cudaStream_t stream) {
   B200_CHECK_ARG(x && sums && voxels > 0, "b200_gn_stats_cl: bad arguments");
-  B200_CHECK_CUDA(cudaMemsetAsync(sums, 0, 2 * GN_GROUPS * sizeof(double), stream));
   const auto* xp = reinterpret_cast<const __nv_bfloat16*>(x);
   const int lpv = C / 8;
   const long long passes = (voxels + (256 / (lpv > 0 ? lpv : 1)) - 1) / (256 / (lpv > 0 ? lpv : 1));
   const int max_blocks = num_sms() * 8;
   const int blocks = (int)(passes < max_blocks ? passes : max_blocks);
+  float* partials = reinterpret_cast<float*>(sums + 2 * GN_GROUPS);
   switch (C) {
-    case 64: gn_stats_kernel<64><<<blocks, 256, 0, stream>>>(xp, voxels, sums); break;
-    case 128: gn_stats_kernel<128><<<blocks, 256, 0, stream>>>(xp, voxels, sums); break;
-    case 256: gn_stats_kernel<256><<<blocks, 256, 0, stream>>>(xp, voxels, sums); break;
-    case 512: gn_stats_kernel<512><<<blocks, 256, 0, stream>>>(xp, voxels, sums); break;
+    case 64: gn_stats_kernel<64><<<blocks, 256, 0, stream>>>(xp, voxels, partials); break;
+    case 128: gn_stats_kernel<128><<<blocks, 256, 0, stream>>>(xp, voxels, partials); break;
+    case 256: gn_stats_kernel<256><<<blocks, 256, 0, stream>>>(xp, voxels, partials); break;
+    case 512: gn_stats_kernel<512><<<blocks, 256, 0, stream>>>(xp, voxels, partials); break;
     default:
       set_last_error("b200_gn_stats_cl: unsupported channel count %d (64 / 128 / 256 / 512)", C);
       return B200_ERR_UNSUPPORTED;
   }
+  gn_stats_finalize_kernel<<<1, 2 * GN_GROUPS, 0, stream>>>(partials, blocks, sums);
   B200_CHECK_CUDA(cudaGetLastError());
   return B200_OK;
 }

@@ -132,7 +132,7 @@ class HunyuanVAEDecoderB200:
                 self.layers.append(("up", _UpsampleConv3d(W[p + ".weight"], W[p + ".bias"], dev, 2 if tm else 1)))
         self.norm_out = norm("decoder.conv_norm_out")
         self.conv_out = _conv333(W["decoder.conv_out.conv.weight"], W["decoder.conv_out.conv.bias"], dev, cout_pad=16)
-        self._sums = torch.empty(64, dtype=torch.float64, device=dev)
+        self._sums = torch.empty(int(lib.load().b200_gn_stats_workspace_doubles()), dtype=torch.float64, device=dev)
         self._zero = torch.zeros(self.zc, dtype=torch.float32, device=dev)
         self._scale = torch.full((self.zc,), float(self.cfg["scaling_factor"]), dtype=torch.float32, device=dev)
 

@@ -172,6 +172,34 @@ def parallelize_wan(model, total_rows: int, attention_fn: Callable, group=None):
     return model
 
 
+def parallelize_wan_cfg(model, total_rows: int, attention_fn: Optional[Callable] = None, sp: str = "fused", group=None):
+    """CFG-parallel x Ulysses: ranks [0, P/2) run the conditional pass, ranks [P/2, P) the unconditional one (SURVEY.md 8f N1;
+    the reference runs them back to back, wan/model.py:203-218); inside each half the token axis is Ulysses-sharded over P/2 ranks
+    (P = 2: no exchange at all inside the block stack).  Returns the description of what was installed."""
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    if world % 2 != 0:
+        raise ValueError(f"CFG-parallel needs an even world size, got {world}")
+    half = world // 2
+    base = dist.get_process_group_ranks(group) if group is not None else list(range(world))
+    groups = [dist.new_group([base[i] for i in range(b * half, (b + 1) * half)]) for b in (0, 1)]      # collective: every rank creates both
+    branch = rank // half
+    model.cfg_parallel = (branch == 0, 0, half, group)
+    mode = "cfg2"
+    if half > 1:
+        sub = groups[branch]
+        if sp == "fused":
+            try:
+                parallelize_wan_fused(model, total_rows, sub)
+                mode = f"cfg2 x ulysses{half} (peer memory)"
+            except Exception as ex:   # symmetric memory not available for sub-groups on this build: NCCL exchange instead
+                parallelize_wan(model, total_rows, attention_fn, sub)
+                mode = f"cfg2 x ulysses{half} (nccl; peer-memory setup failed: {str(ex)[:80]})"
+        else:
+            parallelize_wan(model, total_rows, attention_fn, sub)
+            mode = f"cfg2 x ulysses{half} (nccl)"
+    return mode
+
+
 class HunyuanUlyssesAttention:
     """parallel_attention hook for HunyuanTransformerInfer (reference: ulysses_attn with img_qkv_len / cu_seqlens_qkv,
     lightx2v/attentions/distributed/ulysses/attn.py:7-91; installed by parallelize_hunyuan, ulysses/wrap.py:5-50).

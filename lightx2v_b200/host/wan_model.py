@@ -126,6 +126,7 @@ class WanModel:
         self.scheduler = None
         self.pre_process = None      # sequence-parallel hooks (host/ulysses.py)
         self.post_process = None
+        self.cfg_parallel = None     # (branch_is_cond, cond_src_rank, uncond_src_rank, group) - host/ulysses.py:parallelize_wan_cfg
 
     def set_scheduler(self, scheduler):
         self.scheduler = scheduler
@@ -144,6 +145,19 @@ class WanModel:
     @torch.no_grad()
     def infer(self, inputs):
         """model.py:197-226: cond pass, then (enable_cfg) uncond pass and `uncond + g * (cond - uncond)` in fp32."""
+        if self.cfg_parallel is not None and self.config.get("enable_cfg", False):
+            # CFG-parallel (SURVEY.md 8f N1): the conditional and unconditional passes of model.py:203-218 are independent, so one half
+            # of the ranks runs each and the two 19 MB predictions are exchanged; same kernels on the same inputs -> same values.
+            import torch.distributed as dist
+
+            is_cond, cond_src, uncond_src, group = self.cfg_parallel
+            mine = self._forward(inputs, is_cond).contiguous()
+            world = dist.get_world_size(group)
+            both = torch.empty((world,) + tuple(mine.shape), dtype=mine.dtype, device=mine.device)
+            dist.all_gather_into_tensor(both, mine, group=group)
+            cond, uncond = both[cond_src], both[uncond_src]
+            self.scheduler.noise_pred = uncond + self.config["sample_guide_scale"] * (cond - uncond)
+            return
         cond = self._forward(inputs, True)
         self.scheduler.noise_pred = cond
         if self.config.get("enable_cfg", False):

@@ -38,6 +38,7 @@ SIGNATURES = {
     "b200_quant_nvfp4": (_i32, [_ptr, _i64, _i64, _i32, _ptr, _ptr, _i64, _ptr, _ptr]),
     "b200_nvfp4_act_scale": (_i32, [_ptr, _i64, _i64, _i32, _ptr, _ptr, _ptr, _ptr, _ptr]),
     "b200_gemm_nvfp4": (_i32, [_ptr, _i64, _ptr, _i64, _ptr, _ptr, _ptr, _ptr, _i64, _ptr, _ptr, _i64, _i64, _i64, _i32, _i32, _i32, _ptr]),
+    "b200_gn_stats_workspace_doubles": (_i64, []),
     "b200_gn_stats_cl": (_i32, [_ptr, _i64, _i32, _ptr, _ptr]),
     "b200_gn_apply_pad_cl": (_i32, [_ptr, _ptr, _ptr, _ptr, _ptr, _f32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _ptr]),
     "b200_rms_silu_cl": (_i32, [_ptr, _ptr, _ptr, _i64, _i32, _i32, _ptr]),
@@ -295,13 +296,17 @@ def conv3d_cl_padded(xp: torch.Tensor, wt: torch.Tensor, bias: Optional[torch.Te
 
 
 def gn_stats_cl(x: torch.Tensor, sums: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """Per-group (32 groups) sum / sum-of-squares of a contiguous channels-last tensor [..., C] -> fp64 [64]."""
+    """Per-group (32 groups) sum / sum-of-squares of a contiguous channels-last tensor [..., C] -> fp64 workspace whose first 64
+    entries are the result (the rest holds the per-block partials of the deterministic reduction)."""
     _req(x, "x")
     if not x.is_contiguous():
         raise B200Error("gn_stats_cl: x must be contiguous channels-last")
     C = x.shape[-1]
+    need = int(load().b200_gn_stats_workspace_doubles())
     if sums is None:
-        sums = torch.empty(64, dtype=torch.float64, device=x.device)
+        sums = torch.empty(need, dtype=torch.float64, device=x.device)
+    elif sums.numel() < need:
+        raise B200Error(f"gn_stats_cl: workspace too small ({sums.numel()} < {need} doubles)")
     rc = load().b200_gn_stats_cl(x.data_ptr(), x.numel() // C, C, sums.data_ptr(), _stream())
     _check(rc, "b200_gn_stats_cl")
     return sums

@@ -155,3 +155,55 @@ def test_hunyuan_vae_tile_parallel_decode_is_bit_identical(tmp_path):
     r = torch.load(out)
     print("hunyuan VAE tile-parallel vs single GPU:", r)
     assert r["equal"], r
+
+
+def _run_cfg_rank(rank, world, port, out_path):
+    import torch.distributed as dist
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        import bench as B
+        from lightx2v_b200 import lib
+        from lightx2v_b200.host import ulysses as U
+        from lightx2v_b200.host.wan_model import WanModel
+        from lightx2v_b200.host.wan_scheduler import WanScheduler
+
+        cfg = dict(dim=1536, num_heads=12, ffn_dim=8960, num_layers=2, target_shape=(16, 3, 16, 16), infer_steps=4, enable_cfg=True, sample_guide_scale=5.0,
+                   sample_shift=5.0, task="t2v", freq_dim=256, text_len=512, in_dim=16, out_dim=16, seed=42, mm_config={}, patch_size=(1, 2, 2))
+        dev = torch.device("cuda", rank)
+        W = B.synth_weights(cfg, dev)
+        g = torch.Generator(device=dev).manual_seed(7)
+        ctx = {"context": torch.randn(512, 4096, generator=g, device=dev).to(torch.bfloat16), "context_null": torch.randn(512, 4096, generator=g, device=dev).to(torch.bfloat16)}
+        inputs = {"text_encoder_output": ctx, "image_encoder_output": None}
+        outs = []
+        for parallel in (False, True):
+            model = WanModel(cfg, W)
+            sched = WanScheduler(cfg, device=dev)
+            sched.prepare()
+            model.set_scheduler(sched)
+            if parallel:
+                mode = U.parallelize_wan_cfg(model, 3 * 8 * 8, lib.fmha, sp="nccl")
+                assert mode == "cfg2", mode
+            sched.step_pre(0)
+            model.infer(inputs)
+            outs.append(sched.noise_pred.clone())
+        torch.cuda.synchronize()
+        if rank == 0:
+            torch.save({"equal": bool(torch.equal(outs[0], outs[1])), "max": float((outs[0] - outs[1]).abs().max())}, out_path)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_cfg_parallel_equals_serial_cfg(tmp_path):
+    """cond on rank 0, uncond on rank 1, predictions exchanged: bit-identical to the serial two-pass CFG on one GPU."""
+    import torch.multiprocessing as mp
+
+    out = str(tmp_path / "res_c.pt")
+    mp.spawn(_run_cfg_rank, args=(2, _free_port(), out), nprocs=2, join=True)
+    r = torch.load(out)
+    print("cfg-parallel vs serial:", r)
+    assert r["equal"], r
