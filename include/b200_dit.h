@@ -125,6 +125,44 @@ int b200_conv3d_cl(const void* in, int64_t in_st, int64_t in_sh, int64_t in_sw, 
                    int64_t res_sw, int T, int H, int W, int cin, int cout, int ntaps, const int32_t* taps, int clamp_out,
                    b200_stream_t stream);
 
+/* ---- one Wan DiT block as a single call ------------------------------------------------------------------------------------ */
+
+/* Weights of one block, bf16, checkpoint layout [N, K] row-major (blocks.<i>.* keys of wan/weights/transformer_weights.py:62-250). */
+typedef struct b200_wan_block_weights {
+  const void *wqkv, *bqkv;           /* self_attn.{q,k,v}.weight concatenated along N: [3D, D], [3D] */
+  const void *norm_q, *norm_k;       /* self_attn.norm_{q,k}.weight [D] */
+  const void *wo, *bo;               /* self_attn.o [D, D] */
+  const void *norm3_w, *norm3_b;     /* norm3 (affine LayerNorm) [D] */
+  const void *wcq, *bcq, *cnorm_q;   /* cross_attn.q [D, D], cross_attn.norm_q.weight [D] */
+  const void *wco, *bco;             /* cross_attn.o [D, D] */
+  const void *w0, *b0;               /* ffn.0 [F, D] */
+  const void *w2, *b2;               /* ffn.2 [D, F] */
+} b200_wan_block_weights;
+
+typedef struct b200_wan_block_args {
+  void* x;                                                                            /* residual stream [S, D], updated in place */
+  const void *shift_msa, *scale_msa, *gate_msa, *c_shift_msa, *c_scale_msa, *c_gate_msa; /* (modulation + embed0).chunk(6), [D] each */
+  const void* cos_sin;                                                                /* RoPE table [rope_rows, 64] float2 */
+  int64_t rope_rows;
+  const void *ctx_k, *ctx_v;                                                          /* text K (post norm_k) / V [ctx_len, H, 128] */
+  int64_t ctx_len;
+  const void *img_k, *img_v;                                                          /* i2v: CLIP K / V [img_len, H, 128] or NULL */
+  int64_t img_len;
+  int64_t S;
+  int D, H, F;
+  float eps;
+} b200_wan_block_args;
+
+int64_t b200_wan_block_workspace_bytes(int64_t S, int D, int F);
+
+/* x <- block(x): the launch schedule of WanTransformerInfer.infer_block (lightx2v/models/networks/wan/infer/transformer_infer.py
+ * :289-508: infer_modulation's outputs are inputs here; infer_self_attn, infer_cross_attn, infer_ffn, post_process) issued natively on
+ * `stream`: 13 kernel launches (15 for i2v), no allocation, no synchronisation; intermediates in `workspace`
+ * (b200_wan_block_workspace_bytes).  bf16 linears, single GPU; the quantised and sequence-parallel variants are composed from the
+ * per-op entry points by the host. */
+int b200_wan_block_fwd(const b200_wan_block_weights* w, const b200_wan_block_args* a, void* workspace, int64_t workspace_bytes,
+                       b200_stream_t stream);
+
 /* ---- w4a4 NVFP4 linears ------------------------------------------------------------------------------------------------- */
 
 /* bf16 x[rows, K] -> packed e2m1 q[rows, K/2] (two values per byte, low nibble = even element) + ue4m3 scale factors, one per 16

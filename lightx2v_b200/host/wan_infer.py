@@ -50,7 +50,7 @@ def rope_cos_sin(grid_sizes, freqs: torch.Tensor, head_dim: int, rows: Optional[
 class _BlockCache:
     """Per-block derived tensors: concatenated QKV weight/bias, cached cross-attention text K/V."""
 
-    __slots__ = ("wqkv", "bqkv", "sqkv", "ctx_key", "ck", "cv", "ck_img", "cv_img")
+    __slots__ = ("wqkv", "bqkv", "sqkv", "ctx_key", "ck", "cv", "ck_img", "cv_img", "native", "keep")
 
     def __init__(self):
         self.wqkv = None
@@ -58,6 +58,8 @@ class _BlockCache:
         self.sqkv = None
         self.ctx_key = None
         self.ck = self.cv = self.ck_img = self.cv_img = None
+        self.native = None        # lib.WanBlockWeightsC + the tensors it points to
+        self.keep = None
 
 
 class WanTransformerInfer:
@@ -76,6 +78,7 @@ class WanTransformerInfer:
         self.infer_conditional = True
         self.mask_map = None
         self.cache_cross_kv = bool(config.get("b200_cache_cross_kv", True))
+        self.native_block = bool(config.get("b200_native_block", True))   # one C call per block (csrc/wan_block.cu) when eligible
         self._caches: Dict[int, _BlockCache] = {}
         self._rope: Dict[Tuple, torch.Tensor] = {}
         self._bufs: Dict[Tuple, torch.Tensor] = {}
@@ -94,11 +97,43 @@ class WanTransformerInfer:
         return x
 
     def infer_block(self, weights, grid_sizes, embed, x, embed0, seq_lens, freqs, context):
-        shift_msa, scale_msa, gate_msa, c_shift_msa, c_scale_msa, c_gate_msa = self.infer_modulation(weights.compute_phases[0], embed0)
+        mods = self.infer_modulation(weights.compute_phases[0], embed0)
+        if self.native_block and self._native_eligible(weights):
+            return self._infer_block_native(weights, grid_sizes, x, mods, freqs, context)
+        shift_msa, scale_msa, gate_msa, c_shift_msa, c_scale_msa, c_gate_msa = mods
         x = self.infer_self_attn(weights.compute_phases[1], grid_sizes, x, seq_lens, freqs, shift_msa, scale_msa, gate_msa=gate_msa)
         x, attn_out = self.infer_cross_attn(weights.compute_phases[2], x, context, None, None)
         y = self.infer_ffn(weights.compute_phases[3], x, attn_out, c_shift_msa, c_scale_msa, c_gate_msa=c_gate_msa)
         return self.post_process(x, y, c_gate_msa)
+
+    # ------------------------------------------------------------------ whole block below the C ABI (csrc/wan_block.cu)
+    def _native_eligible(self, weights) -> bool:
+        """bf16 linears, no sequence-parallel hook: the cases b200_wan_block_fwd covers (fp8 / nvfp4 / Ulysses compose the per-op entries)."""
+        sa = weights.compute_phases[1]
+        return self.parallel_attention is None and not self._is_fp8(sa.self_attn_q) and not self._is_f4(sa.self_attn_q)
+
+    def _infer_block_native(self, weights, grid_sizes, x, mods, freqs, context):
+        sa, ca, ff = weights.compute_phases[1], weights.compute_phases[2], weights.compute_phases[3]
+        S, D = x.shape
+        dev = x.device
+        c = self._cache(sa)
+        if c.wqkv is None:
+            c.wqkv = torch.cat([self._nk(sa.self_attn_q), self._nk(sa.self_attn_k), self._nk(sa.self_attn_v)], dim=0).contiguous()
+            c.bqkv = torch.cat([sa.self_attn_q.bias, sa.self_attn_k.bias, sa.self_attn_v.bias]).contiguous()
+        if c.native is None:
+            c.keep = dict(wqkv=c.wqkv, bqkv=c.bqkv, norm_q=sa.self_attn_norm_q.weight, norm_k=sa.self_attn_norm_k.weight, wo=self._nk(sa.self_attn_o),
+                          bo=sa.self_attn_o.bias, norm3_w=ca.norm3.weight, norm3_b=ca.norm3.bias, wcq=self._nk(ca.cross_attn_q), bcq=ca.cross_attn_q.bias,
+                          cnorm_q=ca.cross_attn_norm_q.weight, wco=self._nk(ca.cross_attn_o), bco=ca.cross_attn_o.bias, w0=self._nk(ff.ffn_0),
+                          b0=ff.ffn_0.bias, w2=self._nk(ff.ffn_2), b2=ff.ffn_2.bias)
+            c.native = lib.wan_block_weights(**c.keep)
+        cc = self._cache(ca)
+        self._context_kv(ca, context, cc)
+        F_ = c.keep["w0"].shape[0]
+        ws = self._buf("native_ws", (lib.wan_block_workspace_bytes(S, D, F_) // 2,), dev)
+        cs = self._rope_table(grid_sizes, freqs, S, dev)
+        img = dict(img_k=cc.ck_img.reshape(-1, D), img_v=cc.cv_img.reshape(-1, D)) if self.task == "i2v" else {}
+        return lib.wan_block_fwd(c.native, x, tuple(m.contiguous() for m in mods), cs, min(S, cs.shape[0]), cc.ck.reshape(-1, D), cc.cv.reshape(-1, D), ws,
+                                 self.num_heads, F_, eps=sa.self_attn_norm_q.eps, **img)
 
     def infer_modulation(self, weights, embed0):
         """transformer_infer.py:308-319 (embed0 [6, D]); returns six contiguous [D] vectors."""

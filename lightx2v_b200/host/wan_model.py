@@ -45,13 +45,25 @@ class WanPreInfer:
         self.dim = config["dim"]
         self.text_len = config["text_len"]
         self.scheduler = None
+        self._t_table = None
 
     def set_scheduler(self, scheduler):
         self.scheduler = scheduler
+        self._t_table = None
+
+    def _t_embedding(self, device) -> torch.Tensor:
+        """Sinusoidal embedding of the current timestep (pre_infer.py:56-58).  The fp64 table for ALL timesteps of the schedule is built
+        once on the host (same element-wise math as the per-step call of the reference) and indexed on the device afterwards, so a
+        denoise step has no device->host synchronisation."""
+        ts = self.scheduler.timesteps
+        key = (ts.data_ptr(), ts._version, tuple(ts.shape))
+        if self._t_table is None or self._t_table[0] != key:
+            self._t_table = (key, sinusoidal_embedding_1d(self.freq_dim, ts.flatten().cpu()).to(device))
+        i = self.scheduler.step_index
+        return self._t_table[1][i:i + 1]
 
     def infer(self, W: Dict[str, torch.Tensor], inputs, positive: bool):
         x = self.scheduler.latents                                       # [C, F, H, W] (bf16 after step_pre)
-        t = torch.stack([self.scheduler.timesteps[self.scheduler.step_index]])
         context = inputs["text_encoder_output"]["context" if positive else "context_null"]
         if self.task == "i2v":
             clip_fea = inputs["image_encoder_output"]["clip_encoder_out"]
@@ -65,7 +77,7 @@ class WanPreInfer:
         xs = lib.gemm_bf16(patches, pw, W["patch_embedding.bias"])
         seq_lens = torch.tensor([xs.shape[0]], dtype=torch.long)
 
-        embed = sinusoidal_embedding_1d(self.freq_dim, t.flatten().cpu()).to(xs.device)
+        embed = self._t_embedding(xs.device)
         embed = lib.gemm_bf16(embed, W["time_embedding.0.weight"], W["time_embedding.0.bias"])
         embed = F.silu(embed)
         embed = lib.gemm_bf16(embed, W["time_embedding.2.weight"], W["time_embedding.2.bias"])

@@ -35,6 +35,8 @@ SIGNATURES = {
                               _i32, _ptr, _i32, _ptr]),
     "b200_conv3d_cl_padded": (_i32, [_ptr, _i64, _i64, _i64, _i32, _i32, _i32, _ptr, _ptr, _ptr, _i64, _i64, _i64, _ptr, _i64, _i64, _i64, _i32, _i32,
                                      _i32, _i32, _i32, _i32, _ptr, _i32, _ptr]),
+    "b200_wan_block_workspace_bytes": (_i64, [_i64, _i32, _i32]),
+    "b200_wan_block_fwd": (_i32, [_ptr, _ptr, _ptr, _i64, _ptr]),
     "b200_quant_nvfp4": (_i32, [_ptr, _i64, _i64, _i32, _ptr, _ptr, _i64, _ptr, _ptr]),
     "b200_nvfp4_act_scale": (_i32, [_ptr, _i64, _i64, _i32, _ptr, _ptr, _ptr, _ptr, _ptr]),
     "b200_gemm_nvfp4": (_i32, [_ptr, _i64, _ptr, _i64, _ptr, _ptr, _ptr, _ptr, _i64, _ptr, _ptr, _i64, _i64, _i64, _i32, _i32, _i32, _ptr]),
@@ -233,6 +235,64 @@ def conv3d_cl(x: torch.Tensor, wt: torch.Tensor, bias: Optional[torch.Tensor], o
                                ctypes.cast(tp, ctypes.c_void_p), 1 if clamp_out else 0, _stream())
     _check(rc, "b200_conv3d_cl")
     return out
+
+
+class WanBlockWeightsC(ctypes.Structure):
+    """struct b200_wan_block_weights (include/b200_dit.h)."""
+    _fields_ = [(n, ctypes.c_void_p) for n in ("wqkv", "bqkv", "norm_q", "norm_k", "wo", "bo", "norm3_w", "norm3_b", "wcq", "bcq", "cnorm_q", "wco", "bco",
+                                               "w0", "b0", "w2", "b2")]
+
+
+class WanBlockArgsC(ctypes.Structure):
+    """struct b200_wan_block_args (include/b200_dit.h)."""
+    _fields_ = ([("x", ctypes.c_void_p)] + [(n, ctypes.c_void_p) for n in ("shift_msa", "scale_msa", "gate_msa", "c_shift_msa", "c_scale_msa", "c_gate_msa")]
+                + [("cos_sin", ctypes.c_void_p), ("rope_rows", ctypes.c_int64), ("ctx_k", ctypes.c_void_p), ("ctx_v", ctypes.c_void_p), ("ctx_len", ctypes.c_int64),
+                   ("img_k", ctypes.c_void_p), ("img_v", ctypes.c_void_p), ("img_len", ctypes.c_int64), ("S", ctypes.c_int64), ("D", ctypes.c_int), ("H", ctypes.c_int),
+                   ("F", ctypes.c_int), ("eps", ctypes.c_float)])
+
+
+def wan_block_weights(**tensors) -> WanBlockWeightsC:
+    """Pack bf16 CUDA tensors (kept alive by the caller) into the C struct."""
+    w = WanBlockWeightsC()
+    for name, _ in WanBlockWeightsC._fields_:
+        t = tensors[name]
+        _req(t, name)
+        if not t.is_contiguous():
+            raise B200Error(f"wan_block_weights: {name} must be contiguous")
+        setattr(w, name, t.data_ptr())
+    return w
+
+
+def wan_block_workspace_bytes(S: int, D: int, F: int) -> int:
+    return int(load().b200_wan_block_workspace_bytes(S, D, F))
+
+
+def wan_block_fwd(w: WanBlockWeightsC, x: torch.Tensor, mods, cos_sin: torch.Tensor, rope_rows: int, ctx_k: torch.Tensor, ctx_v: torch.Tensor,
+                  workspace: torch.Tensor, heads: int, ffn_dim: int, *, img_k: Optional[torch.Tensor] = None, img_v: Optional[torch.Tensor] = None,
+                  eps: float = 1e-6) -> torch.Tensor:
+    """x [S, D] <- Wan block(x) in one native call; mods = (shift_msa, scale_msa, gate_msa, c_shift_msa, c_scale_msa, c_gate_msa)."""
+    _req(x, "x"); _req(ctx_k, "ctx_k"); _req(ctx_v, "ctx_v"); _req(cos_sin, "cos_sin", torch.float32)
+    if not (x.is_contiguous() and ctx_k.is_contiguous() and ctx_v.is_contiguous()):
+        raise B200Error("wan_block_fwd: x / ctx_k / ctx_v must be contiguous")
+    S, D = x.shape
+    a = WanBlockArgsC()
+    a.x = x.data_ptr()
+    for name, t in zip(("shift_msa", "scale_msa", "gate_msa", "c_shift_msa", "c_scale_msa", "c_gate_msa"), mods):
+        _req(t, name)
+        if not t.is_contiguous() or t.numel() != D:
+            raise B200Error(f"wan_block_fwd: {name} must be a contiguous [D] vector")
+        setattr(a, name, t.data_ptr())
+    a.cos_sin, a.rope_rows = cos_sin.data_ptr(), rope_rows
+    a.ctx_k, a.ctx_v, a.ctx_len = ctx_k.data_ptr(), ctx_v.data_ptr(), ctx_k.shape[0]
+    if img_k is not None:
+        _req(img_k, "img_k"); _req(img_v, "img_v")
+        a.img_k, a.img_v, a.img_len = img_k.data_ptr(), img_v.data_ptr(), img_k.shape[0]
+    else:
+        a.img_k, a.img_v, a.img_len = None, None, 0
+    a.S, a.D, a.H, a.F, a.eps = S, D, heads, ffn_dim, eps
+    rc = load().b200_wan_block_fwd(ctypes.byref(w), ctypes.byref(a), workspace.data_ptr(), workspace.numel() * workspace.element_size(), _stream())
+    _check(rc, "b200_wan_block_fwd")
+    return x
 
 
 def quant_nvfp4(x: torch.Tensor, global_scale: torch.Tensor):

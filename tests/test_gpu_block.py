@@ -112,3 +112,25 @@ def test_cross_kv_cache_invalidates_on_new_context():
     ctx1.mul_(0.5)                                  # in-place edit bumps the tensor version -> cache must refresh
     o1c = infer.infer(weights, g, None, x.clone(), embed0, None, freqs, ctx1)
     assert not torch.equal(o1, o1c)
+
+
+@pytest.mark.parametrize("name", ["wan13b_t2v_2blocks", "wan13b_i2v_1block"])
+def test_native_block_call_equals_per_op_schedule(golden_dir, name):
+    """b200_wan_block_fwd (one C call per block, csrc/wan_block.cu) issues the same kernels in the same order as the per-op Python
+    schedule: the two paths must agree bit for bit (t2v and the i2v two-softmax cross-attention)."""
+    T, meta = _load(os.path.join(golden_dir, name + ".safetensors"))
+    dim, heads, ffn, L, task = int(meta["dim"]), int(meta["heads"]), int(meta["ffn"]), int(meta["layers"]), meta["task"]
+    W = O.synth_block_weights(L, dim, ffn, task=task, seed=int(meta["weights_seed"]))
+    grid = T["grid"].view(1, 3)
+    freqs = O.wan_freqs_table(dim // heads)
+    outs = []
+    for native in (True, False):
+        cfg = dict(task=task, num_layers=L, num_heads=heads, dim=dim, ffn_dim=ffn, mm_config={}, b200_native_block=native)
+        weights, infer = _build(cfg, W)
+        assert infer.native_block == native
+        x = T["x_in"].cuda().clone()
+        outs.append(infer.infer(weights, grid, None, x, T["embed0"].cuda(), torch.tensor([x.shape[0]]), freqs, T["context"].cuda()).clone())
+    torch.cuda.synchronize()
+    assert torch.equal(outs[0], outs[1])
+    from lightx2v_b200 import lib
+    assert lib.wan_block_workspace_bytes(100, 1536, 8960) == 100 * (1536 + 8960) * 2
