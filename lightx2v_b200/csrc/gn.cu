@@ -14,6 +14,12 @@ namespace b200 {
 
 constexpr int GN_GROUPS = 32;
 
+__device__ __forceinline__ uint4 ld_nc_v4(const __nv_bfloat16* p) {
+  uint4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+  return v;
+}
+
 // Deterministic two-level reduction (no atomics: the decode must be reproducible run to run and across tile-parallel ranks):
 // thread -> warp shuffles -> fixed-order sum over the 8 warps -> one partial per block; a second tiny kernel sums the block
 // partials in block order in fp64.
@@ -33,13 +39,24 @@ gn_stats_kernel(const __nv_bfloat16* __restrict__ x, long long voxels, float* __
   float s[GPT], q[GPT];
 #pragma unroll
   for (int g = 0; g < GPT; ++g) s[g] = q[g] = 0.f;
-  for (long long v = (long long)blockIdx.x * VPB + sub; v < voxels; v += (long long)gridDim.x * VPB) {
-    const uint4 raw = *reinterpret_cast<const uint4*>(x + v * C + l * 8);
-    const float f[8] = {bf16_lo(raw.x), bf16_hi(raw.x), bf16_lo(raw.y), bf16_hi(raw.y), bf16_lo(raw.z), bf16_hi(raw.z), bf16_lo(raw.w), bf16_hi(raw.w)};
+  const long long stride = (long long)gridDim.x * VPB;
+  constexpr int U = 4;
+  for (long long v0 = (long long)blockIdx.x * VPB + sub; v0 < voxels; v0 += U * stride) {
+    uint4 raw[U];
 #pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      s[e / EPG] += f[e];
-      q[e / EPG] += f[e] * f[e];
+    for (int u = 0; u < U; ++u)
+      if (v0 + u * stride < voxels) raw[u] = ld_nc_v4(x + (v0 + u * stride) * C + l * 8);
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (v0 + u * stride < voxels) {
+        const float f[8] = {bf16_lo(raw[u].x), bf16_hi(raw[u].x), bf16_lo(raw[u].y), bf16_hi(raw[u].y),
+                            bf16_lo(raw[u].z), bf16_hi(raw[u].z), bf16_lo(raw[u].w), bf16_hi(raw[u].w)};
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          s[e / EPG] += f[e];
+          q[e / EPG] += f[e] * f[e];
+        }
+      }
     }
   }
 #pragma unroll
@@ -73,10 +90,21 @@ gn_stats_kernel(const __nv_bfloat16* __restrict__ x, long long voxels, float* __
   }
 }
 
-__global__ void gn_stats_finalize_kernel(const float* __restrict__ partials, int blocks, double* __restrict__ sums) {
+// 16 threads per output: thread j sums blocks j, j+16, ... in fp64, then the 16 partial sums are added in index order (fixed order ->
+// reproducible); 1024 threads keep the 1184 dependent loads of the serial version off the critical path of every GroupNorm.
+__global__ void __launch_bounds__(1024) gn_stats_finalize_kernel(const float* __restrict__ partials, int blocks, double* __restrict__ sums) {
+  __shared__ double part[16][2 * GN_GROUPS];
+  const int out = threadIdx.x % (2 * GN_GROUPS), j = threadIdx.x / (2 * GN_GROUPS);
   double t = 0.0;
-  for (int b = 0; b < blocks; ++b) t += (double)partials[(long long)b * 2 * GN_GROUPS + threadIdx.x];
-  sums[threadIdx.x] = t;
+  for (int b = j; b < blocks; b += 16) t += (double)partials[(long long)b * 2 * GN_GROUPS + out];
+  part[j][out] = t;
+  __syncthreads();
+  if (threadIdx.x < 2 * GN_GROUPS) {
+    double r = 0.0;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) r += part[k][threadIdx.x];
+    sums[threadIdx.x] = r;
+  }
 }
 
 // sums: fp64 workspace of gn_stats_workspace_doubles() entries; the first 64 hold the result (sum[32], sum of squares[32]).
@@ -99,7 +127,7 @@ int gn_stats_cl(const void* x, long long voxels, int C, double* sums, cudaStream
       set_last_error("b200_gn_stats_cl: unsupported channel count %d (64 / 128 / 256 / 512)", C);
       return B200_ERR_UNSUPPORTED;
   }
-  gn_stats_finalize_kernel<<<1, 2 * GN_GROUPS, 0, stream>>>(partials, blocks, sums);
+  gn_stats_finalize_kernel<<<1, 16 * 2 * GN_GROUPS, 0, stream>>>(partials, blocks, sums);
   B200_CHECK_CUDA(cudaGetLastError());
   return B200_OK;
 }
@@ -134,25 +162,41 @@ gn_apply_pad_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restri
   }
   const int Hp = H + 2 * ph, Wp = W + 2 * pw;
   const long long pvox = (long long)(T + pt) * Hp * Wp;
-  for (long long v = (long long)blockIdx.x * VPB + sub; v < pvox; v += (long long)gridDim.x * VPB) {
-    const int wp = (int)(v % Wp);
-    const long long r = v / Wp;
-    const int hp = (int)(r % Hp);
-    const int tp = (int)(r / Hp);
-    const int t = max(tp - pt, 0), h = min(max(hp - ph, 0), H - 1), w = min(max(wp - pw, 0), W - 1);
-    const uint4 raw = *reinterpret_cast<const uint4*>(x + (((long long)t * H + h) * W + w) * C + l * 8);
-    float f[8] = {bf16_lo(raw.x), bf16_hi(raw.x), bf16_lo(raw.y), bf16_hi(raw.y), bf16_lo(raw.z), bf16_hi(raw.z), bf16_lo(raw.w), bf16_hi(raw.w)};
-    if (sums != nullptr) {
+  const long long stride = (long long)gridDim.x * VPB;
+  constexpr int U = 4;   // independent 16-byte loads in flight per thread: an HBM-bound pass needs several MB outstanding chip-wide
+  for (long long v0 = (long long)blockIdx.x * VPB + sub; v0 < pvox; v0 += U * stride) {
+    uint4 raw[U];
 #pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        float u = fmaf(f[e], a[e], b[e]);
-        if (apply_silu) u = u / (1.0f + __expf(-u));
-        f[e] = u;
+    for (int u = 0; u < U; ++u) {
+      const long long v = v0 + u * stride;
+      if (v < pvox) {
+        const int wp = (int)(v % Wp);
+        const long long r = v / Wp;
+        const int hp = (int)(r % Hp);
+        const int tp = (int)(r / Hp);
+        const int t = max(tp - pt, 0), h = min(max(hp - ph, 0), H - 1), w = min(max(wp - pw, 0), W - 1);
+        raw[u] = ld_nc_v4(x + (((long long)t * H + h) * W + w) * C + l * 8);
       }
     }
-    uint4 o;
-    o.x = pack_bf16(f[0], f[1]); o.y = pack_bf16(f[2], f[3]); o.z = pack_bf16(f[4], f[5]); o.w = pack_bf16(f[6], f[7]);
-    *reinterpret_cast<uint4*>(y + v * C + l * 8) = o;
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long long v = v0 + u * stride;
+      if (v < pvox) {
+        float f[8] = {bf16_lo(raw[u].x), bf16_hi(raw[u].x), bf16_lo(raw[u].y), bf16_hi(raw[u].y),
+                      bf16_lo(raw[u].z), bf16_hi(raw[u].z), bf16_lo(raw[u].w), bf16_hi(raw[u].w)};
+        if (sums != nullptr) {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            float y_ = fmaf(f[e], a[e], b[e]);
+            if (apply_silu) y_ = y_ / (1.0f + __expf(-y_));
+            f[e] = y_;
+          }
+        }
+        uint4 o;
+        o.x = pack_bf16(f[0], f[1]); o.y = pack_bf16(f[2], f[3]); o.z = pack_bf16(f[4], f[5]); o.w = pack_bf16(f[6], f[7]);
+        *reinterpret_cast<uint4*>(y + v * C + l * 8) = o;
+      }
+    }
   }
 }
 

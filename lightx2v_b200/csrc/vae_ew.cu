@@ -28,28 +28,39 @@ rms_silu_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__
 #pragma unroll
       for (int e = 0; e < 8; ++e) g[e] = gamma[l * 8 + e] * sqrt_c;
     }
-    for (long long v0 = warp_global * VPW; v0 < voxels; v0 += nwarps * VPW) {
-      const long long v = v0 + sub;
-      const bool ok = v < voxels && l < LPV;
-      uint4 raw = make_uint4(0, 0, 0, 0);
-      if (ok) raw = *reinterpret_cast<const uint4*>(x + v * C + l * 8);
-      float f[8] = {bf16_lo(raw.x), bf16_hi(raw.x), bf16_lo(raw.y), bf16_hi(raw.y), bf16_lo(raw.z), bf16_hi(raw.z), bf16_lo(raw.w), bf16_hi(raw.w)};
-      float ss = 0.f;
+    constexpr int U = 4;   // independent 16-byte loads in flight per lane (HBM-bound: keep several MB outstanding chip-wide)
+    const long long stride = nwarps * VPW;
+    for (long long v0 = warp_global * VPW; v0 < voxels; v0 += U * stride) {
+      uint4 raw[U];
 #pragma unroll
-      for (int e = 0; e < 8; ++e) ss += f[e] * f[e];
+      for (int u = 0; u < U; ++u) {
+        const long long v = v0 + u * stride + sub;
+        raw[u] = make_uint4(0, 0, 0, 0);
+        if (v < voxels && l < LPV) raw[u] = *reinterpret_cast<const uint4*>(x + v * C + l * 8);
+      }
 #pragma unroll
-      for (int o = G / 2; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
-      const float inv = 1.0f / fmaxf(sqrtf(ss), 1e-12f);        // F.normalize: x / max(||x||_2, eps)
-      if (ok) {
+      for (int u = 0; u < U; ++u) {
+        const long long v = v0 + u * stride + sub;
+        const bool ok = v < voxels && l < LPV;
+        float f[8] = {bf16_lo(raw[u].x), bf16_hi(raw[u].x), bf16_lo(raw[u].y), bf16_hi(raw[u].y),
+                      bf16_lo(raw[u].z), bf16_hi(raw[u].z), bf16_lo(raw[u].w), bf16_hi(raw[u].w)};
+        float ss = 0.f;
 #pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          float t = f[e] * inv * g[e];
-          if (apply_silu) t = t / (1.0f + __expf(-t));
-          f[e] = t;
+        for (int e = 0; e < 8; ++e) ss += f[e] * f[e];
+#pragma unroll
+        for (int o = G / 2; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+        const float inv = 1.0f / fmaxf(sqrtf(ss), 1e-12f);        // F.normalize: x / max(||x||_2, eps)
+        if (ok) {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            float t = f[e] * inv * g[e];
+            if (apply_silu) t = t / (1.0f + __expf(-t));
+            f[e] = t;
+          }
+          uint4 o;
+          o.x = pack_bf16(f[0], f[1]); o.y = pack_bf16(f[2], f[3]); o.z = pack_bf16(f[4], f[5]); o.w = pack_bf16(f[6], f[7]);
+          *reinterpret_cast<uint4*>(y + v * C + l * 8) = o;
         }
-        uint4 o;
-        o.x = pack_bf16(f[0], f[1]); o.y = pack_bf16(f[2], f[3]); o.z = pack_bf16(f[4], f[5]); o.w = pack_bf16(f[6], f[7]);
-        *reinterpret_cast<uint4*>(y + v * C + l * 8) = o;
       }
     }
   } else {
