@@ -130,3 +130,37 @@ def test_nvfp4_block_psnr_vs_oracle_and_bf16_reference():
     assert torch.equal(a.weight, b.weight) and torch.equal(a.weight_scale, b.weight_scale) and torch.equal(a.weight_global_scale, b.weight_global_scale)
     sd = a.state_dict()
     assert sd[a.weight_name].dtype == torch.uint8 and a.weight_scale_name in sd and a.weight_global_scale_name in sd
+
+
+def test_full_size_properties_nvfp4(lib):
+    """BASELINE sizes (75 600 tokens x 5120 -> 5120), where the oracle cannot run in full: (a) quantiser rows sampled across the whole
+    tensor are bit-identical to the oracle, incl. the scale-factor layout at large row indices; (b) the two tile shapes of the GEMM
+    (BLOCK_N 128 / 256, same K order) agree bit for bit; (c) doubling alpha doubles the output exactly (power-of-two linearity);
+    (d) sampled output rows match the dequantised fp32 matmul."""
+    M, N, K = 75600, 5120, 5120
+    g = torch.Generator(device="cuda").manual_seed(123)
+    a = (torch.randn(M, K, generator=g, device="cuda") * 1.1).to(torch.bfloat16)
+    b = (torch.randn(N, K, generator=g, device="cuda") * 0.03).to(torch.bfloat16)
+    gs_b, _ = lib.nvfp4_act_scale(b)
+    gs_a, alpha = lib.nvfp4_act_scale(a, gs_b)
+    assert torch.equal(gs_a.cpu(), NV.global_scale_for(a.cpu()).reshape(1))
+    aq, sfa = lib.quant_nvfp4(a, gs_a)
+    bq, sfb = lib.quant_nvfp4(b, gs_b)
+    rows = torch.tensor([0, 1, 127, 128, 4095, 37777, 75519, 75599])
+    ref_q, ref_sf = NV.quant(a[rows.cuda()].cpu(), gs_a.cpu()[0])
+    assert torch.equal(NV.unpack_e2m1(aq[rows.cuda()].cpu()), ref_q)
+    sf_lin = NV.unswizzle_sf(sfa.cpu(), M, K)
+    assert torch.equal(sf_lin[rows].view(torch.float8_e4m3fn).float(), ref_sf)
+    o128 = lib.gemm_nvfp4(aq, bq, sfa, sfb, alpha, block_n=128)
+    o256 = lib.gemm_nvfp4(aq, bq, sfa, sfb, alpha, block_n=256)
+    assert torch.equal(o128, o256)
+    o2 = lib.gemm_nvfp4(aq, bq, sfa, sfb, alpha * 2, block_n=128)
+    assert torch.equal(o2.float(), o128.float() * 2)
+    ref = NV.scaled_fp4_mm(aq[rows.cuda()].cpu(), bq.cpu(), sf_rows_swizzled(sf_lin[rows], K), sfb.cpu(), gs_a.cpu()[0], gs_b.cpu()[0])
+    err = (o128[rows.cuda()].float().cpu() - ref).abs()
+    assert err.max() <= 2e-2 + 8e-3 * ref.abs().max()
+
+
+def sf_rows_swizzled(sf_rows_linear, K):
+    """Re-swizzle a few linear scale rows so the oracle's dequantiser (which expects the MMA layout) can consume them."""
+    return NV.swizzle_sf(sf_rows_linear, sf_rows_linear.shape[0], K)
