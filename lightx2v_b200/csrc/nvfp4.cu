@@ -125,7 +125,9 @@ absmax_kernel(const __nv_bfloat16* __restrict__ x, long long ldx, long long rows
 __global__ void nvfp4_scale_finalize_kernel(const uint32_t* __restrict__ amax_bits, const float* __restrict__ weight_global_scale,
                                             float* __restrict__ global_scale, float* __restrict__ alpha) {
   const float amax = __uint_as_float(*amax_bits);
-  const float gs = amax > 0.f ? __fdiv_rn(448.0f * 6.0f, amax) : 1.0f;
+  // torch evaluates `scalar / tensor` as reciprocal(tensor) * scalar (two roundings) - the form the reference's recipe is written in
+  // (test_bench1.py:120-121: (FLOAT8_E4M3_MAX * FLOAT4_E2M1_MAX) / torch.amax(...)); reproduced so the scale is bit-identical
+  const float gs = amax > 0.f ? __fmul_rn(__frcp_rn(amax), 448.0f * 6.0f) : 1.0f;
   *global_scale = gs;
   if (alpha != nullptr) *alpha = __fdiv_rn(1.0f, __fmul_rn(gs, weight_global_scale ? *weight_global_scale : 1.0f));
 }

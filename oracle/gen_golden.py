@@ -360,16 +360,59 @@ def gen_nvfp4_fixture():
     print("nvfp4_quant_small", float(out.abs().max()), "zero-scale groups", int((sa == 0).sum()))
 
 
+def gen_teacache_fixture():
+    """Decision sequence of the REAL WanTransformerInferTeaCaching.calculate_should_calc (feature_caching/transformer_infer.py:30-82) on a
+    seeded random walk of timestep embeddings, cond / uncond passes interleaved as WanModel.infer does, for both `use_ret_steps` modes
+    with the coefficients of configs/caching/teacache/wan_t2v_1_3b_tea_480p.json; `.cuda()` is patched to the identity (CPU run)."""
+    import json
+
+    from safetensors.torch import save_file
+
+    from lightx2v.models.networks.wan.infer.feature_caching.transformer_infer import WanTransformerInferTeaCaching
+
+    torch.Tensor.cuda = lambda self, *a, **k: self
+    ref_cfg = json.load(open(os.path.join(REF, "configs", "caching", "teacache", "wan_t2v_1_3b_tea_480p.json")))
+    steps = 20
+    g = torch.Generator().manual_seed(17)
+    base = torch.randn(1, 1536, generator=g)
+    drift = [base * (1.0 + 0.01 * i) + 0.012 * (1 + (i % 4)) * torch.randn(1, 1536, generator=g) for i in range(steps)]
+    embeds = torch.stack([d.to(torch.bfloat16) for d in drift])                       # [steps, 1, 1536]
+    embed0s = torch.stack([(d.repeat(1, 6) * 0.5).to(torch.bfloat16).view(6, 1536) for d in drift])
+    out = {"embeds": embeds, "embed0s": embed0s}
+    for mode in (True, False):
+        cfg = Cfg(task="t2v", num_layers=1, num_heads=12, dim=1536, cpu_offload=False, infer_steps=steps, enable_cfg=True,
+                  teacache_thresh=ref_cfg["teacache_thresh"], coefficients=ref_cfg["coefficients"], use_ret_steps=mode)
+        ti = WanTransformerInferTeaCaching(cfg)
+        rec = []
+        for i in range(steps):
+            for cond in (True, False):
+                ti.infer_conditional = cond
+                rec.append(bool(ti.calculate_should_calc(embeds[i], embed0s[i])))
+                ti.cnt += 1
+        out[f"decisions_ret{int(mode)}"] = torch.tensor(rec, dtype=torch.uint8)
+    save_file(out, os.path.join(GOLD, "wan_teacache_decisions.safetensors"),
+              metadata={"thresh": str(ref_cfg["teacache_thresh"]), "coefficients": json.dumps(ref_cfg["coefficients"]),
+                        "generator": "oracle/gen_golden.py:gen_teacache_fixture", "reference": "ModelTC/lightx2v@0591c35e"})
+    print("wan_teacache_decisions", {k: int(v.sum()) for k, v in out.items() if k.startswith("dec")}, "of", 2 * steps)
+
+
 if __name__ == "__main__":
+    if os.environ.get("GOLDEN_ONLY", "") == "teacache":
+        install_shims()
+        os.makedirs(GOLD, exist_ok=True)
+        gen_teacache_fixture()
+        sys.exit(0)
     if os.environ.get("GOLDEN_ONLY", "") == "nvfp4":
         os.makedirs(GOLD, exist_ok=True)
         gen_nvfp4_fixture()
+        gen_teacache_fixture()
         sys.exit(0)
     if os.environ.get("GOLDEN_ONLY", "") == "hunyuan_vae":
         install_shims()
         os.makedirs(GOLD, exist_ok=True)
         gen_hunyuan_vae_fixture()
         gen_nvfp4_fixture()
+        gen_teacache_fixture()
         sys.exit(0)
     if os.environ.get("GOLDEN_ONLY", "") == "hunyuan":
         install_shims()
@@ -390,3 +433,4 @@ if __name__ == "__main__":
         gen_hunyuan_fixture()
         gen_hunyuan_vae_fixture()
         gen_nvfp4_fixture()
+        gen_teacache_fixture()

@@ -134,3 +134,44 @@ def test_native_block_call_equals_per_op_schedule(golden_dir, name):
     assert torch.equal(outs[0], outs[1])
     from lightx2v_b200 import lib
     assert lib.wan_block_workspace_bytes(100, 1536, 8960) == 100 * (1536 + 8960) * 2
+
+
+def test_teacache_skips_blocks_and_reuses_the_cached_residual():
+    """WanTransformerInferTeaCaching over the CUDA block stack: computed forwards equal the plain stack bit for bit and store x_out - x_in;
+    skipped forwards return x + cached residual of the same (cond / uncond) branch.  Threshold 1e9 forces 'skip' between warm-up and cut-off."""
+    from lightx2v_b200.host.wan_infer import WanTransformerInfer
+    from lightx2v_b200.host.wan_teacache import WanTransformerInferTeaCaching
+
+    dim, heads, ffn, L, grid = 1536, 12, 8960, 2, (2, 6, 8)
+    S = grid[0] * grid[1] * grid[2]
+    W = O.synth_block_weights(L, dim, ffn, seed=5)
+    cfg = dict(task="t2v", num_layers=L, num_heads=heads, dim=dim, ffn_dim=ffn, mm_config={}, infer_steps=4, enable_cfg=True, teacache_thresh=1e9,
+               coefficients=[[0, 0, 0, 1.0, 0.0], [0, 0, 0, 1.0, 0.0]], use_ret_steps=False)
+    weights, plain = _build(cfg, W)
+    tea = WanTransformerInferTeaCaching(cfg)
+
+    class Sched:
+        infer_steps = 4
+        step_index = 0
+
+    sched = Sched()
+    tea.set_scheduler(sched)
+    freqs = O.wan_freqs_table(dim // heads)
+    g = torch.tensor([grid])
+    pattern, residual = [], {True: None, False: None}
+    for step in range(4):
+        sched.step_index = step
+        for cond in (True, False):
+            x, embed0, context = O.synth_block_inputs(S, dim, seed=10 * step + int(cond), device="cuda")
+            embed = embed0[:1].clone()
+            assert tea.infer_conditional == cond
+            out = tea.infer(weights, g, embed, x.clone(), embed0, None, freqs, context)
+            computed = (sched.caching_records if cond else sched.caching_records_2)[step]
+            pattern.append(computed)
+            if computed:
+                ref = plain.infer(weights, g, embed, x.clone(), embed0, None, freqs, context)
+                assert torch.equal(out, ref)
+                residual[cond] = ref - x
+            else:
+                assert torch.equal(out, x + residual[cond])
+    assert pattern == [True, True, False, False, False, False, True, True]       # ret_steps = 2, cutoff = 2 * 4 - 2

@@ -143,22 +143,22 @@ def test_full_size_properties_nvfp4(lib):
     b = (torch.randn(N, K, generator=g, device="cuda") * 0.03).to(torch.bfloat16)
     gs_b, _ = lib.nvfp4_act_scale(b)
     gs_a, alpha = lib.nvfp4_act_scale(a, gs_b)
-    assert torch.equal(gs_a.cpu(), NV.global_scale_for(a.cpu()).reshape(1))
+    assert torch.equal(gs_a.cpu(), NV.global_scale_for(a.cpu()).reshape(1)), "global scale"
     aq, sfa = lib.quant_nvfp4(a, gs_a)
     bq, sfb = lib.quant_nvfp4(b, gs_b)
     rows = torch.tensor([0, 1, 127, 128, 4095, 37777, 75519, 75599])
     ref_q, ref_sf = NV.quant(a[rows.cuda()].cpu(), gs_a.cpu()[0])
-    assert torch.equal(NV.unpack_e2m1(aq[rows.cuda()].cpu()), ref_q)
+    assert torch.equal(NV.unpack_e2m1(aq[rows.cuda()].cpu()), ref_q), "sampled e2m1 rows"
     sf_lin = NV.unswizzle_sf(sfa.cpu(), M, K)
-    assert torch.equal(sf_lin[rows].view(torch.float8_e4m3fn).float(), ref_sf)
+    assert torch.equal(sf_lin[rows].view(torch.float8_e4m3fn).float(), ref_sf), "sampled scale rows"
     o128 = lib.gemm_nvfp4(aq, bq, sfa, sfb, alpha, block_n=128)
     o256 = lib.gemm_nvfp4(aq, bq, sfa, sfb, alpha, block_n=256)
-    assert torch.equal(o128, o256)
+    assert torch.equal(o128, o256), f"tile shapes differ: {(o128.float() - o256.float()).abs().max().item()} on {(o128 != o256).float().mean().item():.2e} of the elements"
     o2 = lib.gemm_nvfp4(aq, bq, sfa, sfb, alpha * 2, block_n=128)
-    assert torch.equal(o2.float(), o128.float() * 2)
+    assert torch.equal(o2.float(), o128.float() * 2), "alpha linearity"
     ref = NV.scaled_fp4_mm(aq[rows.cuda()].cpu(), bq.cpu(), sf_rows_swizzled(sf_lin[rows], K), sfb.cpu(), gs_a.cpu()[0], gs_b.cpu()[0])
     err = (o128[rows.cuda()].float().cpu() - ref).abs()
-    assert err.max() <= 2e-2 + 8e-3 * ref.abs().max()
+    assert err.max() <= 2e-2 + 8e-3 * ref.abs().max(), (float(err.max()), float(ref.abs().max()))
 
 
 def sf_rows_swizzled(sf_rows_linear, K):

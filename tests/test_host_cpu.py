@@ -180,3 +180,29 @@ def test_vae_dist_strip_bounds_match_reference_rules():
         assert first_lat * 8 + first_px == 20 * r * 8
         cols.append(px)
     assert sum(cols) == 1280
+
+
+def test_teacache_decisions_match_reference_fixture(golden_dir):
+    """host/wan_teacache.py decision logic vs the decisions recorded from the REAL WanTransformerInferTeaCaching.calculate_should_calc
+    (tests/golden/wan_teacache_decisions.safetensors), both `use_ret_steps` modes, cond / uncond interleaved."""
+    import json
+
+    from safetensors import safe_open
+
+    from lightx2v_b200.host.wan_teacache import WanTransformerInferTeaCaching
+
+    with safe_open(os.path.join(golden_dir, "wan_teacache_decisions.safetensors"), framework="pt") as f:
+        T = {k: f.get_tensor(k) for k in f.keys()}
+        meta = f.metadata()
+    steps = T["embeds"].shape[0]
+    for mode in (True, False):
+        cfg = dict(task="t2v", num_layers=1, num_heads=12, dim=1536, infer_steps=steps, enable_cfg=True, teacache_thresh=float(meta["thresh"]),
+                   coefficients=json.loads(meta["coefficients"]), use_ret_steps=mode)
+        ti = WanTransformerInferTeaCaching(cfg)
+        got = []
+        for i in range(steps):
+            for cond in (True, False):
+                ti.infer_conditional = cond
+                got.append(ti.calculate_should_calc(T["embeds"][i], T["embed0s"][i]))
+                ti.cnt += 1
+        assert got == [bool(v) for v in T[f"decisions_ret{int(mode)}"]], mode
