@@ -206,3 +206,31 @@ def test_teacache_decisions_match_reference_fixture(golden_dir):
                 got.append(ti.calculate_should_calc(T["embeds"][i], T["embed0s"][i]))
                 ti.cnt += 1
         assert got == [bool(v) for v in T[f"decisions_ret{int(mode)}"]], mode
+
+
+def test_block_driver_structs_match_header():
+    """The ctypes mirrors of b200_wan_block_weights / b200_wan_block_args must list the header's fields in the header's order
+    (a silent mismatch would hand the native driver the wrong pointers)."""
+    import re
+
+    from lightx2v_b200 import lib
+
+    hdr = open(os.path.join(ROOT, "include", "b200_dit.h")).read()
+
+    def fields(struct):
+        body = re.search(r"typedef struct %s \{(.*?)\} %s;" % (struct, struct), hdr, re.S).group(1)
+        body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+        names = []
+        for decl in body.split(";"):
+            decl = decl.strip()
+            if not decl:
+                continue
+            for part in decl.split(","):
+                names.append(re.sub(r"[\s\*]", " ", part).split()[-1])
+        return names
+
+    assert fields("b200_wan_block_weights") == [n for n, _ in lib.WanBlockWeightsC._fields_]
+    assert fields("b200_wan_block_args") == [n for n, _ in lib.WanBlockArgsC._fields_]
+    import ctypes as C
+    types = dict(lib.WanBlockArgsC._fields_)
+    assert types["S"] is C.c_int64 and types["ctx_len"] is C.c_int64 and types["D"] is C.c_int and types["eps"] is C.c_float
