@@ -34,6 +34,9 @@ WORKLOADS = {
     # north_star's w4a4-nvfp4 weight path on the same distilled sampler (the reference ships the kernels but no model wiring for it)
     "wan2.1-t2v-14b-nvfp4-distill-720p-81f": dict(dim=5120, num_heads=40, ffn_dim=13824, num_layers=40, target_shape=(16, 21, 90, 160), infer_steps=4,
                                                   enable_cfg=False, sample_guide_scale=1.0, sample_shift=5.0, nvfp4=True, distill=True),
+    # BASELINE config 4: image-to-video (36 input channels = 16 noise + 4 mask + 16 VAE-encoded image, 257 CLIP tokens in a second cross-attention)
+    "wan2.1-i2v-14b-720p-81f": dict(dim=5120, num_heads=40, ffn_dim=13824, num_layers=40, target_shape=(16, 21, 90, 160), infer_steps=50,
+                                    enable_cfg=True, sample_guide_scale=5.0, sample_shift=5.0, task="i2v"),
     "wan2.1-t2v-1.3b-480p-17f": dict(dim=1536, num_heads=12, ffn_dim=8960, num_layers=30, target_shape=(16, 5, 60, 104), infer_steps=50,
                                      enable_cfg=True, sample_guide_scale=5.0, sample_shift=5.0),   # quick self-test of this script
 }
@@ -51,7 +54,7 @@ def step_flops(cfg):
     from oracle.wan_oracle import block_flops  # FLOP model only; not on the measured path
     C, Fr, H, W = cfg["target_shape"]
     S = Fr * (H // 2) * (W // 2)
-    per_fwd = cfg["num_layers"] * block_flops(S, cfg["dim"], cfg["ffn_dim"], 512)
+    per_fwd = cfg["num_layers"] * block_flops(S, cfg["dim"], cfg["ffn_dim"], 512, i2v=cfg.get("task") == "i2v")
     return S, per_fwd * (2 if cfg["enable_cfg"] else 1)
 
 
@@ -68,7 +71,8 @@ def synth_weights(cfg, device, seed=42):
         W[name + ".weight"] = rnd(n, k)
         W[name + ".bias"] = rnd(n)
 
-    W["patch_embedding.weight"] = rnd(D, 16, 1, 2, 2, scale=0.05)
+    i2v = cfg.get("task") == "i2v"
+    W["patch_embedding.weight"] = rnd(D, 36 if i2v else 16, 1, 2, 2, scale=0.05)
     W["patch_embedding.bias"] = rnd(D)
     lin("text_embedding.0", D, 4096)
     lin("text_embedding.2", D, D)
@@ -88,6 +92,15 @@ def synth_weights(cfg, device, seed=42):
         W[p + "norm3.bias"] = rnd(D)
         lin(p + "ffn.0", F_, D)
         lin(p + "ffn.2", D, F_)
+        if i2v:
+            lin(p + "cross_attn.k_img", D, D)
+            lin(p + "cross_attn.v_img", D, D)
+            W[p + "cross_attn.norm_k_img.weight"] = (1.0 + rnd(D, scale=0.05).float()).to(torch.bfloat16)
+    if i2v:                                                       # img_emb.proj: LN(1280) -> Linear(1280, 1280) -> GELU -> Linear(1280, D) -> LN(D)
+        W["img_emb.proj.0.weight"], W["img_emb.proj.0.bias"] = (1.0 + rnd(1280, scale=0.05).float()).to(torch.bfloat16), rnd(1280)
+        lin("img_emb.proj.1", 1280, 1280)
+        lin("img_emb.proj.3", D, 1280)
+        W["img_emb.proj.4.weight"], W["img_emb.proj.4.bias"] = (1.0 + rnd(D, scale=0.05).float()).to(torch.bfloat16), rnd(D)
     return W
 
 
@@ -141,7 +154,8 @@ def run_ours(args):
     lib.load()
 
     cfg = dict(WORKLOADS[args.workload])
-    cfg.update(task="t2v", freq_dim=256, text_len=512, in_dim=16, out_dim=16, seed=42, mm_config={}, patch_size=(1, 2, 2))
+    cfg.update(task=cfg.get("task", "t2v"), freq_dim=256, text_len=512, in_dim=36 if cfg.get("task") == "i2v" else 16, out_dim=16, seed=42, mm_config={},
+               patch_size=(1, 2, 2))
     if cfg.get("fp8"):
         from lightx2v_b200.host.ops import FP8_MM_KEY
         cfg["mm_config"] = {"mm_type": FP8_MM_KEY, "weight_auto_quant": True}
@@ -164,6 +178,10 @@ def run_ours(args):
     ctx = {"context": torch.randn(512, 4096, generator=g, device=dev).to(torch.bfloat16),
            "context_null": torch.randn(512, 4096, generator=g, device=dev).to(torch.bfloat16)}
     inputs = {"text_encoder_output": ctx, "image_encoder_output": None}
+    if cfg["task"] == "i2v":      # synthetic encoder outputs of the published shapes: CLIP ViT-H tokens, VAE-encoded image + mask
+        ts = cfg["target_shape"]
+        inputs["image_encoder_output"] = {"clip_encoder_out": torch.randn(257, 1280, generator=g, device=dev).to(torch.bfloat16),
+                                          "vae_encode_out": torch.randn(20, ts[1], ts[2], ts[3], generator=g, device=dev).to(torch.bfloat16)}
 
     # launch counter + per-launch CUDA events for the dominant kernel (self-attention FMHA)
     counters = {"launches": 0}
