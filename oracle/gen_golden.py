@@ -396,16 +396,63 @@ def gen_teacache_fixture():
     print("wan_teacache_decisions", {k: int(v.sum()) for k, v in out.items() if k.startswith("dec")}, "of", 2 * steps)
 
 
+def gen_causvid_fixture():
+    """Real WanTransformerInferCausVid (wan/infer/causvid/transformer_infer.py) - the autoregressive block variant with a self-attention KV
+    cache - on two Wan-1.3B-width blocks, three chunks of one latent frame (6 x 8 = 48 tokens each) fed in order with kv_start / kv_end
+    advancing, t2v, torch_sdpa.  Outputs per chunk + the final K cache of block 0 pin oracle.wan_oracle.infer_blocks_causvid."""
+    from safetensors.torch import save_file
+
+    import lightx2v.common.ops  # noqa: F401
+    from lightx2v.models.networks.wan.infer.causvid.transformer_infer import WanTransformerInferCausVid
+    from lightx2v.models.networks.wan.weights.transformer_weights import WanTransformerWeights
+
+    from oracle import wan_oracle as O
+
+    dim, heads, ffn, L = 1536, 12, 8960, 2
+    frame_tokens, chunks = 48, 3
+    cfg = ref_config(dim, heads, ffn, L, "t2v")
+    cfg.update(num_frames=chunks, num_frame_per_block=1, frame_seq_length=frame_tokens, model_cls="wan2.1_causvid")
+    W = O.synth_block_weights(L, dim, ffn, seed=42)
+    weights = WanTransformerWeights(cfg)
+    weights.load(W)
+    infer = WanTransformerInferCausVid(cfg)
+    infer._init_kv_cache(torch.bfloat16, "cpu")
+    infer._init_crossattn_cache(torch.bfloat16, "cpu")
+    freqs = O.wan_freqs_table(dim // heads)
+    gs = torch.tensor([[1, 6, 8]], dtype=torch.long)
+    tensors = {}
+    context = None
+    for c in range(chunks):
+        x, embed0, ctx = O.synth_block_inputs(frame_tokens, dim, seed=100 + c)
+        context = ctx if context is None else context                      # the prompt does not change between chunks
+        tensors[f"x_in.{c}"], tensors[f"embed0.{c}"] = x.clone(), embed0
+        out = infer.infer(weights, gs, None, x, embed0, torch.tensor([frame_tokens]), freqs, context, c * frame_tokens, (c + 1) * frame_tokens)
+        tensors[f"x_out.{c}"] = out.clone()
+    tensors["context"] = context
+    tensors["k_cache.0"] = infer.kv_cache[0]["k"].reshape(chunks * frame_tokens, dim).clone()
+    save_file({k: v.contiguous() for k, v in tensors.items()}, os.path.join(GOLD, "wan13b_causvid_2blocks.safetensors"),
+              metadata={"dim": str(dim), "heads": str(heads), "ffn": str(ffn), "layers": str(L), "chunks": str(chunks), "frame_tokens": str(frame_tokens),
+                        "grid": "1,6,8", "weights_seed": "42", "generator": "oracle/gen_golden.py:gen_causvid_fixture", "reference": "ModelTC/lightx2v@0591c35e"})
+    print("wan13b_causvid_2blocks", [float(tensors[f"x_out.{c}"].float().abs().max()) for c in range(chunks)])
+
+
 if __name__ == "__main__":
+    if os.environ.get("GOLDEN_ONLY", "") == "causvid":
+        install_shims()
+        os.makedirs(GOLD, exist_ok=True)
+        gen_causvid_fixture()
+        sys.exit(0)
     if os.environ.get("GOLDEN_ONLY", "") == "teacache":
         install_shims()
         os.makedirs(GOLD, exist_ok=True)
         gen_teacache_fixture()
+        gen_causvid_fixture()
         sys.exit(0)
     if os.environ.get("GOLDEN_ONLY", "") == "nvfp4":
         os.makedirs(GOLD, exist_ok=True)
         gen_nvfp4_fixture()
         gen_teacache_fixture()
+        gen_causvid_fixture()
         sys.exit(0)
     if os.environ.get("GOLDEN_ONLY", "") == "hunyuan_vae":
         install_shims()
@@ -413,6 +460,7 @@ if __name__ == "__main__":
         gen_hunyuan_vae_fixture()
         gen_nvfp4_fixture()
         gen_teacache_fixture()
+        gen_causvid_fixture()
         sys.exit(0)
     if os.environ.get("GOLDEN_ONLY", "") == "hunyuan":
         install_shims()
@@ -434,3 +482,4 @@ if __name__ == "__main__":
         gen_hunyuan_vae_fixture()
         gen_nvfp4_fixture()
         gen_teacache_fixture()
+        gen_causvid_fixture()

@@ -291,6 +291,65 @@ def infer_blocks(W, num_layers, x, embed0, grid_sizes, freqs, context, num_heads
 
 
 # ---------------------------------------------------------------------------------------------------------------
+# CausVid: autoregressive block variant with a self-attention KV cache (wan/infer/causvid/transformer_infer.py)
+# ---------------------------------------------------------------------------------------------------------------
+def compute_freqs_causvid(c: int, grid_sizes, freqs: torch.Tensor, start_frame: int = 0) -> torch.Tensor:
+    """utils.py:62-75 - like compute_freqs but the temporal rows start at `start_frame`."""
+    fs = freqs.split([c - 2 * (c // 3), c // 3, c // 3], dim=1)
+    f, h, w = [int(v) for v in grid_sizes]
+    return torch.cat(
+        [
+            fs[0][start_frame:start_frame + f].view(f, 1, 1, -1).expand(f, h, w, -1),
+            fs[1][:h].view(1, h, 1, -1).expand(f, h, w, -1),
+            fs[2][:w].view(1, 1, w, -1).expand(f, h, w, -1),
+        ],
+        dim=-1,
+    ).reshape(f * h * w, 1, -1)
+
+
+def infer_block_causvid(W, block_idx, x, embed0, grid_sizes, freqs, context, num_heads, kv_cache, kv_start, kv_end, attn="torch_sdpa"):
+    """WanTransformerInferCausVid.infer_block (t2v) - causvid/transformer_infer.py:205-220: self-attention :95-137 (q/k/v of the chunk,
+    RoPE at the chunk's frame offset, K/V appended to the cache at [kv_start, kv_end), attention of the chunk's queries against
+    cache[:kv_end]), cross-attention :139-190, FFN :192-199.  kv_cache: dict(k=[N, H, d], v=[N, H, d]) of this block, updated in place."""
+    pre = f"blocks.{block_idx}."
+    e = (W[pre + "modulation"] + embed0).chunk(6, dim=1)                                  # :211-212 (embed0.dim() == 2)
+    norm1_out = ln_apply(x)
+    norm1_out = (norm1_out * (1 + e[1]) + e[0]).squeeze(0)                                # :96-97
+    s, n = norm1_out.shape[0], num_heads
+    d = norm1_out.shape[1] // n
+    sa = pre + "self_attn."
+    q = rms_apply(mm_named(W, sa + "q", norm1_out), W[sa + "norm_q.weight"]).view(s, n, d)
+    k = rms_apply(mm_named(W, sa + "k", norm1_out), W[sa + "norm_k.weight"]).view(s, n, d)
+    v = mm_named(W, sa + "v", norm1_out).view(s, n, d)
+    f, h, w = [int(t) for t in grid_sizes]
+    freqs_i = compute_freqs_causvid(d // 2, grid_sizes, freqs, start_frame=kv_start // (h * w))   # :104
+    q, k = apply_rotary_emb(q, freqs_i), apply_rotary_emb(k, freqs_i)
+    kv_cache["k"][kv_start:kv_end] = k                                                    # :112-113
+    kv_cache["v"][kv_start:kv_end] = v
+    attn_out = attn_apply(q, kv_cache["k"][:kv_end], kv_cache["v"][:kv_end], attn)        # :118-127
+    x = x + mm_named(W, sa + "o", attn_out) * e[2].squeeze(0)                             # :133-135
+    # cross-attention (:139-190): identical maths to the base class, K/V of the prompt cached after the first chunk
+    ca = pre + "cross_attn."
+    norm3_out = ln_apply(x, W[pre + "norm3.weight"], W[pre + "norm3.bias"])
+    cq = rms_apply(mm_named(W, ca + "q", norm3_out), W[ca + "norm_q.weight"]).view(-1, n, d)
+    ck = rms_apply(mm_named(W, ca + "k", context), W[ca + "norm_k.weight"]).view(-1, n, d)
+    cv = mm_named(W, ca + "v", context).view(-1, n, d)
+    x = x + mm_named(W, ca + "o", attn_apply(cq, ck, cv, attn))
+    # FFN (:192-199)
+    norm2_out = ln_apply(x)
+    y = mm_named(W, pre + "ffn.0", norm2_out * (1 + e[4].squeeze(0)) + e[3].squeeze(0))
+    y = mm_named(W, pre + "ffn.2", F.gelu(y, approximate="tanh"))
+    return x + y * e[5].squeeze(0)
+
+
+def infer_blocks_causvid(W, num_layers, x, embed0, grid_sizes, freqs, context, num_heads, kv_caches, kv_start, kv_end, attn="torch_sdpa"):
+    """_infer_without_offload - causvid/transformer_infer.py:77-93."""
+    for i in range(num_layers):
+        x = infer_block_causvid(W, i, x, embed0, grid_sizes, freqs, context, num_heads, kv_caches[i], kv_start, kv_end, attn)
+    return x
+
+
+# ---------------------------------------------------------------------------------------------------------------
 # synthetic weights at checkpoint key names (SURVEY.md §8d recipe)
 # ---------------------------------------------------------------------------------------------------------------
 def synth_block_weights(num_layers: int, dim: int, ffn_dim: int, task: str = "t2v", seed: int = 42, device="cpu") -> Dict[str, torch.Tensor]:

@@ -175,3 +175,33 @@ def test_teacache_skips_blocks_and_reuses_the_cached_residual():
             else:
                 assert torch.equal(out, x + residual[cond])
     assert pattern == [True, True, False, False, False, False, True, True]       # ret_steps = 2, cutoff = 2 * 4 - 2
+
+
+def test_causvid_kv_cache_blocks_vs_reference_fixture(golden_dir):
+    """WanTransformerInferCausVid on the CUDA kernels (K/V projected straight into the cache, RoPE at the chunk's frame offset, FMHA with
+    sq != sk over the cache prefix) vs the fixture of the REAL reference class: three chunks, two blocks."""
+    from lightx2v_b200.host.wan_causvid import WanTransformerInferCausVid
+    from lightx2v_b200.host.wan_weights import WanTransformerWeights
+
+    T, meta = _load(os.path.join(golden_dir, "wan13b_causvid_2blocks.safetensors"))
+    dim, heads, ffn, L = int(meta["dim"]), int(meta["heads"]), int(meta["ffn"]), int(meta["layers"])
+    chunks, ft = int(meta["chunks"]), int(meta["frame_tokens"])
+    grid = torch.tensor([[int(v) for v in meta["grid"].split(",")]])
+    cfg = dict(task="t2v", num_layers=L, num_heads=heads, dim=dim, ffn_dim=ffn, mm_config={}, num_frames=chunks, num_frame_per_block=1, frame_seq_length=ft,
+               text_len=512)
+    W = O.synth_block_weights(L, dim, ffn, seed=int(meta["weights_seed"]))
+    weights = WanTransformerWeights(cfg)
+    weights.load({k: v.cuda() for k, v in W.items()})
+    infer = WanTransformerInferCausVid(cfg)
+    infer._init_kv_cache(torch.bfloat16, "cuda")
+    infer._init_crossattn_cache(torch.bfloat16, "cuda")
+    freqs = O.wan_freqs_table(dim // heads)
+    ctx = T["context"].cuda()
+    for c in range(chunks):
+        out = infer.infer(weights, grid, None, T[f"x_in.{c}"].cuda().clone(), T[f"embed0.{c}"].cuda(), torch.tensor([ft]), freqs, ctx, c * ft, (c + 1) * ft)
+        torch.cuda.synchronize()
+        frac, mx = _bad_frac(out, T[f"x_out.{c}"])
+        print(f"causvid chunk {c}: bad_frac={frac:.3e} max_abs_err={mx:.4f}")
+        assert frac < 2e-3 and mx < 0.13, (c, frac, mx)
+    fk, mk = _bad_frac(infer.kv_cache[0]["k"].reshape(chunks * ft, dim), T["k_cache.0"])
+    assert fk < 2e-3, (fk, mk)

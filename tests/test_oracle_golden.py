@@ -129,3 +129,21 @@ def test_nvfp4_oracle_matches_reference_fixture(golden_dir):
     assert sfa.reshape(-1)[off] == sa.to(torch.float8_e4m3fn).view(torch.uint8)[m, g]
     out = NV.scaled_fp4_mm(pa, pb, sfa, sfb, gs_a, gs_b, T["bias"])
     assert torch.allclose(out, T["out"], rtol=1e-5, atol=1e-4)
+
+
+def test_causvid_oracle_matches_reference_fixture(golden_dir):
+    """oracle.wan_oracle.infer_blocks_causvid vs the REAL WanTransformerInferCausVid: three chunks through two blocks with the KV cache
+    growing, bit for bit (outputs of every chunk and the final K cache of block 0)."""
+    torch.set_num_threads(8)
+    T, meta = _load(os.path.join(golden_dir, "wan13b_causvid_2blocks.safetensors"))
+    dim, heads, ffn, L = int(meta["dim"]), int(meta["heads"]), int(meta["ffn"]), int(meta["layers"])
+    chunks, ft = int(meta["chunks"]), int(meta["frame_tokens"])
+    grid = tuple(int(v) for v in meta["grid"].split(","))
+    W = O.synth_block_weights(L, dim, ffn, seed=int(meta["weights_seed"]))
+    freqs = O.wan_freqs_table(dim // heads)
+    caches = [{"k": torch.zeros(chunks * ft, heads, dim // heads, dtype=torch.bfloat16), "v": torch.zeros(chunks * ft, heads, dim // heads, dtype=torch.bfloat16)}
+              for _ in range(L)]
+    for c in range(chunks):
+        out = O.infer_blocks_causvid(W, L, T[f"x_in.{c}"].clone(), T[f"embed0.{c}"], grid, freqs, T["context"], heads, caches, c * ft, (c + 1) * ft)
+        assert torch.equal(out, T[f"x_out.{c}"]), c
+    assert torch.equal(caches[0]["k"].reshape(chunks * ft, dim), T["k_cache.0"])
