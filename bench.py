@@ -164,6 +164,9 @@ def run_ours(args):
         cfg["mm_config"] = {"mm_type": NVFP4_MM_KEY}
     if cfg.get("distill"):
         cfg["denoising_step_list"] = [1000, 750, 500, 250]
+    # per-op launch schedule from Python, so that every kernel launch is counted and the FMHA launches carry CUDA events for the roofline;
+    # the library's default (one native b200_wan_block_fwd call per block) issues the same kernels in the same order (tests/test_gpu_block.py)
+    cfg["b200_native_block"] = False
     S, flops_step = step_flops(cfg)
     W = synth_weights(cfg, dev)
     model = WanModel(cfg, W)
@@ -312,7 +315,7 @@ def run_ours(args):
             "vs_baseline": None, "dtype": "fp8-e4m3 linears, bf16 attention" if cfg.get("fp8") else ("nvfp4 (e2m1 + ue4m3/16) linears, bf16 attention" if cfg.get("nvfp4") else "bf16"),
             "data": "synthetic latents/prompt embeddings, random-init weights of the named shapes",
             "config": {"workload": args.workload, "tokens": S, "forwards_per_step": 2 if cfg["enable_cfg"] else 1, "blocks": cfg["num_layers"],
-                       "parallelism": (sp_mode if sp_mode.startswith("cfg2") else f"ulysses{world}") if world > 1 else "single", "sp_exchange": sp_mode, "l2": "activations (774 MB/tensor) and weights (28 GB) exceed the 126 MB L2",
+                       "parallelism": (sp_mode if sp_mode.startswith("cfg2") else f"ulysses{world}") if world > 1 else "single", "sp_exchange": sp_mode, "block_schedule": "per-op launches (instrumented)", "l2": "activations (774 MB/tensor) and weights (28 GB) exceed the 126 MB L2",
                        "scheduler": "step-distill 4-step (x0 re-noising)" if cfg.get("distill") else "UniPC order 2 (flow), 50-step sigma grid"},
             "achieved_tflops": round(flops_step / (ms_resident * 1e-3) / 1e12, 1),
             "model_tflop_per_step": round(flops_step / 1e12, 1),
