@@ -234,3 +234,43 @@ def test_block_driver_structs_match_header():
     import ctypes as C
     types = dict(lib.WanBlockArgsC._fields_)
     assert types["S"] is C.c_int64 and types["ctx_len"] is C.c_int64 and types["D"] is C.c_int and types["eps"] is C.c_float
+
+
+def test_argument_validation_of_the_newer_entry_points(built_lib):
+    """Same idea as test_argument_validation_without_gpu for the nvfp4, VAE and block-driver entry points: bad shapes / pointers are
+    rejected with a message before any CUDA call."""
+    C = ctypes
+    built_lib.b200_last_error.restype = C.c_char_p
+    q = built_lib.b200_quant_nvfp4
+    q.restype = C.c_int
+    q.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
+    assert q(16, 96, 4, 96, 16, 16, 48, 16, None) == -1                      # K % 64 != 0
+    assert b"multiple of 64" in built_lib.b200_last_error()
+    assert q(None, 64, 4, 64, 16, 16, 32, 16, None) == -1
+    g = built_lib.b200_gemm_nvfp4
+    g.restype = C.c_int
+    g.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64] + [C.c_void_p] * 4 + [C.c_int64, C.c_void_p, C.c_void_p] + [C.c_int64] * 3 + [C.c_int] * 3 + [C.c_void_p]
+    assert g(16, 32, 16, 32, 16, 16, None, 16, 64, None, None, 8, 64, 64, 0, 0, 0, None) == -1       # alpha missing
+    assert g(16, 32, 16, 32, 16, 16, 16, 16, 64, None, None, 8, 64, 100, 0, 0, 0, None) == -1        # K % 64 != 0
+    cv = built_lib.b200_conv3d_cl_padded
+    cv.restype = C.c_int
+    cv.argtypes = ([C.c_void_p] + [C.c_int64] * 3 + [C.c_int] * 3 + [C.c_void_p] * 3 + [C.c_int64] * 3 + [C.c_void_p] + [C.c_int64] * 3 + [C.c_int] * 6
+                   + [C.c_void_p, C.c_int, C.c_void_p])
+    taps = (C.c_int32 * 3)(0, 0, 0)
+    assert cv(16, 8, 8, 8, 4, 4, 4, 16, None, 16, 8, 8, 8, None, 0, 0, 0, 2, 2, 2, 48, 64, 1, C.cast(taps, C.c_void_p), 0, None) == -1   # cin % 32 != 0
+    assert b"multiple of 32" in built_lib.b200_last_error()
+    gs = built_lib.b200_gn_stats_cl
+    gs.restype = C.c_int
+    gs.argtypes = [C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_void_p]
+    assert gs(16, 0, 128, 16, None) == -1                                     # empty tensor
+    wb = built_lib.b200_wan_block_fwd
+    wb.restype = C.c_int
+    wb.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
+    from lightx2v_b200 import lib
+    w, a = lib.WanBlockWeightsC(), lib.WanBlockArgsC()
+    a.S, a.D, a.H, a.F, a.eps = 64, 1536, 11, 8960, 1e-6                      # D != 128 * H
+    assert wb(C.byref(w), C.byref(a), 16, 1 << 30, None) == -1
+    assert b"128" in built_lib.b200_last_error()
+    built_lib.b200_wan_block_workspace_bytes.restype = C.c_int64
+    built_lib.b200_wan_block_workspace_bytes.argtypes = [C.c_int64, C.c_int, C.c_int]
+    assert built_lib.b200_wan_block_workspace_bytes(75600, 5120, 13824) == 75600 * (5120 + 15360) * 2
