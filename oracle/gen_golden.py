@@ -436,23 +436,81 @@ def gen_causvid_fixture():
     print("wan13b_causvid_2blocks", [float(tensors[f"x_out.{c}"].float().abs().max()) for c in range(chunks)])
 
 
+def gen_prepost_fixture():
+    """Real WanPreInfer / WanPostInfer (wan/infer/pre_infer.py, post_infer.py) with the reference's own WanPreWeights / WanPostWeights on
+    seeded weights at Wan-1.3B width, latent [16, 3, 8, 12] (t2v) and the i2v variant (36 input channels, 257 CLIP tokens); `.cuda()` is
+    patched to the identity.  Pins oracle.wan_oracle.pre_infer / post_infer (A13)."""
+    from safetensors.torch import save_file
+
+    import lightx2v.common.ops  # noqa: F401
+    from lightx2v.models.networks.wan.infer.post_infer import WanPostInfer
+    from lightx2v.models.networks.wan.infer.pre_infer import WanPreInfer
+    from lightx2v.models.networks.wan.weights.post_weights import WanPostWeights
+    from lightx2v.models.networks.wan.weights.pre_weights import WanPreWeights
+
+    from oracle import wan_oracle as O
+
+    torch.Tensor.cuda = lambda self, *a, **k: self
+    dim, heads = 1536, 12
+    out = {}
+    for task in ("t2v", "i2v"):
+        cfg = ref_config(dim, heads, 8960, 1, task)
+        cfg.update(in_dim=36 if task == "i2v" else 16, model_cls="wan2.1")
+        W = O.synth_prepost_weights(dim, cfg["in_dim"], task, seed=13)
+        pre_w, post_w = WanPreWeights(cfg), WanPostWeights(cfg)
+        pre_w.load(W)
+        post_w.load(W)
+        g = torch.Generator().manual_seed(31)
+        latents = torch.randn(16, 3, 8, 12, generator=g).to(torch.bfloat16)
+        context = torch.randn(77, 4096, generator=g).to(torch.bfloat16)
+        timesteps = torch.tensor([999.0, 937.5, 612.25], dtype=torch.float32)
+        sched = types.SimpleNamespace(latents=latents, timesteps=timesteps, step_index=1, flag_df=False, seq_len=3 * 4 * 6)
+        inputs = {"text_encoder_output": {"context": [context], "context_null": [context]}, "image_encoder_output": None}
+        if task == "i2v":
+            inputs["image_encoder_output"] = {"clip_encoder_out": torch.randn(257, 1280, generator=g).to(torch.bfloat16),
+                                              "vae_encode_out": torch.randn(20, 3, 8, 12, generator=g).to(torch.bfloat16)}
+        pre, post = WanPreInfer(cfg), WanPostInfer(cfg)
+        pre.set_scheduler(sched)
+        post.set_scheduler(sched)
+        embed, grid_sizes, (x, embed0, seq_lens, freqs, ctx) = pre.infer(pre_w, inputs, True)
+        x_blocks = torch.randn(x.shape, generator=torch.Generator().manual_seed(37)).to(torch.bfloat16)       # stand-in for the block stack's output
+        noise = post.infer(post_w, x_blocks.clone(), embed, grid_sizes)[0]
+        t = {"latents": latents, "context": context, "timesteps": timesteps, "embed": embed, "x": x, "embed0": embed0, "context_out": ctx,
+             "x_blocks": x_blocks, "noise_pred": noise, "grid": grid_sizes[0]}
+        if task == "i2v":
+            t.update(inputs["image_encoder_output"])
+        out.update({f"{task}.{k}": v.contiguous() for k, v in t.items()})
+    save_file(out, os.path.join(GOLD, "wan13b_prepost.safetensors"),
+              metadata={"dim": str(dim), "weights_seed": "13", "step_index": "1", "generator": "oracle/gen_golden.py:gen_prepost_fixture",
+                        "reference": "ModelTC/lightx2v@0591c35e"})
+    print("wan13b_prepost", {k: tuple(v.shape) for k, v in out.items() if k.endswith((".x", ".context_out", ".noise_pred"))})
+
+
 if __name__ == "__main__":
+    if os.environ.get("GOLDEN_ONLY", "") == "prepost":
+        install_shims()
+        os.makedirs(GOLD, exist_ok=True)
+        gen_prepost_fixture()
+        sys.exit(0)
     if os.environ.get("GOLDEN_ONLY", "") == "causvid":
         install_shims()
         os.makedirs(GOLD, exist_ok=True)
         gen_causvid_fixture()
+        gen_prepost_fixture()
         sys.exit(0)
     if os.environ.get("GOLDEN_ONLY", "") == "teacache":
         install_shims()
         os.makedirs(GOLD, exist_ok=True)
         gen_teacache_fixture()
         gen_causvid_fixture()
+        gen_prepost_fixture()
         sys.exit(0)
     if os.environ.get("GOLDEN_ONLY", "") == "nvfp4":
         os.makedirs(GOLD, exist_ok=True)
         gen_nvfp4_fixture()
         gen_teacache_fixture()
         gen_causvid_fixture()
+        gen_prepost_fixture()
         sys.exit(0)
     if os.environ.get("GOLDEN_ONLY", "") == "hunyuan_vae":
         install_shims()
@@ -461,6 +519,7 @@ if __name__ == "__main__":
         gen_nvfp4_fixture()
         gen_teacache_fixture()
         gen_causvid_fixture()
+        gen_prepost_fixture()
         sys.exit(0)
     if os.environ.get("GOLDEN_ONLY", "") == "hunyuan":
         install_shims()
@@ -483,3 +542,4 @@ if __name__ == "__main__":
         gen_nvfp4_fixture()
         gen_teacache_fixture()
         gen_causvid_fixture()
+        gen_prepost_fixture()

@@ -291,6 +291,83 @@ def infer_blocks(W, num_layers, x, embed0, grid_sizes, freqs, context, num_heads
 
 
 # ---------------------------------------------------------------------------------------------------------------
+# pre-infer / post-infer (A13) and the CFG combine (A18)
+# ---------------------------------------------------------------------------------------------------------------
+def sinusoidal_embedding_1d(dim: int, position: torch.Tensor) -> torch.Tensor:
+    """utils.py:161-172 (BF16 mode)."""
+    half = dim // 2
+    position = position.type(torch.float64)
+    sinusoid = torch.outer(position, torch.pow(10000, -torch.arange(half).to(position).div(half)))
+    return torch.cat([torch.cos(sinusoid), torch.sin(sinusoid)], dim=1).to(torch.bfloat16)
+
+
+def pre_infer(W, latents, t, context, dim: int, freq_dim: int = 256, text_len: int = 512, clip_fea=None, vae_encode_out=None):
+    """WanPreInfer.infer - pre_infer.py:29-120 (no diffusion forcing, no dynamic cfg, seq_len == token count).
+    latents [C, F, H, W] bf16; t [1]; context [L <= 512, 4096].  Returns embed [1, D], grid (F, H/2, W/2), x [S, D], embed0 [6, D], context'."""
+    x = latents
+    if vae_encode_out is not None:
+        x = torch.cat([x, vae_encode_out.to(x.dtype)], dim=0)                                         # :52-53
+    u = F.conv3d(x.unsqueeze(0), W["patch_embedding.weight"], W["patch_embedding.bias"], stride=(1, 2, 2))   # :56
+    grid = tuple(int(v) for v in u.shape[2:])
+    xs = u.flatten(2).transpose(1, 2)[0]
+    embed = sinusoidal_embedding_1d(freq_dim, t.flatten())
+    embed = mm_named(W, "time_embedding.0", embed)
+    embed = mm_named(W, "time_embedding.2", F.silu(embed))
+    embed0 = mm_named(W, "time_projection.1", F.silu(embed)).unflatten(1, (6, dim)).squeeze(0)       # :75-78
+    ctx = torch.cat([context, context.new_zeros(text_len - context.size(0), context.size(1))])       # :90
+    ctx = mm_named(W, "text_embedding.2", F.gelu(mm_named(W, "text_embedding.0", ctx), approximate="tanh"))
+    if clip_fea is not None:                                                                         # :100-111
+        c = ln_apply(clip_fea, W["img_emb.proj.0.weight"], W["img_emb.proj.0.bias"], 1e-6)
+        c = F.gelu(mm_named(W, "img_emb.proj.1", c), approximate="none")
+        c = ln_apply(mm_named(W, "img_emb.proj.3", c), W["img_emb.proj.4.weight"], W["img_emb.proj.4.bias"], 1e-6)
+        ctx = torch.cat([c, ctx], dim=0)
+    return embed, grid, xs, embed0, ctx
+
+
+def post_infer(W, x, e, grid, out_dim: int = 16):
+    """WanPostInfer.infer - post_infer.py:15-50 (BF16 mode)."""
+    e0, e1 = (W["head.modulation"] + e.unsqueeze(1)).chunk(2, dim=1)
+    x = ln_apply(x)
+    x = x.mul_(1 + e1.squeeze(0)).add_(e0.squeeze(0))
+    x = mm_named(W, "head.head", x)
+    f, h, w = grid
+    u = x[: f * h * w].view(f, h, w, 1, 2, 2, out_dim)
+    u = torch.einsum("fhwpqrc->cfphqwr", u)
+    return u.reshape(out_dim, f, h * 2, w * 2).float()
+
+
+def cfg_combine(cond, uncond, scale: float):
+    """WanModel.infer - wan/model.py:216-218."""
+    return uncond + scale * (cond - uncond)
+
+
+def synth_prepost_weights(dim: int, in_dim: int = 16, task: str = "t2v", seed: int = 13, device="cpu") -> Dict[str, torch.Tensor]:
+    g = torch.Generator().manual_seed(seed)
+    W: Dict[str, torch.Tensor] = {}
+
+    def lin(name, n, k, scale=None):
+        W[name + ".weight"] = (torch.randn(n, k, generator=g) * (scale or k ** -0.5)).to(torch.bfloat16).to(device)
+        W[name + ".bias"] = (torch.randn(n, generator=g) * 0.02).to(torch.bfloat16).to(device)
+
+    W["patch_embedding.weight"] = (torch.randn(dim, in_dim, 1, 2, 2, generator=g) * (in_dim * 4) ** -0.5).to(torch.bfloat16).to(device)
+    W["patch_embedding.bias"] = (torch.randn(dim, generator=g) * 0.02).to(torch.bfloat16).to(device)
+    lin("text_embedding.0", dim, 4096)
+    lin("text_embedding.2", dim, dim)
+    lin("time_embedding.0", dim, 256)
+    lin("time_embedding.2", dim, dim)
+    lin("time_projection.1", 6 * dim, dim)
+    lin("head.head", 64, dim)
+    W["head.modulation"] = (torch.randn(1, 2, dim, generator=g) * 0.1).to(torch.bfloat16).to(device)
+    if task == "i2v":
+        for n, c in (("img_emb.proj.0", 1280), ("img_emb.proj.4", dim)):
+            W[n + ".weight"] = (1 + 0.05 * torch.randn(c, generator=g)).to(torch.bfloat16).to(device)
+            W[n + ".bias"] = (0.02 * torch.randn(c, generator=g)).to(torch.bfloat16).to(device)
+        lin("img_emb.proj.1", 1280, 1280)
+        lin("img_emb.proj.3", dim, 1280)
+    return W
+
+
+# ---------------------------------------------------------------------------------------------------------------
 # CausVid: autoregressive block variant with a self-attention KV cache (wan/infer/causvid/transformer_infer.py)
 # ---------------------------------------------------------------------------------------------------------------
 def compute_freqs_causvid(c: int, grid_sizes, freqs: torch.Tensor, start_frame: int = 0) -> torch.Tensor:

@@ -147,3 +147,20 @@ def test_causvid_oracle_matches_reference_fixture(golden_dir):
         out = O.infer_blocks_causvid(W, L, T[f"x_in.{c}"].clone(), T[f"embed0.{c}"], grid, freqs, T["context"], heads, caches, c * ft, (c + 1) * ft)
         assert torch.equal(out, T[f"x_out.{c}"]), c
     assert torch.equal(caches[0]["k"].reshape(chunks * ft, dim), T["k_cache.0"])
+
+
+@pytest.mark.parametrize("task", ["t2v", "i2v"])
+def test_prepost_oracle_matches_reference_fixture(golden_dir, task):
+    """oracle.wan_oracle.pre_infer / post_infer vs the REAL WanPreInfer / WanPostInfer (A13), bit for bit."""
+    torch.set_num_threads(8)
+    T, meta = _load(os.path.join(golden_dir, "wan13b_prepost.safetensors"))
+    dim = int(meta["dim"])
+    g = lambda k: T[f"{task}.{k}"]       # noqa: E731
+    W = O.synth_prepost_weights(dim, 36 if task == "i2v" else 16, task, seed=int(meta["weights_seed"]))
+    t = g("timesteps")[int(meta["step_index"])].reshape(1)
+    extra = dict(clip_fea=g("clip_encoder_out"), vae_encode_out=g("vae_encode_out")) if task == "i2v" else {}
+    embed, grid, x, embed0, ctx = O.pre_infer(W, g("latents"), t, g("context"), dim, **extra)
+    assert grid == tuple(int(v) for v in g("grid"))
+    assert torch.equal(embed, g("embed")) and torch.equal(x, g("x")) and torch.equal(embed0, g("embed0")) and torch.equal(ctx, g("context_out"))
+    noise = O.post_infer(W, g("x_blocks").clone(), embed, grid)
+    assert torch.equal(noise, g("noise_pred"))
