@@ -38,7 +38,7 @@ class WanTransformerInferCausVid(WanTransformerInfer):
         """Kept for interface parity (:32-45): the prompt K/V cache of the base class is keyed on the context tensor and needs no allocation."""
         self.crossattn_cache = [{"is_init": False} for _ in range(self.blocks_num)]
         for c in self._caches.values():
-            c.ctx_key = None
+            c.kv.clear()
 
     def infer(self, weights, grid_sizes, embed, x, embed0, seq_lens, freqs, context, kv_start, kv_end):
         if self.kv_cache is None:

@@ -50,14 +50,13 @@ def rope_cos_sin(grid_sizes, freqs: torch.Tensor, head_dim: int, rows: Optional[
 class _BlockCache:
     """Per-block derived tensors: concatenated QKV weight/bias, cached cross-attention text K/V."""
 
-    __slots__ = ("wqkv", "bqkv", "sqkv", "ctx_key", "ck", "cv", "ck_img", "cv_img", "native", "keep")
+    __slots__ = ("wqkv", "bqkv", "sqkv", "kv", "native", "keep")
 
     def __init__(self):
         self.wqkv = None
         self.bqkv = None
         self.sqkv = None
-        self.ctx_key = None
-        self.ck = self.cv = self.ck_img = self.cv_img = None
+        self.kv = {}              # id(context tensor) -> (context tensor, its _version, ck, cv, ck_img, cv_img); see _context_kv
         self.native = None        # lib.WanBlockWeightsC + the tensors it points to
         self.keep = None
 
@@ -127,12 +126,12 @@ class WanTransformerInfer:
                           b0=ff.ffn_0.bias, w2=self._nk(ff.ffn_2), b2=ff.ffn_2.bias)
             c.native = lib.wan_block_weights(**c.keep)
         cc = self._cache(ca)
-        self._context_kv(ca, context, cc)
+        ck, cv, ck_img, cv_img = self._context_kv(ca, context, cc)
         F_ = c.keep["w0"].shape[0]
         ws = self._buf("native_ws", (lib.wan_block_workspace_bytes(S, D, F_) // 2,), dev)
         cs = self._rope_table(grid_sizes, freqs, S, dev)
-        img = dict(img_k=cc.ck_img.reshape(-1, D), img_v=cc.cv_img.reshape(-1, D)) if self.task == "i2v" else {}
-        return lib.wan_block_fwd(c.native, x, tuple(m.contiguous() for m in mods), cs, min(S, cs.shape[0]), cc.ck.reshape(-1, D), cc.cv.reshape(-1, D), ws,
+        img = dict(img_k=ck_img.reshape(-1, D), img_v=cv_img.reshape(-1, D)) if self.task == "i2v" else {}
+        return lib.wan_block_fwd(c.native, x, tuple(m.contiguous() for m in mods), cs, min(S, cs.shape[0]), ck.reshape(-1, D), cv.reshape(-1, D), ws,
                                  self.num_heads, F_, eps=sa.self_attn_norm_q.eps, **img)
 
     def infer_modulation(self, weights, embed0):
@@ -271,9 +270,13 @@ class WanTransformerInfer:
         return x
 
     def _context_kv(self, weights, context, c: _BlockCache):
-        key = (context.data_ptr(), context._version, tuple(context.shape))
-        if self.cache_cross_kv and c.ctx_key == key:
-            return
+        """Text (and CLIP) K/V of this block for `context`, computed once per context tensor (the reference recomputes them
+        in every block of every step, transformer_infer.py:418-420).  The cache is keyed on the tensor OBJECT and keeps a reference to it, so
+        a freed-and-reallocated buffer at the same address can never alias an entry; an in-place update bumps `_version` and invalidates it.
+        Up to four contexts per block stay cached (cond / uncond alternate inside one step)."""
+        ent = c.kv.get(id(context)) if self.cache_cross_kv else None
+        if ent is not None and ent[0] is context and ent[1] == context._version:
+            return ent[2:]
         H, d = self.num_heads, self.head_dim
         if self.task == "i2v":
             context_img, ctx = context[:257], context[257:]
@@ -282,13 +285,17 @@ class WanTransformerInfer:
         ck = self._linear(weights.cross_attn_k, ctx.contiguous(), qname="ctx8")
         lib.rms_rope_(ck, weights.cross_attn_norm_k.weight, eps=weights.cross_attn_norm_k.eps)
         cv = self._linear(weights.cross_attn_v, ctx.contiguous(), qname="ctx8")
-        c.ck, c.cv = ck.view(-1, H, d), cv.view(-1, H, d)
+        out = [ck.view(-1, H, d), cv.view(-1, H, d), None, None]
         if context_img is not None:
             ki = self._linear(weights.cross_attn_k_img, context_img.contiguous(), qname="img8")
             lib.rms_rope_(ki, weights.cross_attn_norm_k_img.weight, eps=weights.cross_attn_norm_k_img.eps)
             vi = self._linear(weights.cross_attn_v_img, context_img.contiguous(), qname="img8")
-            c.ck_img, c.cv_img = ki.view(-1, H, d), vi.view(-1, H, d)
-        c.ctx_key = key
+            out[2], out[3] = ki.view(-1, H, d), vi.view(-1, H, d)
+        if self.cache_cross_kv:
+            if len(c.kv) >= 4:
+                c.kv.pop(next(iter(c.kv)))
+            c.kv[id(context)] = (context, context._version, *out)
+        return tuple(out)
 
     def infer_cross_attn(self, weights, x, context, y_out, gate_msa):
         """transformer_infer.py:398-465.  If y_out is given the gated residual `x += y_out * gate_msa` (:402) is applied
@@ -305,11 +312,11 @@ class WanTransformerInfer:
         cq = self._buf("b", (S, D), dev)
         self._linear(weights.cross_attn_q, n3, out=cq)
         lib.rms_rope_(cq, weights.cross_attn_norm_q.weight, eps=weights.cross_attn_norm_q.eps)
-        self._context_kv(weights, context, c)
+        ck, cv, ck_img, cv_img = self._context_kv(weights, context, c)
         attn = self._buf("a", (S, D), dev).view(S, H, d)
-        lib.fmha(cq.view(S, H, d), c.ck, c.cv, out=attn)
+        lib.fmha(cq.view(S, H, d), ck, cv, out=attn)
         if self.task == "i2v":
-            img = lib.fmha(cq.view(S, H, d), c.ck_img, c.cv_img, out=self._buf("c", (S, H, d), dev))
+            img = lib.fmha(cq.view(S, H, d), ck_img, cv_img, out=self._buf("c", (S, H, d), dev))
             attn.add_(img)                                                      # :454 (two softmaxes, summed in bf16)
         self._linear(weights.cross_attn_o, attn.reshape(S, D), out=x, epilogue=lib.EPI_RESIDUAL)
         return x, None

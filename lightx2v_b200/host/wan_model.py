@@ -46,25 +46,52 @@ class WanPreInfer:
         self.text_len = config["text_len"]
         self.scheduler = None
         self._t_table = None
+        self._ctx_cache = {}
 
     def set_scheduler(self, scheduler):
         self.scheduler = scheduler
         self._t_table = None
+
+    def _embed_context(self, W, context, clip_fea):
+        """Text MLP (+ CLIP MLP for i2v) of pre_infer.py:89-111.  The prompt embeddings do not change between denoise steps, so the result is
+        computed once per (context, clip) tensor pair and the SAME tensor object is handed to the blocks every step - which is what lets
+        their per-context K/V caches hit.  Entries hold references to their inputs (no address aliasing) and check `_version`."""
+        key = (id(context), None if clip_fea is None else id(clip_fea))
+        ent = self._ctx_cache.get(key)
+        if ent is not None and ent[0] is context and ent[1] == context._version and ent[2] is clip_fea and (clip_fea is None or ent[3] == clip_fea._version):
+            return ent[4]
+        ctx = context
+        if ctx.shape[0] < self.text_len:
+            ctx = torch.cat([ctx, ctx.new_zeros(self.text_len - ctx.shape[0], ctx.shape[1])])
+        out = lib.gemm_bf16(ctx.contiguous(), W["text_embedding.0.weight"], W["text_embedding.0.bias"], epilogue=lib.EPI_BIAS_GELU)
+        res = lib.gemm_bf16(out, W["text_embedding.2.weight"], W["text_embedding.2.bias"])
+        if clip_fea is not None:
+            c = lib.ln_modulate(clip_fea.contiguous(), weight=W["img_emb.proj.0.weight"], bias=W["img_emb.proj.0.bias"], eps=1e-6)
+            c = lib.gemm_bf16(c, W["img_emb.proj.1.weight"], W["img_emb.proj.1.bias"])
+            c = F.gelu(c, approximate="none")
+            c = lib.gemm_bf16(c, W["img_emb.proj.3.weight"], W["img_emb.proj.3.bias"])
+            c = lib.ln_modulate(c, weight=W["img_emb.proj.4.weight"], bias=W["img_emb.proj.4.bias"], eps=1e-6)
+            res = torch.cat([c, res], dim=0)
+        if len(self._ctx_cache) >= 4:
+            self._ctx_cache.pop(next(iter(self._ctx_cache)))
+        self._ctx_cache[key] = (context, context._version, clip_fea, None if clip_fea is None else clip_fea._version, res)
+        return res
 
     def _t_embedding(self, device) -> torch.Tensor:
         """Sinusoidal embedding of the current timestep (pre_infer.py:56-58).  The fp64 table for ALL timesteps of the schedule is built
         once on the host (same element-wise math as the per-step call of the reference) and indexed on the device afterwards, so a
         denoise step has no device->host synchronisation."""
         ts = self.scheduler.timesteps
-        key = (ts.data_ptr(), ts._version, tuple(ts.shape))
-        if self._t_table is None or self._t_table[0] != key:
-            self._t_table = (key, sinusoidal_embedding_1d(self.freq_dim, ts.flatten().cpu()).to(device))
+        if self._t_table is None or self._t_table[0] is not ts or self._t_table[1] != ts._version:      # keyed on the tensor object (kept alive here)
+            self._t_table = (ts, ts._version, sinusoidal_embedding_1d(self.freq_dim, ts.flatten().cpu()).to(device))
         i = self.scheduler.step_index
-        return self._t_table[1][i:i + 1]
+        return self._t_table[2][i:i + 1]
 
     def infer(self, W: Dict[str, torch.Tensor], inputs, positive: bool):
         x = self.scheduler.latents                                       # [C, F, H, W] (bf16 after step_pre)
         context = inputs["text_encoder_output"]["context" if positive else "context_null"]
+        if isinstance(context, (list, tuple)):                           # the reference passes a one-element list (pre_infer.py:90 stacks it)
+            context = context[0]
         if self.task == "i2v":
             clip_fea = inputs["image_encoder_output"]["clip_encoder_out"]
             x = torch.cat([x, inputs["image_encoder_output"]["vae_encode_out"].to(x.dtype)], dim=0)
@@ -83,18 +110,7 @@ class WanPreInfer:
         embed = lib.gemm_bf16(embed, W["time_embedding.2.weight"], W["time_embedding.2.bias"])
         embed0 = lib.gemm_bf16(F.silu(embed), W["time_projection.1.weight"], W["time_projection.1.bias"]).unflatten(1, (6, self.dim))
 
-        ctx = context
-        if ctx.shape[0] < self.text_len:
-            ctx = torch.cat([ctx, ctx.new_zeros(self.text_len - ctx.shape[0], ctx.shape[1])])
-        out = lib.gemm_bf16(ctx.contiguous(), W["text_embedding.0.weight"], W["text_embedding.0.bias"], epilogue=lib.EPI_BIAS_GELU)
-        context = lib.gemm_bf16(out, W["text_embedding.2.weight"], W["text_embedding.2.bias"])
-        if self.task == "i2v":
-            c = lib.ln_modulate(clip_fea.contiguous(), weight=W["img_emb.proj.0.weight"], bias=W["img_emb.proj.0.bias"], eps=1e-6)
-            c = lib.gemm_bf16(c, W["img_emb.proj.1.weight"], W["img_emb.proj.1.bias"])
-            c = F.gelu(c, approximate="none")
-            c = lib.gemm_bf16(c, W["img_emb.proj.3.weight"], W["img_emb.proj.3.bias"])
-            c = lib.ln_modulate(c, weight=W["img_emb.proj.4.weight"], bias=W["img_emb.proj.4.bias"], eps=1e-6)
-            context = torch.cat([c, context], dim=0)
+        context = self._embed_context(W, context, clip_fea if self.task == "i2v" else None)
         return embed, grid_sizes, (xs, embed0.squeeze(0), seq_lens, self.freqs, context)
 
 
