@@ -156,6 +156,6 @@ class WanStepDistillScheduler(WanScheduler):
         x0 = self.latents.to(torch.float32) - sigma * v
         if self.step_index < self.infer_steps - 1:
             s1 = self.sigmas[self.step_index + 1].item()
-            noise = torch.randn(x0.shape, dtype=x0.dtype, device=x0.device, generator=self.generator)
+            noise = torch.randn_like(x0)                 # the reference draws from the device's DEFAULT generator here (:53), not the seeded one
             x0 = ((1 - s1) * x0 + s1 * noise).type_as(noise)
         self.latents = x0.to(self.latents.dtype)

@@ -486,7 +486,38 @@ def gen_prepost_fixture():
     print("wan13b_prepost", {k: tuple(v.shape) for k, v in out.items() if k.endswith((".x", ".context_out", ".noise_pred"))})
 
 
+def gen_distill_scheduler_fixture():
+    """Real WanStepDistillScheduler (schedulers/wan/step_distill/scheduler.py) for its 4 steps on CPU with seeded pseudo model outputs; the
+    re-noising draws from the default generator (:53), so the global seed is set before every step_post and recorded."""
+    from safetensors.torch import save_file
+
+    from lightx2v.models.schedulers.wan.step_distill.scheduler import WanStepDistillScheduler
+
+    cfg = Cfg(infer_steps=4, target_video_length=17, sample_shift=5.0, seed=42, task="t2v", target_shape=(16, 3, 8, 8), patch_size=(1, 2, 2),
+              denoising_step_list=[1000, 750, 500, 250])
+    sch = WanStepDistillScheduler(cfg)
+    sch.device = torch.device("cpu")
+    sch.prepare(None)
+    g = torch.Generator().manual_seed(19)
+    tensors = {"latents_0": sch.latents.clone(), "timesteps": sch.timesteps.clone(), "sigmas": sch.sigmas.clone()}
+    for i in range(4):
+        sch.step_pre(i)
+        sch.noise_pred = torch.randn(sch.latents.shape, generator=g)
+        tensors[f"noise_pred_{i}"] = sch.noise_pred.clone()
+        torch.manual_seed(1000 + i)
+        sch.step_post()
+        tensors[f"latents_post_{i}"] = sch.latents.clone()
+    save_file({k: v.contiguous() for k, v in tensors.items()}, os.path.join(GOLD, "wan_scheduler_step_distill.safetensors"),
+              metadata={"sample_shift": "5.0", "seed": "42", "step_seed_base": "1000", "generator": "oracle/gen_golden.py:gen_distill_scheduler_fixture"})
+    print("wan_scheduler_step_distill", sch.timesteps.tolist(), sch.sigmas.tolist())
+
+
 if __name__ == "__main__":
+    if os.environ.get("GOLDEN_ONLY", "") == "distill":
+        install_shims()
+        os.makedirs(GOLD, exist_ok=True)
+        gen_distill_scheduler_fixture()
+        sys.exit(0)
     if os.environ.get("GOLDEN_ONLY", "") == "prepost":
         install_shims()
         os.makedirs(GOLD, exist_ok=True)
@@ -536,6 +567,7 @@ if __name__ == "__main__":
     else:
         main()
         gen_scheduler_fixture()
+        gen_distill_scheduler_fixture()
         gen_vae_fixture()
         gen_hunyuan_fixture()
         gen_hunyuan_vae_fixture()

@@ -274,3 +274,27 @@ def test_argument_validation_of_the_newer_entry_points(built_lib):
     built_lib.b200_wan_block_workspace_bytes.restype = C.c_int64
     built_lib.b200_wan_block_workspace_bytes.argtypes = [C.c_int64, C.c_int, C.c_int]
     assert built_lib.b200_wan_block_workspace_bytes(75600, 5120, 13824) == 75600 * (5120 + 15360) * 2
+
+
+def test_step_distill_scheduler_matches_reference_fixture(golden_dir):
+    """host/wan_scheduler.py:WanStepDistillScheduler vs the REAL class (4-step sampler of BASELINE config 3): sigma / timestep grid, x0
+    prediction and the re-noising from the default generator, bit for bit."""
+    from safetensors import safe_open
+
+    from lightx2v_b200.host.wan_scheduler import WanStepDistillScheduler
+
+    with safe_open(os.path.join(golden_dir, "wan_scheduler_step_distill.safetensors"), framework="pt") as f:
+        T = {k: f.get_tensor(k) for k in f.keys()}
+        meta = f.metadata()
+    cfg = dict(infer_steps=4, sample_shift=5.0, seed=42, target_shape=(16, 3, 8, 8), patch_size=(1, 2, 2), denoising_step_list=[1000, 750, 500, 250])
+    sch = WanStepDistillScheduler(cfg, device="cpu")
+    sch.prepare()
+    assert torch.equal(sch.latents, T["latents_0"])
+    assert torch.equal(sch.timesteps, T["timesteps"]) and torch.equal(sch.sigmas, T["sigmas"])
+    for i in range(4):
+        sch.step_pre(i)
+        sch.noise_pred = T[f"noise_pred_{i}"]
+        torch.manual_seed(int(meta["step_seed_base"]) + i)
+        sch.step_post()
+        assert sch.latents.dtype == T[f"latents_post_{i}"].dtype
+        assert torch.equal(sch.latents, T[f"latents_post_{i}"]), i
