@@ -32,6 +32,17 @@ const char* b200_last_error(void);
 int b200_version(void);
 int b200_num_sms(void);
 
+/* Number of kernel launches this library has issued in this process so far (all entry points, incl. the ones issued below
+ * b200_wan_block_fwd).  bench.py reports the difference over its timed region as `gpu_launches`. */
+int64_t b200_launch_count(void);
+
+/* Attention launch profiler for bench.py's roofline: after b200_prof_fmha_begin(capacity) every b200_fmha_fwd_* launch (also the ones
+ * issued inside b200_wan_block_fwd) is bracketed by a CUDA event pair on ITS stream, up to `capacity` launches.
+ * b200_prof_fmha_end waits for them, writes ms[i] and meta[4 i + {0,1,2,3}] = {sq, sk, heads, head_dim} for the first `capacity`
+ * launches, disables the profiler and returns the number written.  Off by default (no events, no overhead). */
+int b200_prof_fmha_begin(int capacity);
+int b200_prof_fmha_end(float* ms, int64_t* meta, int capacity);
+
 /* GEMM epilogues (fusions of the elementwise passes that follow each linear in WanTransformerInfer). */
 #define B200_EPI_BIAS 0          /* C = bf16(A B^T + bias)                         mm_weight.py:81-88            */
 #define B200_EPI_BIAS_GELU 1     /* C = gelu_tanh(bf16(A B^T + bias))              + transformer_infer.py:492     */
@@ -66,6 +77,11 @@ int b200_rms_rope(void* x0, int64_t ld0, const void* w0, void* x1, int64_t ld1, 
 int b200_fmha_fwd_d128(const void* q, int64_t q_stride_s, const void* k, int64_t k_stride_s, const void* v,
                        int64_t v_stride_s, void* out, int64_t o_stride_s, int64_t sq, int64_t sk, int heads,
                        float softmax_scale, b200_stream_t stream);
+
+/* Same kernel instantiated for head_dim 64: q/k/v/out [rows, H, 64].  CogVideoX's joint text+video attention (48 heads x 64,
+ * lightx2v/models/networks/cogvideox/infer/transformer_infer.py:118-132: F.scaled_dot_product_attention over [text ; video] tokens). */
+int b200_fmha_fwd_d64(const void* q, int64_t q_stride_s, const void* k, int64_t k_stride_s, const void* v, int64_t v_stride_s,
+                      void* out, int64_t o_stride_s, int64_t sq, int64_t sk, int heads, float softmax_scale, b200_stream_t stream);
 
 /* ---- w8a8-fp8 path (BASELINE config 3) ------------------------------------------------------------------------------- */
 
@@ -107,7 +123,8 @@ int b200_rms_rope_scatter(const void* qkv, int64_t ld, const void* wq, const voi
                           int64_t rows_per_rank, b200_stream_t stream);
 
 /* b200_fmha_fwd_d128 whose epilogue scatters each query row to the rank that owns the token: row r -> peers[r / rows_per_rank]
- * at [(r % rows_per_rank), head_offset + head, :] with row stride peer_stride_s.  Replaces the attention + all2all_head2seq of
+ * at [(r % rows_per_rank), head_offset + head, :] with row stride peer_stride_s.  world <= 8 (one NVSwitch domain of a B200 box; the
+ * kernel parameter block carries 8 peer pointers).  Replaces the attention + all2all_head2seq of
  * ulysses_attn (attn.py:51-88, all2all.py:48-89). */
 int b200_fmha_fwd_d128_scatter(const void* q, int64_t q_stride_s, const void* k, int64_t k_stride_s, const void* v,
                                int64_t v_stride_s, void* const* peers, int world, int64_t rows_per_rank, int64_t peer_stride_s,

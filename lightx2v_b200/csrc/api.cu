@@ -15,6 +15,10 @@ int rms_rope(void* x0, long long ld0, const void* w0, void* x1, long long ld1, c
 int fmha_fwd_d128(const void* q, long long q_stride_s, const void* k, long long k_stride_s, const void* v,
                   long long v_stride_s, void* out, long long o_stride_s, long long sq, long long sk, int heads,
                   float softmax_scale, cudaStream_t stream);
+int fmha_fwd_d64(const void* q, long long q_stride_s, const void* k, long long k_stride_s, const void* v, long long v_stride_s, void* out,
+                 long long o_stride_s, long long sq, long long sk, int heads, float softmax_scale, cudaStream_t stream);
+int prof_fmha_begin(int capacity);
+int prof_fmha_end(float* ms, long long* meta, int capacity);
 int gemm_fp8(const void* A, long long lda, const void* B, long long ldb, void* C, long long ldc, const float* scale_a,
              const float* scale_b, const void* bias, const void* gate, long long M, long long N, long long K,
              int epilogue, int block_n, int max_ctas, cudaStream_t stream);
@@ -57,6 +61,12 @@ extern "C" {
 const char* b200_last_error(void) { return b200::last_error(); }
 int b200_version(void) { return 100; }
 int b200_num_sms(void) { return b200::num_sms(); }
+int64_t b200_launch_count(void) { return b200::launch_count(); }
+int b200_prof_fmha_begin(int capacity) { return b200::prof_fmha_begin(capacity); }
+int b200_prof_fmha_end(float* ms, int64_t* meta, int capacity) {
+  static_assert(sizeof(long long) == sizeof(int64_t), "int64_t is long long on this ABI");
+  return b200::prof_fmha_end(ms, reinterpret_cast<long long*>(meta), capacity);
+}
 
 int b200_gemm_bf16(const void* A, int64_t lda, const void* B, int64_t ldb, void* C, int64_t ldc, const void* bias,
                    const void* gate, int64_t M, int64_t N, int64_t K, int epilogue, int block_n, int max_ctas,
@@ -82,6 +92,12 @@ int b200_fmha_fwd_d128(const void* q, int64_t q_stride_s, const void* k, int64_t
                        float softmax_scale, b200_stream_t stream) {
   return b200::fmha_fwd_d128(q, q_stride_s, k, k_stride_s, v, v_stride_s, out, o_stride_s, sq, sk, heads,
                              softmax_scale, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int b200_fmha_fwd_d64(const void* q, int64_t q_stride_s, const void* k, int64_t k_stride_s, const void* v, int64_t v_stride_s,
+                      void* out, int64_t o_stride_s, int64_t sq, int64_t sk, int heads, float softmax_scale, b200_stream_t stream) {
+  return b200::fmha_fwd_d64(q, q_stride_s, k, k_stride_s, v, v_stride_s, out, o_stride_s, sq, sk, heads, softmax_scale,
+                            reinterpret_cast<cudaStream_t>(stream));
 }
 
 int b200_gemm_fp8(const void* A, int64_t lda, const void* B, int64_t ldb, void* C, int64_t ldc, const float* a_scale,

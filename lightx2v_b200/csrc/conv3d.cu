@@ -323,7 +323,7 @@ static int launch_conv(const CUtensorMap& tmIn, const CUtensorMap& tmW, const CU
   }
   const long long num_tiles = (long long)p.T * p.tiles_w * p.tiles_h * p.num_n_blocks;
   const int grid = (int)(num_tiles < num_sms() ? num_tiles : num_sms());
-  kern<<<grid, CONV_THREADS, Cfg::kSmemBytes, stream>>>(tmIn, tmW, tmOut, p);
+  kern<<<grid, CONV_THREADS, Cfg::kSmemBytes, stream>>>(tmIn, tmW, tmOut, p); note_launch();
   B200_CHECK_CUDA(cudaGetLastError());
   return B200_OK;
 }

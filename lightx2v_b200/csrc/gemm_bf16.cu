@@ -373,7 +373,7 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUt
   }
   const int num_tiles = p.num_m_blocks * p.num_n_blocks;
   int grid = num_tiles < max_ctas ? num_tiles : max_ctas;
-  kern<<<grid, GEMM_THREADS, Cfg::kSmemBytes, stream>>>(tmA, tmB, tmC, tmSFA, tmSFB, p);
+  kern<<<grid, GEMM_THREADS, Cfg::kSmemBytes, stream>>>(tmA, tmB, tmC, tmSFA, tmSFB, p); note_launch();
   B200_CHECK_CUDA(cudaGetLastError());
   return B200_OK;
 }

@@ -119,15 +119,15 @@ int gn_stats_cl(const void* x, long long voxels, int C, double* sums, cudaStream
   const int blocks = (int)(passes < max_blocks ? passes : max_blocks);
   float* partials = reinterpret_cast<float*>(sums + 2 * GN_GROUPS);
   switch (C) {
-    case 64: gn_stats_kernel<64><<<blocks, 256, 0, stream>>>(xp, voxels, partials); break;
-    case 128: gn_stats_kernel<128><<<blocks, 256, 0, stream>>>(xp, voxels, partials); break;
-    case 256: gn_stats_kernel<256><<<blocks, 256, 0, stream>>>(xp, voxels, partials); break;
-    case 512: gn_stats_kernel<512><<<blocks, 256, 0, stream>>>(xp, voxels, partials); break;
+    case 64: gn_stats_kernel<64><<<blocks, 256, 0, stream>>>(xp, voxels, partials); note_launch(); break;
+    case 128: gn_stats_kernel<128><<<blocks, 256, 0, stream>>>(xp, voxels, partials); note_launch(); break;
+    case 256: gn_stats_kernel<256><<<blocks, 256, 0, stream>>>(xp, voxels, partials); note_launch(); break;
+    case 512: gn_stats_kernel<512><<<blocks, 256, 0, stream>>>(xp, voxels, partials); note_launch(); break;
     default:
       set_last_error("b200_gn_stats_cl: unsupported channel count %d (64 / 128 / 256 / 512)", C);
       return B200_ERR_UNSUPPORTED;
   }
-  gn_stats_finalize_kernel<<<1, 16 * 2 * GN_GROUPS, 0, stream>>>(partials, blocks, sums);
+  gn_stats_finalize_kernel<<<1, 16 * 2 * GN_GROUPS, 0, stream>>>(partials, blocks, sums); note_launch();
   B200_CHECK_CUDA(cudaGetLastError());
   return B200_OK;
 }
@@ -225,6 +225,7 @@ int gn_apply_pad_cl(const void* x, void* y, const double* sums, const float* gam
       return B200_ERR_UNSUPPORTED;
   }
 #undef B200_GN_LAUNCH
+  note_launch();
   B200_CHECK_CUDA(cudaGetLastError());
   return B200_OK;
 }

@@ -3,7 +3,9 @@
 #include <stdarg.h>
 #include <string.h>
 
+#include <atomic>
 #include <mutex>
+#include <vector>
 
 namespace b200 {
 
@@ -26,6 +28,67 @@ int num_sms() {
     if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) sms = 148;
   }
   return sms;
+}
+
+static std::atomic<long long> g_launches{0};
+void note_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+long long launch_count() { return g_launches.load(std::memory_order_relaxed); }
+
+// ---- attention launch profiler (off unless b200_prof_fmha_begin was called) ------------------------------------------------
+struct ProfRec {
+  cudaEvent_t e0, e1;
+  long long sq, sk;
+  int heads, head_dim;
+};
+static std::mutex g_prof_mu;
+static std::vector<ProfRec> g_prof;
+static int g_prof_cap = 0;      // 0 = disabled
+
+ProfScope::ProfScope(long long sq, long long sk, int heads, int head_dim, cudaStream_t s) : slot(-1), stream(s) {
+  if (g_prof_cap == 0) return;
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  if ((int)g_prof.size() >= g_prof_cap) return;
+  ProfRec r{nullptr, nullptr, sq, sk, heads, head_dim};
+  if (cudaEventCreate(&r.e0) != cudaSuccess || cudaEventCreate(&r.e1) != cudaSuccess) return;
+  cudaEventRecord(r.e0, s);
+  g_prof.push_back(r);
+  slot = (int)g_prof.size() - 1;
+}
+ProfScope::~ProfScope() {
+  if (slot < 0) return;
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  if (slot < (int)g_prof.size()) cudaEventRecord(g_prof[slot].e1, stream);
+}
+
+int prof_fmha_begin(int capacity) {
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  for (auto& r : g_prof) {
+    cudaEventDestroy(r.e0);
+    cudaEventDestroy(r.e1);
+  }
+  g_prof.clear();
+  g_prof_cap = capacity > 0 ? capacity : 0;
+  return B200_OK;
+}
+
+// Blocks until the recorded launches have finished; ms[i] = duration, meta[4 i ..] = {sq, sk, heads, head_dim}.  Returns the count.
+int prof_fmha_end(float* ms, long long* meta, int capacity) {
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  int n = 0;
+  for (auto& r : g_prof) {
+    float t = -1.f;
+    if (cudaEventSynchronize(r.e1) == cudaSuccess) cudaEventElapsedTime(&t, r.e0, r.e1);
+    if (n < capacity && ms && meta) {
+      ms[n] = t;
+      meta[4 * n + 0] = r.sq; meta[4 * n + 1] = r.sk; meta[4 * n + 2] = r.heads; meta[4 * n + 3] = r.head_dim;
+      ++n;
+    }
+    cudaEventDestroy(r.e0);
+    cudaEventDestroy(r.e1);
+  }
+  g_prof.clear();
+  g_prof_cap = 0;
+  return n;
 }
 
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,

@@ -37,6 +37,19 @@ void set_last_error(const char* fmt, ...);
 
 int num_sms();
 
+// Launch accounting for bench.py's `gpu_launches` (b200_launch_count): every kernel launch of this library calls note_launch().
+void note_launch(int n = 1);
+long long launch_count();
+
+// Optional CUDA-event bracket around the attention launches (b200_prof_fmha_begin / _end): the roofline of the dominant kernel is
+// measured on the launching stream even when the launch happens below the C ABI (b200_wan_block_fwd).
+struct ProfScope {
+  int slot;
+  cudaStream_t stream;
+  ProfScope(long long sq, long long sk, int heads, int head_dim, cudaStream_t stream);
+  ~ProfScope();
+};
+
 // Encode a tiled tensor map over a row-major tensor.  dims/box are innermost-first; strides_bytes
 // has rank-1 entries (stride of dim 1..rank-1).  Returns 0 on success.
 int encode_tmap(CUtensorMap* out, CUtensorMapDataType dtype, int rank, const void* base, const uint64_t* dims,

@@ -96,7 +96,7 @@ int quant_nvfp4(const void* x, long long ldx, long long rows, int K, const float
   const int max_blocks = num_sms() * 16;
   const int blocks = (int)(want < max_blocks ? want : max_blocks);
   quant_nvfp4_kernel<<<blocks, 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(x), ldx, rows, rows_padded, K, global_scale,
-                                                  reinterpret_cast<uint8_t*>(q), ldq, reinterpret_cast<uint8_t*>(sf));
+                                                  reinterpret_cast<uint8_t*>(q), ldq, reinterpret_cast<uint8_t*>(sf)); note_launch();
   B200_CHECK_CUDA(cudaGetLastError());
   return B200_OK;
 }
@@ -141,8 +141,8 @@ int nvfp4_act_scale(const void* x, long long ldx, long long rows, int K, const f
   const long long want = (rows * (K / 8) + 255) / 256;
   const int max_blocks = num_sms() * 8;
   const int blocks = (int)(want < max_blocks ? want : max_blocks);
-  absmax_kernel<<<blocks, 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(x), ldx, rows, K, reinterpret_cast<uint32_t*>(scratch));
-  nvfp4_scale_finalize_kernel<<<1, 1, 0, stream>>>(reinterpret_cast<const uint32_t*>(scratch), weight_global_scale, global_scale, alpha);
+  absmax_kernel<<<blocks, 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(x), ldx, rows, K, reinterpret_cast<uint32_t*>(scratch)); note_launch();
+  nvfp4_scale_finalize_kernel<<<1, 1, 0, stream>>>(reinterpret_cast<const uint32_t*>(scratch), weight_global_scale, global_scale, alpha); note_launch();
   B200_CHECK_CUDA(cudaGetLastError());
   return B200_OK;
 }

@@ -203,6 +203,7 @@ static int ln_modulate_impl(const void* x, long long ldx, void* y, long long ldy
     else B200_LN_LAUNCH(false, false, false);
   }
 #undef B200_LN_LAUNCH
+  note_launch();
   B200_CHECK_CUDA(cudaGetLastError());
   return B200_OK;
 }
@@ -269,7 +270,7 @@ int quant_fp8_per_token(const void* x, long long ldx, void* q8, long long ldq, f
                  "b200_quant_fp8_per_token: D=%d must be a multiple of 8 and <= %d", D, QUANT_THREADS * QUANT_MAX_VEC * 8);
   B200_CHECK_ARG(ldx % 8 == 0 && ldx >= D && ldq % 8 == 0 && ldq >= D, "b200_quant_fp8_per_token: bad leading dimension");
   quant_fp8_kernel<<<(unsigned)rows, QUANT_THREADS, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(x), ldx,
-                                                               reinterpret_cast<uint8_t*>(q8), ldq, q_scale, D);
+                                                               reinterpret_cast<uint8_t*>(q8), ldq, q_scale, D); note_launch();
   B200_CHECK_CUDA(cudaGetLastError());
   return B200_OK;
 }
@@ -359,6 +360,7 @@ int rms_rope(void* x0, long long ld0, const void* w0, void* x1, long long ld1, c
                                                             rope_rows, pos_offset);
   else
     rms_rope_kernel<false><<<grid, ROW_THREADS, 0, stream>>>(a, D, eps, nullptr, 0, 0);
+  note_launch();
   B200_CHECK_CUDA(cudaGetLastError());
   return B200_OK;
 }
@@ -424,7 +426,7 @@ int rms_rope_heads(void* x0, long long ld0, const void* w0, void* x1, long long 
   a.w[1] = reinterpret_cast<const __nv_bfloat16*>(w1);
   a.ld[1] = ld1;
   dim3 grid((unsigned)rows, x1 ? 2 : 1);
-  rms_rope_heads_kernel<<<grid, ROW_THREADS, 0, stream>>>(a, H, eps, reinterpret_cast<const float2*>(cos_sin), rope_rows);
+  rms_rope_heads_kernel<<<grid, ROW_THREADS, 0, stream>>>(a, H, eps, reinterpret_cast<const float2*>(cos_sin), rope_rows); note_launch();
   B200_CHECK_CUDA(cudaGetLastError());
   return B200_OK;
 }
@@ -523,7 +525,7 @@ int rms_rope_scatter(const void* qkv, long long ld, const void* wq, const void* 
   rms_rope_scatter_kernel<<<grid, ROW_THREADS, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(qkv), ld,
                                                           reinterpret_cast<const __nv_bfloat16*>(wq),
                                                           reinterpret_cast<const __nv_bfloat16*>(wk), D, eps,
-                                                          reinterpret_cast<const float2*>(cos_sin), rope_rows, sc);
+                                                          reinterpret_cast<const float2*>(cos_sin), rope_rows, sc); note_launch();
   B200_CHECK_CUDA(cudaGetLastError());
   return B200_OK;
 }

@@ -111,9 +111,9 @@ int rms_silu_cl(const void* x, void* y, const float* gamma, long long voxels, in
   auto* yp = reinterpret_cast<__nv_bfloat16*>(y);
   const int blocks = num_sms() * 8;
   switch (C) {
-    case 96: rms_silu_kernel<96><<<blocks, 256, 0, stream>>>(xp, yp, gamma, voxels, apply_silu); break;
-    case 192: rms_silu_kernel<192><<<blocks, 256, 0, stream>>>(xp, yp, gamma, voxels, apply_silu); break;
-    case 384: rms_silu_kernel<384><<<blocks, 256, 0, stream>>>(xp, yp, gamma, voxels, apply_silu); break;
+    case 96: rms_silu_kernel<96><<<blocks, 256, 0, stream>>>(xp, yp, gamma, voxels, apply_silu); note_launch(); break;
+    case 192: rms_silu_kernel<192><<<blocks, 256, 0, stream>>>(xp, yp, gamma, voxels, apply_silu); note_launch(); break;
+    case 384: rms_silu_kernel<384><<<blocks, 256, 0, stream>>>(xp, yp, gamma, voxels, apply_silu); note_launch(); break;
     default:
       set_last_error("b200_rms_silu_cl: unsupported channel count %d (96 / 192 / 384)", C);
       return B200_ERR_UNSUPPORTED;
@@ -138,7 +138,7 @@ int latent_to_cl(const float* z, void* out, const float* mean, const float* inv_
                  cudaStream_t stream) {
   B200_CHECK_ARG(z && out && mean && inv_std && voxels > 0 && CZ > 0 && CP >= CZ, "b200_latent_to_cl: bad arguments");
   const long long n = voxels * CP;
-  latent_to_cl_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(z, reinterpret_cast<__nv_bfloat16*>(out), mean, inv_std, voxels, CZ, CP);
+  latent_to_cl_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(z, reinterpret_cast<__nv_bfloat16*>(out), mean, inv_std, voxels, CZ, CP); note_launch();
   B200_CHECK_CUDA(cudaGetLastError());
   return B200_OK;
 }
@@ -155,7 +155,7 @@ __global__ void cl_to_video_kernel(const __nv_bfloat16* __restrict__ in, float* 
 
 int cl_to_video(const void* in, float* out, long long voxels, int CP, cudaStream_t stream) {
   B200_CHECK_ARG(in && out && voxels > 0 && CP >= 3, "b200_cl_to_video: bad arguments");
-  cl_to_video_kernel<<<(unsigned)((voxels + 255) / 256), 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(in), out, voxels, CP);
+  cl_to_video_kernel<<<(unsigned)((voxels + 255) / 256), 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(in), out, voxels, CP); note_launch();
   B200_CHECK_CUDA(cudaGetLastError());
   return B200_OK;
 }

@@ -85,7 +85,7 @@ int wan_block_fwd(const b200_wan_block_weights* w, const b200_wan_block_args* a,
     const long long n8 = S * D / 8;
     const long long want = (n8 + 255) / 256;
     const int blocks = (int)(want < num_sms() * 8 ? want : num_sms() * 8);
-    add_bf16_kernel<<<blocks, 256, 0, stream>>>(n, tmp, n8);
+    add_bf16_kernel<<<blocks, 256, 0, stream>>>(n, tmp, n8); note_launch();
     B200_CHECK_CUDA(cudaGetLastError());
   }
   B200_TRY(gemm_bf16(n, D, w->wco, D, x, D, w->bco, nullptr, S, D, D, 3 /*residual*/, 0, 0, stream));

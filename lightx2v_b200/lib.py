@@ -21,6 +21,10 @@ SIGNATURES = {
     "b200_last_error": (ctypes.c_char_p, []),
     "b200_version": (_i32, []),
     "b200_num_sms": (_i32, []),
+    "b200_launch_count": (_i64, []),
+    "b200_prof_fmha_begin": (_i32, [_i32]),
+    "b200_prof_fmha_end": (_i32, [_ptr, _ptr, _i32]),
+    "b200_fmha_fwd_d64": (_i32, [_ptr, _i64, _ptr, _i64, _ptr, _i64, _ptr, _i64, _i64, _i64, _i32, _f32, _ptr]),
     "b200_gemm_bf16": (_i32, [_ptr, _i64, _ptr, _i64, _ptr, _i64, _ptr, _ptr, _i64, _i64, _i64, _i32, _i32, _i32, _ptr]),
     "b200_ln_modulate": (_i32, [_ptr, _i64, _ptr, _i64, _ptr, _ptr, _ptr, _ptr, _i64, _i32, _f32, _ptr]),
     "b200_rms_rope": (_i32, [_ptr, _i64, _ptr, _ptr, _i64, _ptr, _i64, _i32, _f32, _ptr, _i64, _i64, _ptr]),
@@ -150,20 +154,41 @@ def rms_rope_(x0: torch.Tensor, w0: torch.Tensor, x1: Optional[torch.Tensor] = N
 
 def fmha(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, *, softmax_scale: Optional[float] = None,
          out: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """q [Sq,H,128], k/v [Sk,H,128] (row-strided views allowed) -> out [Sq,H,128]; one segment, non-causal."""
+    """q [Sq,H,d], k/v [Sk,H,d] (row-strided views allowed), d = 128 or 64 -> out [Sq,H,d]; one segment, non-causal."""
+    d = q.shape[-1]
+    if d not in (64, 128):
+        raise B200Error(f"fmha: head_dim must be 64 or 128, got {d}")
     for n, t in (("q", q), ("k", k), ("v", v)):
         _req(t, n)
-        if t.dim() != 3 or t.shape[2] != 128 or t.stride(1) != 128:
-            raise B200Error(f"fmha: {n} must be [S,H,128] with contiguous heads, got {tuple(t.shape)} / {t.stride()}")
+        if t.dim() != 3 or t.shape[2] != d or t.stride(1) != d:
+            raise B200Error(f"fmha: {n} must be [S,H,{d}] with contiguous heads, got {tuple(t.shape)} / {t.stride()}")
     sq, H, _ = q.shape
     sk = k.shape[0]
     if out is None:
-        out = torch.empty((sq, H, 128), dtype=torch.bfloat16, device=q.device)
-    scale = 128 ** -0.5 if softmax_scale is None else softmax_scale
-    rc = load().b200_fmha_fwd_d128(q.data_ptr(), q.stride(0), k.data_ptr(), k.stride(0), v.data_ptr(), v.stride(0),
-                                   out.data_ptr(), out.stride(0), sq, sk, H, scale, _stream())
-    _check(rc, "b200_fmha_fwd_d128")
+        out = torch.empty((sq, H, d), dtype=torch.bfloat16, device=q.device)
+    _req(out, "out")
+    scale = d ** -0.5 if softmax_scale is None else softmax_scale
+    fn = load().b200_fmha_fwd_d128 if d == 128 else load().b200_fmha_fwd_d64
+    rc = fn(q.data_ptr(), q.stride(0), k.data_ptr(), k.stride(0), v.data_ptr(), v.stride(0), out.data_ptr(), out.stride(0), sq, sk, H, scale, _stream())
+    _check(rc, f"b200_fmha_fwd_d{d}")
     return out
+
+
+def launch_count() -> int:
+    """Kernel launches issued by libb200dit.so in this process so far (bench.py's `gpu_launches` = difference over the timed region)."""
+    return int(load().b200_launch_count())
+
+
+def prof_fmha_begin(capacity: int = 8192) -> None:
+    _check(load().b200_prof_fmha_begin(int(capacity)), "b200_prof_fmha_begin")
+
+
+def prof_fmha_end(capacity: int = 8192):
+    """-> list of (ms, sq, sk, heads, head_dim) for the attention launches since prof_fmha_begin (blocks until they finished)."""
+    ms = (ctypes.c_float * capacity)()
+    meta = (ctypes.c_int64 * (4 * capacity))()
+    n = load().b200_prof_fmha_end(ctypes.cast(ms, ctypes.c_void_p), ctypes.cast(meta, ctypes.c_void_p), capacity)
+    return [(float(ms[i]), int(meta[4 * i]), int(meta[4 * i + 1]), int(meta[4 * i + 2]), int(meta[4 * i + 3])) for i in range(n)]
 
 
 # ---------------------------------------------------------------------------------------------------------------- fp8 (w8a8)
