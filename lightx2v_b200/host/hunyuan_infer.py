@@ -88,6 +88,9 @@ class HunyuanTransformerInfer:
         self.infer_func = self._infer_without_offload
 
     # ------------------------------------------------------------------ reference surface
+    def set_scheduler(self, scheduler):
+        self.scheduler = scheduler
+
     def infer(self, weights, img, txt, vec, cu_seqlens_qkv, max_seqlen_qkv, freqs_cis, token_replace_vec=None, frist_frame_token_num=None):
         if token_replace_vec is not None:
             raise lib.B200Error("HunyuanTransformerInfer(B200): i2v token replacement is not implemented on this path")

@@ -354,6 +354,7 @@ class FmhaWeightB200:
 
     def __init__(self):
         self.config = {}
+        self._cu_cache = {}
 
     def load(self, weight_dict):
         pass
@@ -371,12 +372,20 @@ class FmhaWeightB200:
     def state_dict(self, destination=None):
         return {} if destination is None else destination
 
-    @staticmethod
-    def _bounds(cu, total):
+    def _bounds(self, cu, total):
+        """Host copy of a cu_seqlens argument.  A CUDA tensor costs one device->host read the first time it is seen; the result is cached per
+        tensor object (+ `_version`), so the reference infer classes, which pass the same cu_seqlens every block, do not sync per call."""
         if cu is None:
             return [0, total]
         if isinstance(cu, torch.Tensor):
-            return [int(v) for v in cu.tolist()]
+            ent = self._cu_cache.get(id(cu))
+            if ent is not None and ent[0] is cu and ent[1] == cu._version:
+                return ent[2]
+            b = [int(v) for v in cu.tolist()]
+            if len(self._cu_cache) >= 8:
+                self._cu_cache.pop(next(iter(self._cu_cache)))
+            self._cu_cache[id(cu)] = (cu, cu._version, b)
+            return b
         return [int(v) for v in cu]
 
     def apply(self, q, k, v, cu_seqlens_q=None, cu_seqlens_kv=None, max_seqlen_q=None, max_seqlen_kv=None,
@@ -386,9 +395,15 @@ class FmhaWeightB200:
         if len(bq) != len(bk):
             raise lib.B200Error("b200_fmha: cu_seqlens_q and cu_seqlens_kv must have the same number of segments")
         out = torch.empty((q.shape[0], q.shape[1], q.shape[2]), dtype=torch.bfloat16, device=q.device)
+        covered = 0
         for i in range(len(bq) - 1):
             if bq[i + 1] > bq[i] and bk[i + 1] > bk[i]:
+                if bq[i] > covered:
+                    out[covered:bq[i]].zero_()                     # rows no segment attends from: defined (zero) output, like flash-attn's padded rows
                 lib.fmha(q[bq[i]:bq[i + 1]], k[bk[i]:bk[i + 1]], v[bk[i]:bk[i + 1]], out=out[bq[i]:bq[i + 1]])
+                covered = bq[i + 1]
+        if covered < q.shape[0]:
+            out[covered:].zero_()
         rows = q.shape[0] if max_seqlen_q is None else max_seqlen_q
         return out.reshape(rows, -1)
 

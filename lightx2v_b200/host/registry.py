@@ -5,46 +5,53 @@ SURVEY.md §8b)."""
 from __future__ import annotations
 
 
-class Register(dict):
-    def __init__(self, *args, **kwargs):
-        super().__init__(*args, **kwargs)
-        self._dict = {}
+class Register:
+    """Stand-alone key -> class table for this package (when LightX2V itself is importable its own registries are used instead, see
+    `install_into_lightx2v`).  Contract relied on by the weight trees and by plugins: decorating with a key that is already taken is an
+    error, while plain item assignment replaces an entry."""
 
-    def __call__(self, target_or_name):
-        if callable(target_or_name):
-            return self.register(target_or_name)
-        return lambda x: self.register(x, key=target_or_name)
+    __slots__ = ("_table",)
 
-    def register(self, target, key=None):
-        if not callable(target):
-            raise Exception(f"Error: {target} must be callable!")
-        if key is None:
-            key = target.__name__
-        if key in self._dict:
-            raise Exception(f"{key} already exists.")
-        self[key] = target
-        return target
+    def __init__(self):
+        self._table = {}
 
-    def __setitem__(self, key, value):
-        self._dict[key] = value
+    def __call__(self, key_or_class):
+        if isinstance(key_or_class, str):
+            return lambda cls: self.register(cls, key=key_or_class)
+        return self.register(key_or_class)
+
+    def register(self, cls, key=None):
+        key = getattr(cls, "__name__", None) if key is None else key
+        if not callable(cls) or key is None:
+            raise TypeError(f"cannot register {cls!r}")
+        if key in self._table:
+            raise KeyError(f"{key} already exists.")
+        self._table[key] = cls
+        return cls
+
+    def __setitem__(self, key, cls):
+        self._table[key] = cls
 
     def __getitem__(self, key):
-        return self._dict[key]
+        return self._table[key]
 
     def __contains__(self, key):
-        return key in self._dict
+        return key in self._table
 
-    def __str__(self):
-        return str(self._dict)
+    def __iter__(self):
+        return iter(self._table)
+
+    def __len__(self):
+        return len(self._table)
 
     def keys(self):
-        return self._dict.keys()
-
-    def values(self):
-        return self._dict.values()
+        return self._table.keys()
 
     def items(self):
-        return self._dict.items()
+        return self._table.items()
+
+    def __repr__(self):
+        return f"Register({sorted(self._table)})"
 
 
 MM_WEIGHT_REGISTER = Register()

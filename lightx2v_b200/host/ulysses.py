@@ -132,6 +132,10 @@ class FusedUlyssesAttention:
         self.recv = symm_mem.empty((self.world * self.s, 3, self.hp, 128), dtype=torch.bfloat16, device=device)
         # attention output for my tokens, all heads (written by every rank)
         self.attn = symm_mem.empty((self.s, num_heads, 128), dtype=torch.bfloat16, device=device)
+        # rows >= total_rows (padding to a multiple of the world size) are never written by the kernels: keep them zero, like the NCCL path,
+        # so that nothing downstream (o-proj residual epilogue, the nvfp4 per-tensor absmax) ever sees uninitialised memory
+        self.recv.zero_()
+        self.attn.zero_()
         self.recv_h = symm_mem.rendezvous(self.recv, self.group)
         self.attn_h = symm_mem.rendezvous(self.attn, self.group)
         self.recv_ptrs = list(self.recv_h.buffer_ptrs)
@@ -175,7 +179,11 @@ def parallelize_wan(model, total_rows: int, attention_fn: Callable, group=None):
 def parallelize_wan_cfg(model, total_rows: int, attention_fn: Optional[Callable] = None, sp: str = "fused", group=None):
     """CFG-parallel x Ulysses: ranks [0, P/2) run the conditional pass, ranks [P/2, P) the unconditional one (SURVEY.md 8f N1;
     the reference runs them back to back, wan/model.py:203-218); inside each half the token axis is Ulysses-sharded over P/2 ranks
-    (P = 2: no exchange at all inside the block stack).  Returns the description of what was installed."""
+    (P = 2: no exchange at all inside the block stack).  `sp` selects the exchange inside a half ("fused": peer-memory kernels,
+    "nccl": all-to-all); a failing peer-memory setup raises - there is no silent change of path.  Returns a description of what was installed."""
+    if attention_fn is None:
+        from .. import lib
+        attention_fn = lib.fmha
     world, rank = dist.get_world_size(group), dist.get_rank(group)
     if world % 2 != 0:
         raise ValueError(f"CFG-parallel needs an even world size, got {world}")
@@ -188,12 +196,8 @@ def parallelize_wan_cfg(model, total_rows: int, attention_fn: Optional[Callable]
     if half > 1:
         sub = groups[branch]
         if sp == "fused":
-            try:
-                parallelize_wan_fused(model, total_rows, sub)
-                mode = f"cfg2 x ulysses{half} (peer memory)"
-            except Exception as ex:   # symmetric memory not available for sub-groups on this build: NCCL exchange instead
-                parallelize_wan(model, total_rows, attention_fn, sub)
-                mode = f"cfg2 x ulysses{half} (nccl; peer-memory setup failed: {str(ex)[:80]})"
+            parallelize_wan_fused(model, total_rows, sub)
+            mode = f"cfg2 x ulysses{half} (peer memory)"
         else:
             parallelize_wan(model, total_rows, attention_fn, sub)
             mode = f"cfg2 x ulysses{half} (nccl)"

@@ -50,9 +50,11 @@ def rope_cos_sin(grid_sizes, freqs: torch.Tensor, head_dim: int, rows: Optional[
 class _BlockCache:
     """Per-block derived tensors: concatenated QKV weight/bias, cached cross-attention text K/V."""
 
-    __slots__ = ("wqkv", "bqkv", "sqkv", "kv", "native", "keep")
+    __slots__ = ("wqkv", "bqkv", "sqkv", "kv", "native", "keep", "owner", "fingerprint")
 
     def __init__(self):
+        self.owner = None
+        self.fingerprint = None
         self.wqkv = None
         self.bqkv = None
         self.sqkv = None
@@ -75,6 +77,7 @@ class WanTransformerInfer:
         self.parallel_attention = None          # set by parallel.ulysses.parallelize_wan
         self.sp_rank, self.sp_world = 0, 1
         self.infer_conditional = True
+        self.scheduler = None
         self.mask_map = None
         self.cache_cross_kv = bool(config.get("b200_cache_cross_kv", True))
         self.native_block = bool(config.get("b200_native_block", True))   # one C call per block (csrc/wan_block.cu) when eligible
@@ -84,6 +87,16 @@ class WanTransformerInfer:
         self.infer_func = self._infer_without_offload
 
     # ------------------------------------------------------------------ reference surface
+    def set_scheduler(self, scheduler):
+        """BaseTransformerInfer.set_scheduler (lightx2v/common/transformer_infer/transformer_infer.py; called by WanModel.set_scheduler,
+        wan/model.py:185)."""
+        self.scheduler = scheduler
+
+    def clear_weight_caches(self):
+        """Drop every tensor derived from the weights (concatenated QKV, the native block's pointer struct, cached text K/V): call after the
+        weight tree was reloaded or moved (WeightModule.load / to_cuda), so no block keeps computing with - or pinning - the old tensors."""
+        self._caches.clear()
+
     def switch_status(self):
         self.infer_conditional = not self.infer_conditional
 
@@ -150,10 +163,25 @@ class WanTransformerInfer:
             self._bufs[key] = b
         return b
 
+    @staticmethod
+    def _weight_fingerprint(weights):
+        """(data_ptr, _version) of every weight tensor of a phase: changes when a tensor is replaced, moved or edited in place."""
+        fp = []
+        for m in getattr(weights, "_modules", {}).values():
+            for a in ("weight", "bias", "weight_scale", "tensor"):
+                t = getattr(m, a, None)
+                if isinstance(t, torch.Tensor):
+                    fp.append((t.data_ptr(), t._version))
+        return tuple(fp)
+
     def _cache(self, weights) -> _BlockCache:
+        """Derived tensors of one phase object.  The entry holds a reference to the phase (so id() cannot be reused by another object while
+        the entry lives) and a fingerprint of its weight tensors; a reload / LoRA merge / to_cpu-to_cuda round trip rebuilds the entry."""
+        fp = self._weight_fingerprint(weights)
         c = self._caches.get(id(weights))
-        if c is None:
+        if c is None or c.owner is not weights or c.fingerprint != fp:
             c = _BlockCache()
+            c.owner, c.fingerprint = weights, fp
             self._caches[id(weights)] = c
         return c
 

@@ -19,6 +19,7 @@ import torch.nn.functional as F
 
 from .. import lib
 from .wan_infer import WanTransformerInfer
+from .registry import MM_KEY
 from .wan_weights import WanTransformerWeights
 
 
@@ -141,25 +142,110 @@ class WanPostInfer:
 
 
 class WanModel:
-    """Weights already resident on the GPU (180 GB HBM3e: no offload), built from a flat checkpoint-named dict."""
+    """`WanModel(model_path, config, device)` like the reference (lightx2v/models/networks/wan/model.py:33-59): loads every
+    `*.safetensors` under `model_path` (or `model_path/original/`, model.py:79-95) as bf16 onto `device` and builds the weight tree and the
+    pre / transformer / post infer objects; `config["feature_caching"]` ("NoCaching" | "Tea") and `config["model_cls"]` ("wan2.1_causvid")
+    select the transformer infer class like `_init_infer_class` (:61-75; the CausVid subclass is wan/causvid/model.py);
+    `config["parallel_attn_type"] == "ulysses"` installs the sequence-parallel hooks (:52-58).  Weights stay resident on the GPU
+    (180 GB HBM3e: the reference's cpu_offload managers are not needed).  `WanModel.from_weight_dict(config, weight_dict)` builds the
+    same object from an in-memory checkpoint-named dict (synthetic weights in the tests and bench.py)."""
 
-    def __init__(self, config, weight_dict: Dict[str, torch.Tensor]):
+    def __init__(self, model_path, config, device):
+        self.model_path = model_path
         self.config = config
-        self.W = weight_dict
-        self.transformer_weights = WanTransformerWeights(config)
-        self.transformer_weights.load(weight_dict)
-        self.pre_infer = WanPreInfer(config)
-        self.post_infer = WanPostInfer(config)
-        self.transformer_infer = WanTransformerInfer(config)
+        self.device = torch.device(device) if device is not None else None
+        self._init_infer_class()
+        self._init_weights()
+        self._init_infer()
+        if config.get("parallel_attn_type"):
+            self._init_parallel(config["parallel_attn_type"])
+
+    @classmethod
+    def from_weight_dict(cls, config, weight_dict: Dict[str, torch.Tensor], device=None):
+        self = cls.__new__(cls)
+        self.model_path = None
+        self.config = config
+        self.device = torch.device(device) if device is not None else None
+        self._init_infer_class()
+        self._init_weights(weight_dict)
+        self._init_infer()
+        if config.get("parallel_attn_type"):
+            self._init_parallel(config["parallel_attn_type"])
+        return self
+
+    # ------------------------------------------------------------------ construction (model.py:61-140)
+    def _init_infer_class(self):
+        self.pre_infer_class = WanPreInfer
+        self.post_infer_class = WanPostInfer
+        caching = self.config.get("feature_caching", "NoCaching")
+        if self.config.get("model_cls") == "wan2.1_causvid":
+            from .wan_causvid import WanTransformerInferCausVid
+            self.transformer_infer_class = WanTransformerInferCausVid
+        elif caching == "NoCaching":
+            self.transformer_infer_class = WanTransformerInfer
+        elif caching == "Tea":
+            from .wan_teacache import WanTransformerInferTeaCaching
+            self.transformer_infer_class = WanTransformerInferTeaCaching
+        else:       # TaylorSeer / Ada / Custom change which steps run, not the step (DESIGN.md §10)
+            raise NotImplementedError(f"Unsupported feature_caching type: {caching}")
+
+    def _load_ckpt(self) -> Dict[str, torch.Tensor]:
+        import glob
+        import os
+
+        from safetensors import safe_open
+
+        files = glob.glob(os.path.join(self.model_path, "*.safetensors")) or glob.glob(os.path.join(self.model_path, "original", "*.safetensors"))
+        if not files:
+            raise FileNotFoundError(f"No .safetensors files found in directory: {self.model_path}")
+        out = {}
+        quant = (self.config.get("mm_config") or {}).get("mm_type", MM_KEY) != MM_KEY          # pre-quantised checkpoints keep their dtypes
+        for fp in sorted(files):
+            with safe_open(fp, framework="pt") as f:
+                for key in f.keys():
+                    t = f.get_tensor(key)
+                    if t.is_floating_point() and t.dtype in (torch.float32, torch.float16) and not (quant and key.endswith(("weight_scale", "weight_global_scale"))):
+                        t = t.to(torch.bfloat16)
+                    out[key] = t.to(self.device)
+        return out
+
+    def _init_weights(self, weight_dict: Optional[Dict[str, torch.Tensor]] = None):
+        self.W = self._load_ckpt() if weight_dict is None else weight_dict
+        self.transformer_weights = WanTransformerWeights(self.config)
+        self.transformer_weights.load(self.W)
+        self.pre_weight = self.post_weight = self.W        # the reference's WanPreWeights / WanPostWeights: here the flat dict itself
+
+    def _init_infer(self):
+        self.pre_infer = self.pre_infer_class(self.config)
+        self.post_infer = self.post_infer_class(self.config)
+        self.transformer_infer = self.transformer_infer_class(self.config)
         self.scheduler = None
         self.pre_process = None      # sequence-parallel hooks (host/ulysses.py)
         self.post_process = None
         self.cfg_parallel = None     # (branch_is_cond, cond_src_rank, uncond_src_rank, group) - host/ulysses.py:parallelize_wan_cfg
 
+    def _init_parallel(self, kind: str):
+        from . import ulysses
+
+        if kind != "ulysses":        # ring attention is out of scope (superseded by Ulysses on NVSwitch, DESIGN.md §10)
+            raise Exception("Unsuppotred parallel_attn_type")
+        ts = self.config["target_shape"]
+        total = ts[1] * (ts[2] // 2) * (ts[3] // 2)
+        ulysses.parallelize_wan_fused(self, total)
+
     def set_scheduler(self, scheduler):
+        """model.py:180-185."""
         self.scheduler = scheduler
         self.pre_infer.set_scheduler(scheduler)
         self.post_infer.set_scheduler(scheduler)
+        self.transformer_infer.set_scheduler(scheduler)
+
+    def to_cpu(self):
+        self.transformer_weights.to_cpu()
+
+    def to_cuda(self):
+        self.transformer_weights.to_cuda()
+        self.transformer_infer.clear_weight_caches()
 
     def _forward(self, inputs, positive: bool):
         embed, grid_sizes, (x, embed0, seq_lens, freqs, context) = self.pre_infer.infer(self.W, inputs, positive)

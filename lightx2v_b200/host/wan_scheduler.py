@@ -36,12 +36,31 @@ class WanScheduler:
         ts = self.config["target_shape"]
         self.latents = torch.randn(ts[0], ts[1], ts[2], ts[3], dtype=torch.float32, device=self.device, generator=self.generator)
         ps = self.config.get("patch_size", (1, 2, 2))
-        self.seq_len = math.ceil((ts[2] * ts[3]) / (ps[1] * ps[2]) * ts[1])
+        if self.config.get("task", "t2v") == "i2v" and "lat_h" in self.config:      # scheduler.py:32-33 (floor, from the VAE grid)
+            frames = (self.config["target_video_length"] - 1) // self.config.get("vae_stride", (4, 8, 8))[0] + 1
+            self.seq_len = frames * self.config["lat_h"] * self.config["lat_w"] // (ps[1] * ps[2])
+        else:                                                                       # scheduler.py:30-31
+            self.seq_len = math.ceil((ts[2] * ts[3]) / (ps[1] * ps[2]) * ts[1])
+        self._seed_default_generator()
         alphas = np.linspace(1, 1 / self.num_train_timesteps, self.num_train_timesteps)[::-1].copy()
         sig = torch.from_numpy(1.0 - alphas).to(dtype=torch.float32)
         self.sigma_min = sig[-1].item()
         self.sigma_max = sig[0].item()
         self.set_timesteps(self.infer_steps, shift=self.sample_shift)
+
+    def _seed_default_generator(self):
+        """Sequence / CFG parallel runs replicate the latents on every rank; any draw from the process DEFAULT generator (the step-distill
+        re-noising, step_distill/scheduler.py:53) must therefore be identical across ranks.  The reference gets this from its runner's
+        seed_all(config.seed) at start-up (lightx2v/utils/utils.py seed_all); a stand-alone user of this scheduler gets it here."""
+        try:
+            import torch.distributed as dist
+            multi = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+        except Exception:
+            multi = False
+        if multi:
+            torch.manual_seed(self.config["seed"])
+            if self.device.type == "cuda":
+                torch.cuda.manual_seed(self.config["seed"])
 
     def set_timesteps(self, infer_steps, shift=1.0):
         sig = np.linspace(self.sigma_max, self.sigma_min, infer_steps + 1).copy()[:-1]

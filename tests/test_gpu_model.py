@@ -67,7 +67,7 @@ def test_model_cfg_combine_and_step():
     gen = torch.Generator(device=dev).manual_seed(7)
     ctx = {"context": torch.randn(100, 4096, generator=gen, device=dev).to(torch.bfloat16), "context_null": torch.randn(512, 4096, generator=gen, device=dev).to(torch.bfloat16)}
     inputs = {"text_encoder_output": ctx, "image_encoder_output": None}
-    model = WanModel(cfg, W)
+    model = WanModel.from_weight_dict(cfg, W)
     sched = WanScheduler(cfg, device=dev)
     sched.prepare()
     model.set_scheduler(sched)

@@ -180,7 +180,7 @@ def _run_cfg_rank(rank, world, port, out_path):
         inputs = {"text_encoder_output": ctx, "image_encoder_output": None}
         outs = []
         for parallel in (False, True):
-            model = WanModel(cfg, W)
+            model = WanModel.from_weight_dict(cfg, W)
             sched = WanScheduler(cfg, device=dev)
             sched.prepare()
             model.set_scheduler(sched)

@@ -134,9 +134,14 @@ def test_rope_cos_sin_matches_reference_tables():
 def test_fmha_op_segment_bounds():
     from lightx2v_b200.host.ops import FmhaWeightB200
 
-    assert FmhaWeightB200._bounds(None, 7) == [0, 7]
-    assert FmhaWeightB200._bounds(torch.tensor([0, 5, 9], dtype=torch.int32), 9) == [0, 5, 9]
-    assert FmhaWeightB200._bounds([0, 3], 3) == [0, 3]
+    op = FmhaWeightB200()
+    assert op._bounds(None, 7) == [0, 7]
+    cu = torch.tensor([0, 5, 9], dtype=torch.int32)
+    assert op._bounds(cu, 9) == [0, 5, 9]
+    assert op._bounds(cu, 9) is op._bounds(cu, 9)              # cached per tensor object: no repeated device->host read
+    cu[1] = 4                                                  # an in-place edit bumps _version and invalidates the entry
+    assert op._bounds(cu, 9) == [0, 4, 9]
+    assert op._bounds([0, 3], 3) == [0, 3]
 
 
 def test_unipc_scheduler_matches_reference_fixture(golden_dir):
