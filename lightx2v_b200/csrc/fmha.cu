@@ -71,25 +71,6 @@ __device__ __forceinline__ float ex2(float x) {
   return y;
 }
 
-// 2^x for x <= ~8 on the FMA pipe: n = round(x) by the 1.5*2^23 trick, f = x - n in [-0.5, 0.5], degree-3 minimax
-// polynomial for 2^f (max relative error 7.5e-5, far below the 2^-9 of the bf16 P it feeds), exponent add in integer.
-__device__ __forceinline__ float2 exp2_poly2(float2 x) {
-  x.x = fmaxf(x.x, -126.f);
-  x.y = fmaxf(x.y, -126.f);
-  const float2 magic = make_float2(12582912.f, 12582912.f);
-  const float2 fi = __fadd2_rn(x, magic);
-  const float2 n = __fadd2_rn(fi, make_float2(-12582912.f, -12582912.f));
-  const float2 f = __ffma2_rn(n, make_float2(-1.f, -1.f), x);
-  float2 p = __ffma2_rn(f, make_float2(0.055171649903059006f, 0.055171649903059006f),
-                        make_float2(0.2426111251115799f, 0.2426111251115799f));
-  p = __ffma2_rn(p, f, make_float2(0.6932609677314758f, 0.6932609677314758f));
-  p = __ffma2_rn(p, f, make_float2(0.9999280571937561f, 0.9999280571937561f));
-  float2 r;
-  r.x = __int_as_float(__float_as_int(p.x) + (__float_as_int(fi.x) << 23));
-  r.y = __int_as_float(__float_as_int(p.y) + (__float_as_int(fi.y) << 23));
-  return r;
-}
-
 template <int kD, int kPolyPairs>
 __global__ void __launch_bounds__(FMHA_THREADS, 1)
 fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,

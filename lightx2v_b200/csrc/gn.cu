@@ -186,10 +186,11 @@ gn_apply_pad_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restri
                       bf16_lo(raw[u].z), bf16_hi(raw[u].z), bf16_lo(raw[u].w), bf16_hi(raw[u].w)};
         if (sums != nullptr) {
 #pragma unroll
-          for (int e = 0; e < 8; ++e) {
-            float y_ = fmaf(f[e], a[e], b[e]);
-            if (apply_silu) y_ = y_ / (1.0f + __expf(-y_));
-            f[e] = y_;
+          for (int e = 0; e < 8; e += 2) {
+            float2 y_ = make_float2(fmaf(f[e], a[e], b[e]), fmaf(f[e + 1], a[e + 1], b[e + 1]));
+            if (apply_silu) y_ = silu2(y_);
+            f[e] = y_.x;
+            f[e + 1] = y_.y;
           }
         }
         uint4 o;

@@ -52,10 +52,11 @@ rms_silu_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__
         const float inv = 1.0f / fmaxf(sqrtf(ss), 1e-12f);        // F.normalize: x / max(||x||_2, eps)
         if (ok) {
 #pragma unroll
-          for (int e = 0; e < 8; ++e) {
-            float t = f[e] * inv * g[e];
-            if (apply_silu) t = t / (1.0f + __expf(-t));
-            f[e] = t;
+          for (int e = 0; e < 8; e += 2) {
+            float2 t = make_float2(f[e] * inv * g[e], f[e + 1] * inv * g[e + 1]);
+            if (apply_silu) t = silu2(t);
+            f[e] = t.x;
+            f[e + 1] = t.y;
           }
           uint4 o;
           o.x = pack_bf16(f[0], f[1]); o.y = pack_bf16(f[2], f[3]); o.z = pack_bf16(f[4], f[5]); o.w = pack_bf16(f[6], f[7]);
@@ -90,10 +91,11 @@ rms_silu_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__
         if (c0 < C) {
           float o8[8];
 #pragma unroll
-          for (int e = 0; e < 8; ++e) {
-            float t = f[h][e] * inv * gamma[c0 + e];
-            if (apply_silu) t = t / (1.0f + __expf(-t));
-            o8[e] = t;
+          for (int e = 0; e < 8; e += 2) {
+            float2 t = make_float2(f[h][e] * inv * gamma[c0 + e], f[h][e + 1] * inv * gamma[c0 + e + 1]);
+            if (apply_silu) t = silu2(t);
+            o8[e] = t.x;
+            o8[e + 1] = t.y;
           }
           uint4 o;
           o.x = pack_bf16(o8[0], o8[1]); o.y = pack_bf16(o8[2], o8[3]); o.z = pack_bf16(o8[4], o8[5]); o.w = pack_bf16(o8[6], o8[7]);

@@ -193,7 +193,7 @@ def apply_rotary_emb(x: torch.Tensor, freqs_i: torch.Tensor) -> torch.Tensor:
     x_i = torch.view_as_complex(x[:seq_len].to(torch.float64).reshape(seq_len, n, -1, 2))
     x_i = torch.view_as_real(x_i * freqs_i).flatten(2)
     x_i = torch.cat([x_i, x[seq_len:]])
-    return x_i.to(torch.bfloat16)
+    return x_i.to(torch.float64 if x.dtype == torch.float64 else torch.bfloat16)   # fp64 only in infer_blocks_exact (not a reference mode)
 
 
 def cos_sin_table(freqs_i: torch.Tensor) -> torch.Tensor:
@@ -288,6 +288,15 @@ def infer_blocks(W, num_layers, x, embed0, grid_sizes, freqs, context, num_heads
         freqs_i = compute_freqs(d // 2, grid_sizes, freqs)
         x = infer_block(W, i, x, embed0, freqs_i, context, num_heads, task, attn)
     return x
+
+
+def infer_blocks_exact(W, num_layers, x, embed0, grid_sizes, freqs, context, num_heads, task="t2v"):
+    """The same block stack evaluated in float64 from the same bf16 weights and inputs, with NO intermediate rounding: the "truth" both the
+    reference's bf16 path and the CUDA path approximate.  Not a reference mode - used by the tests that show the CUDA path is as close to
+    the exact result as the reference's own bf16 evaluation is (the honest way to read an element-wise tolerance between two bf16 pipelines)."""
+    Wd = {k: v.to(torch.float64) for k, v in W.items()}
+    return infer_blocks(Wd, num_layers, x.to(torch.float64), embed0.to(torch.float64), grid_sizes, freqs.to(x.device), context.to(torch.float64), num_heads,
+                        task, "torch_sdpa")
 
 
 # ---------------------------------------------------------------------------------------------------------------

@@ -1,8 +1,11 @@
 """GPU parity of the fused DiT block path (host/wan_infer.py over libb200dit.so) against
 (a) the committed fixtures produced by the REAL reference classes on CPU (oracle/gen_golden.py), and
-(b) the oracle restatement executed on the same GPU with flash-attn + torch ops (the reference's own GPU path).
-Tolerance rtol = atol = 1e-2 (BASELINE.json north_star); a small fraction of elements may sit one bf16 ulp apart
-(2^-8 relative > 1e-2 - the reference's CPU and GPU paths differ from each other by the same amount), stated per test."""
+(b) the oracle restatement executed on the same GPU with flash-attn + torch ops (the reference's own GPU path), and
+(c) a float64 evaluation of the same blocks ("truth"): the CUDA path must be as close to it as the reference's bf16 path is.
+Tolerance rtol = atol = 1e-2 (BASELINE.json north_star).  The residual stream has |x| ~ 1-4, where one bf16 ulp is 2^-7 .. 2^-6 absolute
+(0.8 - 1.6 e-2): two correct bf16 pipelines with different fp32 summation orders land one ulp apart on a small fraction of elements, so
+every test states the fraction it admits (set at ~3x what the code measures; the measured values are recorded to
+gpurun_out/parity_numbers.json -> profiles/) and a hard cap on the largest error, and (c) shows the deviation is not a loss of accuracy."""
 import os
 
 import pytest
@@ -24,6 +27,11 @@ def _bad_frac(got, ref, rtol=1e-2, atol=1e-2):
     return ((got - ref).abs() > atol + rtol * ref.abs()).float().mean().item(), (got - ref).abs().max().item()
 
 
+def _err_stats(got, truth):
+    d = (got.double() - truth.double()).abs()
+    return d.max().item(), d.pow(2).mean().sqrt().item()
+
+
 def _build(cfg, W):
     from lightx2v_b200.host.wan_infer import WanTransformerInfer
     from lightx2v_b200.host.wan_weights import WanTransformerWeights
@@ -34,7 +42,7 @@ def _build(cfg, W):
 
 
 @pytest.mark.parametrize("name", ["wan13b_t2v_2blocks", "wan13b_i2v_1block"])
-def test_blocks_vs_reference_fixture(golden_dir, name):
+def test_blocks_vs_reference_fixture(golden_dir, name, record):
     T, meta = _load(os.path.join(golden_dir, name + ".safetensors"))
     dim, heads, ffn, L, task = int(meta["dim"]), int(meta["heads"]), int(meta["ffn"]), int(meta["layers"]), meta["task"]
     cfg = dict(task=task, num_layers=L, num_heads=heads, dim=dim, ffn_dim=ffn, mm_config={})
@@ -47,11 +55,12 @@ def test_blocks_vs_reference_fixture(golden_dir, name):
     torch.cuda.synchronize()
     frac, mx = _bad_frac(out, T["x_out"])
     print(f"{name}: bad_frac={frac:.3e} max_abs_err={mx:.4f}")
-    assert frac < 2e-3, (frac, mx)
-    assert mx < 0.13
+    record(bad_frac=frac, max_abs_err=mx)
+    assert frac < 5e-4, (frac, mx)
+    assert mx < 0.07
 
 
-def test_per_phase_vs_reference_fixture(golden_dir):
+def test_per_phase_vs_reference_fixture(golden_dir, record):
     """Probe points of block 0: self-attention update, cross-attention update, FFN update, each from the fixture's own input."""
     T, meta = _load(os.path.join(golden_dir, "wan13b_t2v_2blocks.safetensors"))
     dim, heads, ffn = int(meta["dim"]), int(meta["heads"]), int(meta["ffn"])
@@ -65,18 +74,21 @@ def test_per_phase_vs_reference_fixture(golden_dir):
     x = T["x_in"].cuda().clone()
     y = infer.infer_self_attn(blk.compute_phases[1], grid, x, None, freqs, sh, sc)          # reference-style return
     f, m = _bad_frac(y, T["probe.self_attn_y"])
-    assert f < 2e-3, ("self_attn_y", f, m)
+    record(self_attn_y_bad_frac=f, self_attn_y_max=m)
+    assert f < 5e-4, ("self_attn_y", f, m)
     x, attn_out = infer.infer_cross_attn(blk.compute_phases[2], x, T["context"].cuda(), y, ga)
     # fused path: x already holds x_after_cross + cross_attn_out
     ref = (T["probe.x_after_cross"].float() + T["probe.cross_attn_out"].float()).bfloat16()
     f, m = _bad_frac(x, ref)
-    assert f < 2e-3, ("cross", f, m)
+    record(cross_bad_frac=f, cross_max=m)
+    assert f < 5e-4, ("cross", f, m)
     yf = infer.infer_ffn(blk.compute_phases[3], x.clone(), None, csh, csc)                    # reference-style return
     f, m = _bad_frac(yf, T["probe.ffn_y"])
+    record(ffn_y_bad_frac=f, ffn_y_max=m)
     assert f < 3e-3, ("ffn_y", f, m)
 
 
-def test_block_vs_oracle_on_gpu_larger():
+def test_block_vs_oracle_on_gpu_larger(record):
     """One 14B-width block (D 5120, 40 heads, F 13824) on 21x6x10 = 1260 tokens, against the oracle restatement run on the
     same GPU with flash-attn + torch ops (the reference's GPU path)."""
     dim, heads, ffn, grid = 5120, 40, 13824, (21, 6, 10)
@@ -91,7 +103,32 @@ def test_block_vs_oracle_on_gpu_larger():
     torch.cuda.synchronize()
     f, m = _bad_frac(out, ref)
     print(f"14B-width block: bad_frac={f:.3e} max_abs_err={m:.4f}")
-    assert f < 2e-3 and m < 0.13, (f, m)
+    record(bad_frac=f, max_abs_err=m)
+    assert f < 1e-3 and m < 0.07, (f, m)
+
+
+@pytest.mark.parametrize("dim,heads,ffn,layers,grid,task", [(1536, 12, 8960, 2, (3, 8, 10), "t2v"), (1536, 12, 8960, 1, (3, 8, 10), "i2v"),
+                                                           (5120, 40, 13824, 1, (21, 6, 10), "t2v")])
+def test_cuda_path_is_as_close_to_fp64_truth_as_the_reference_bf16_path(dim, heads, ffn, layers, grid, task, record):
+    """The waiver behind the admitted bad fractions above: evaluate the same blocks in float64 (no intermediate rounding) and require
+       err(cuda, truth) <= 1.1 x err(reference bf16 path, truth)      in RMS, and <= 1.5 x in max (a single-element statistic),
+    where the reference bf16 path is the oracle restatement run on this GPU with flash-attn + torch ops."""
+    S = grid[0] * grid[1] * grid[2]
+    W = O.synth_block_weights(layers, dim, ffn, task=task, seed=21, device="cuda")
+    x, embed0, context = O.synth_block_inputs(S, dim, task=task, seed=22, device="cuda")
+    freqs = O.wan_freqs_table(dim // heads)
+    truth = O.infer_blocks_exact(W, layers, x.clone(), embed0, grid, freqs, context, heads, task=task)
+    ref = O.infer_blocks(W, layers, x.clone(), embed0, grid, freqs.cuda(), context, heads, task=task, attn="flash_attn2")
+    cfg = dict(task=task, num_layers=layers, num_heads=heads, dim=dim, ffn_dim=ffn, mm_config={})
+    weights, infer = _build(cfg, W)
+    out = infer.infer(weights, torch.tensor([grid]), None, x.clone(), embed0, None, freqs, context)
+    torch.cuda.synchronize()
+    mx_o, rms_o = _err_stats(out, truth)
+    mx_r, rms_r = _err_stats(ref, truth)
+    print(f"{task} D={dim} L={layers}: cuda vs truth max {mx_o:.4f} rms {rms_o:.3e} | reference-bf16 vs truth max {mx_r:.4f} rms {rms_r:.3e}")
+    record(cuda_max=mx_o, cuda_rms=rms_o, ref_bf16_max=mx_r, ref_bf16_rms=rms_r)
+    assert rms_o <= 1.1 * rms_r, (rms_o, rms_r)
+    assert mx_o <= 1.5 * mx_r, (mx_o, mx_r)
 
 
 def test_cross_kv_cache_invalidates_on_new_context():
@@ -190,6 +227,7 @@ def test_teacache_skips_blocks_and_reuses_the_cached_residual():
 
 
 def test_causvid_kv_cache_blocks_vs_reference_fixture(golden_dir):
+    # (numbers of every chunk are printed; the fixture test above records the block-stack numbers)
     """WanTransformerInferCausVid on the CUDA kernels (K/V projected straight into the cache, RoPE at the chunk's frame offset, FMHA with
     sq != sk over the cache prefix) vs the fixture of the REAL reference class: three chunks, two blocks."""
     from lightx2v_b200.host.wan_causvid import WanTransformerInferCausVid
@@ -214,6 +252,6 @@ def test_causvid_kv_cache_blocks_vs_reference_fixture(golden_dir):
         torch.cuda.synchronize()
         frac, mx = _bad_frac(out, T[f"x_out.{c}"])
         print(f"causvid chunk {c}: bad_frac={frac:.3e} max_abs_err={mx:.4f}")
-        assert frac < 2e-3 and mx < 0.13, (c, frac, mx)
+        assert frac < 1e-3 and mx < 0.07, (c, frac, mx)
     fk, mk = _bad_frac(infer.kv_cache[0]["k"].reshape(chunks * ft, dim), T["k_cache.0"])
     assert fk < 2e-3, (fk, mk)
