@@ -65,11 +65,14 @@ MM_KEY = "B200-bf16"
 ATTN_KEY = "b200_fmha"
 
 
+_saved_reference_entries = {}
+
+
 def install_into_lightx2v() -> bool:
     """Register the B200 op classes into a LightX2V checkout that is importable in this process, so that a stock
     LightX2V config selects them with `mm_config.mm_type = "B200-bf16"` and `self_attn_1_type = cross_attn_1_type =
-    cross_attn_2_type = "b200_fmha"`; the hard-coded norm keys are overridden in place (registry_factory.py:25-26).
-    Returns False when LightX2V is not importable (stand-alone use of this package)."""
+    cross_attn_2_type = "b200_fmha"`; the hard-coded norm keys are overridden in place (registry_factory.py:25-26; the entries they
+    replace are remembered for `uninstall_from_lightx2v`).  Returns False when LightX2V is not importable (stand-alone use of this package)."""
     try:
         from lightx2v.utils import registry_factory as rf  # type: ignore
     except Exception:
@@ -83,6 +86,21 @@ def install_into_lightx2v() -> bool:
             rf.MM_WEIGHT_REGISTER.register(cls, key=key)
     if ATTN_KEY not in rf.ATTN_WEIGHT_REGISTER:
         rf.ATTN_WEIGHT_REGISTER.register(ops.FmhaWeightB200, key=ATTN_KEY)
-    rf.RMS_WEIGHT_REGISTER["sgl-kernel"] = ops.RMSWeightB200
-    rf.LN_WEIGHT_REGISTER["Default"] = ops.LNWeightB200
+    for reg_name, key, cls in (("RMS_WEIGHT_REGISTER", "sgl-kernel", ops.RMSWeightB200), ("LN_WEIGHT_REGISTER", "Default", ops.LNWeightB200)):
+        reg = getattr(rf, reg_name)
+        if key in reg and reg[key] is not cls:
+            _saved_reference_entries[(reg_name, key)] = reg[key]
+        reg[key] = cls
     return True
+
+
+def uninstall_from_lightx2v() -> None:
+    """Put the reference's own norm classes back under the keys `install_into_lightx2v` overrode (the added keys stay registered: they do
+    not shadow anything)."""
+    try:
+        from lightx2v.utils import registry_factory as rf  # type: ignore
+    except Exception:
+        return
+    for (reg_name, key), cls in list(_saved_reference_entries.items()):
+        getattr(rf, reg_name)[key] = cls
+        del _saved_reference_entries[(reg_name, key)]
