@@ -112,6 +112,13 @@ int b200_ln_modulate_fp8(const void* x, int64_t ldx, void* q8, int64_t ldq, floa
 int b200_rms_rope_heads(void* x0, int64_t ld0, const void* w0, void* x1, int64_t ld1, const void* w1, int64_t rows, int H,
                         float eps, const void* cos_sin, int64_t rope_rows, b200_stream_t stream);
 
+/* In-place per-head affine LayerNorm over head_dim 64 of x0 (and x1) laid out [rows, H, 64] (weight / bias [64] bf16; F.layer_norm in
+ * bf16), then for rows >= rope_start the pair rotation bf16(x * cos + rotate(x) * sin) in fp32 with table cos_sin[row - rope_start, 32]
+ * float2.  CogVideoX's q/k path: attn1.norm_q / norm_k + apply_rotary_emb on the video tokens of the joint [text ; video] sequence
+ * (lightx2v/models/networks/cogvideox/infer/transformer_infer.py:5-36, 99-103). */
+int b200_ln_rope_heads64(void* x0, int64_t ld0, const void* w0, const void* b0, void* x1, int64_t ld1, const void* w1, const void* b1,
+                         int64_t rows, int H, float eps, const void* cos_sin, int64_t rope_start, b200_stream_t stream);
+
 /* ---- Ulysses sequence parallelism fused into the kernels (peer memory over NVLink / NVSwitch) ------------------------------ */
 
 /* q/k RMSNorm + RoPE (and a copy of v) of the local token shard qkv[rows, 3*D], every 16-byte vector stored directly into the

@@ -54,6 +54,8 @@ int fmha_fwd_d128_scatter(const void* q, long long q_stride_s, const void* k, lo
                           int head_offset, long long sq, long long sk, int heads, float softmax_scale, cudaStream_t stream);
 int rms_rope_heads(void* x0, long long ld0, const void* w0, void* x1, long long ld1, const void* w1, long long rows,
                    int H, float eps, const void* cos_sin, long long rope_rows, cudaStream_t stream);
+int ln_rope_heads64(void* x0, long long ld0, const void* w0, const void* b0, void* x1, long long ld1, const void* w1, const void* b1, long long rows,
+                    int H, float eps, const void* cos_sin, long long rope_start, cudaStream_t stream);
 }  // namespace b200
 
 extern "C" {
@@ -193,6 +195,11 @@ int b200_fmha_fwd_d128_scatter(const void* q, int64_t q_stride_s, const void* k,
 int b200_rms_rope_heads(void* x0, int64_t ld0, const void* w0, void* x1, int64_t ld1, const void* w1, int64_t rows, int H,
                         float eps, const void* cos_sin, int64_t rope_rows, b200_stream_t stream) {
   return b200::rms_rope_heads(x0, ld0, w0, x1, ld1, w1, rows, H, eps, cos_sin, rope_rows, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int b200_ln_rope_heads64(void* x0, int64_t ld0, const void* w0, const void* b0, void* x1, int64_t ld1, const void* w1, const void* b1,
+                         int64_t rows, int H, float eps, const void* cos_sin, int64_t rope_start, b200_stream_t stream) {
+  return b200::ln_rope_heads64(x0, ld0, w0, b0, x1, ld1, w1, b1, rows, H, eps, cos_sin, rope_start, reinterpret_cast<cudaStream_t>(stream));
 }
 
 }  // extern "C"

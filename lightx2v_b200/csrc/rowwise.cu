@@ -432,6 +432,79 @@ int rms_rope_heads(void* x0, long long ld0, const void* w0, void* x1, long long 
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// CogVideoX flavour: affine LayerNorm PER HEAD over head_dim 64 (weight / bias [64], F.layer_norm in bf16 -> bf16) on q and k laid
+// out [rows, H, 64], then for rows >= rope_start (the video tokens behind the text tokens)
+//   out = bf16( x.float() * cos + rotate(x).float() * sin ),  rotate(x)[2i] = -x[2i+1], rotate(x)[2i+1] = x[2i]
+// (lightx2v/models/networks/cogvideox/infer/transformer_infer.py:99-103 and apply_rotary_emb :5-36; fp32 products and sum, one
+// rounding).  Table cs[(row - rope_start), 32] float2 = (cos, sin) of pair i.  8 lanes own one head (8 elements = 4 pairs each).
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(ROW_THREADS)
+ln_rope_heads64_kernel(RmsRopeArgs a, const __nv_bfloat16* __restrict__ b0, const __nv_bfloat16* __restrict__ b1, long long rows, int H, float eps,
+                       const float2* __restrict__ cs, long long rope_start) {
+  const int which = blockIdx.y;
+  const int l8 = threadIdx.x & 7;
+  float w[8], b[8];
+  unpack8(__ldg(reinterpret_cast<const uint4*>(a.w[which]) + l8), w);
+  unpack8(__ldg(reinterpret_cast<const uint4*>(which ? b1 : b0) + l8), b);
+  const long long units = rows * H;
+  for (long long u = (long long)blockIdx.x * (ROW_THREADS / 8) + (threadIdx.x >> 3); u < units; u += (long long)gridDim.x * (ROW_THREADS / 8)) {
+    const long long row = u / H;
+    const int head = (int)(u - row * H);
+    uint4* p = reinterpret_cast<uint4*>(a.x[which] + row * a.ld[which] + head * 64) + l8;
+    float f[8];
+    unpack8(*p, f);
+    float sum = 0.f;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) sum += f[e];
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    const float mean = sum * (1.0f / 64.0f);
+    float sq = 0.f;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) sq += (f[e] - mean) * (f[e] - mean);
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+    const float rstd = rsqrtf(sq * (1.0f / 64.0f) + eps);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) f[e] = bf16_round(fmaf((f[e] - mean) * rstd, w[e], b[e]));
+    if (cs != nullptr && row >= rope_start) {
+      const float2* c = cs + (row - rope_start) * 32 + l8 * 4;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float2 t = __ldg(c + e);
+        const float re = f[2 * e], im = f[2 * e + 1];
+        f[2 * e] = __fadd_rn(__fmul_rn(re, t.x), __fmul_rn(-im, t.y));
+        f[2 * e + 1] = __fadd_rn(__fmul_rn(im, t.x), __fmul_rn(re, t.y));
+      }
+    }
+    *p = pack8(f);
+  }
+}
+
+int ln_rope_heads64(void* x0, long long ld0, const void* w0, const void* b0, void* x1, long long ld1, const void* w1, const void* b1, long long rows,
+                    int H, float eps, const void* cos_sin, long long rope_start, cudaStream_t stream) {
+  B200_CHECK_ARG(x0 && w0 && b0, "b200_ln_rope_heads64: null pointer");
+  B200_CHECK_ARG(rows > 0 && H > 0, "b200_ln_rope_heads64: empty problem");
+  B200_CHECK_ARG(ld0 % 8 == 0 && ld0 >= 64LL * H && (x1 == nullptr || (ld1 % 8 == 0 && ld1 >= 64LL * H && w1 && b1)),
+                 "b200_ln_rope_heads64: bad leading dimension / missing weight");
+  B200_CHECK_ARG(rope_start >= 0, "b200_ln_rope_heads64: negative rope_start");
+  RmsRopeArgs a;
+  a.x[0] = reinterpret_cast<__nv_bfloat16*>(x0);
+  a.w[0] = reinterpret_cast<const __nv_bfloat16*>(w0);
+  a.ld[0] = ld0;
+  a.x[1] = reinterpret_cast<__nv_bfloat16*>(x1);
+  a.w[1] = reinterpret_cast<const __nv_bfloat16*>(w1);
+  a.ld[1] = ld1;
+  const long long want = (rows * H + ROW_THREADS / 8 - 1) / (ROW_THREADS / 8);
+  const long long cap = (long long)num_sms() * 16;
+  dim3 grid((unsigned)(want < cap ? want : cap), x1 ? 2 : 1);
+  ln_rope_heads64_kernel<<<grid, ROW_THREADS, 0, stream>>>(a, reinterpret_cast<const __nv_bfloat16*>(b0), reinterpret_cast<const __nv_bfloat16*>(b1), rows, H,
+                                                         eps, reinterpret_cast<const float2*>(cos_sin), rope_start); note_launch();
+  B200_CHECK_CUDA(cudaGetLastError());
+  return B200_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // Ulysses head scatter fused into the q/k RMSNorm + RoPE pass (and a plain copy for v): instead of normalising in
 // place and then packing + all-to-all'ing, every 16-byte vector is stored STRAIGHT INTO THE PEER GPU that owns its head
 // (NVLink P2P stores through NVSwitch), in the layout the attention kernel reads: recv[dest][token_global][which][h % hp][128].

@@ -345,6 +345,7 @@ class LNWeightB200(_WeightOp):
 
 
 LN_WEIGHT_REGISTER["Default"] = LNWeightB200
+LN_WEIGHT_REGISTER[MM_KEY] = LNWeightB200      # CogVideoX looks its LayerNorms up under the mm_type key (cogvideox/weights/transformers_weights.py:45-48)
 
 
 @ATTN_WEIGHT_REGISTER(ATTN_KEY)

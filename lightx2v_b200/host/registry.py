@@ -86,6 +86,8 @@ def install_into_lightx2v() -> bool:
             rf.MM_WEIGHT_REGISTER.register(cls, key=key)
     if ATTN_KEY not in rf.ATTN_WEIGHT_REGISTER:
         rf.ATTN_WEIGHT_REGISTER.register(ops.FmhaWeightB200, key=ATTN_KEY)
+    if MM_KEY not in rf.LN_WEIGHT_REGISTER:          # CogVideoX indexes the LayerNorm registry with the mm_type string
+        rf.LN_WEIGHT_REGISTER.register(ops.LNWeightB200, key=MM_KEY)
     for reg_name, key, cls in (("RMS_WEIGHT_REGISTER", "sgl-kernel", ops.RMSWeightB200), ("LN_WEIGHT_REGISTER", "Default", ops.LNWeightB200)):
         reg = getattr(rf, reg_name)
         if key in reg and reg[key] is not cls:

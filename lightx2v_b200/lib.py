@@ -33,6 +33,7 @@ SIGNATURES = {
     "b200_quant_fp8_per_token": (_i32, [_ptr, _i64, _ptr, _i64, _ptr, _i64, _i32, _ptr]),
     "b200_ln_modulate_fp8": (_i32, [_ptr, _i64, _ptr, _i64, _ptr, _ptr, _ptr, _ptr, _ptr, _i64, _i32, _f32, _ptr]),
     "b200_rms_rope_heads": (_i32, [_ptr, _i64, _ptr, _ptr, _i64, _ptr, _i64, _i32, _f32, _ptr, _i64, _ptr]),
+    "b200_ln_rope_heads64": (_i32, [_ptr, _i64, _ptr, _ptr, _ptr, _i64, _ptr, _ptr, _i64, _i32, _f32, _ptr, _i64, _ptr]),
     "b200_rms_rope_scatter": (_i32, [_ptr, _i64, _ptr, _ptr, _i64, _i32, _f32, _ptr, _i64, _ptr, _i32, _i32, _i64, _ptr]),
     "b200_fmha_fwd_d128_scatter": (_i32, [_ptr, _i64, _ptr, _i64, _ptr, _i64, _ptr, _i32, _i64, _i64, _i32, _i64, _i64, _i32, _f32, _ptr]),
     "b200_conv3d_cl": (_i32, [_ptr, _i64, _i64, _i64, _ptr, _ptr, _ptr, _i64, _i64, _i64, _ptr, _i64, _i64, _i64, _i32, _i32, _i32, _i32, _i32,
@@ -491,3 +492,25 @@ def rms_rope_heads_(x0: torch.Tensor, w0: torch.Tensor, x1: Optional[torch.Tenso
     rc = load().b200_rms_rope_heads(x0.data_ptr(), x0.stride(0), w0.data_ptr(), _p(x1), 0 if x1 is None else x1.stride(0), _p(w1), rows, H, eps,
                                     _p(cos_sin), rope_rows if cos_sin is not None else 0, _stream())
     _check(rc, "b200_rms_rope_heads")
+
+
+# ---------------------------------------------------------------------------------------------------------------- CogVideoX q/k path
+def ln_rope_heads64_(x0: torch.Tensor, w0: torch.Tensor, b0: torch.Tensor, x1: Optional[torch.Tensor] = None, w1: Optional[torch.Tensor] = None,
+                     b1: Optional[torch.Tensor] = None, *, eps: float = 1e-6, cos_sin: Optional[torch.Tensor] = None, rope_start: int = 0) -> None:
+    """In place: per-head affine LayerNorm (weight / bias [64]) of x0/x1 [rows, H, 64] (row-strided views), pair rotation on rows >= rope_start
+    with cos_sin [rows - rope_start, 32, 2] fp32."""
+    _req(x0, "x0"); _req(w0, "w0"); _req(b0, "b0")
+    rows, H, d = x0.shape
+    if d != 64 or x0.stride(1) != 64:
+        raise B200Error("ln_rope_heads64_: expected [rows, H, 64] with contiguous heads")
+    if x1 is not None:
+        _req(x1, "x1"); _req(w1, "w1"); _req(b1, "b1")
+        if x1.shape != x0.shape or x1.stride(1) != 64:
+            raise B200Error("ln_rope_heads64_: x1 must match x0's shape")
+    if cos_sin is not None:
+        _req(cos_sin, "cos_sin", torch.float32)
+        if not cos_sin.is_contiguous() or tuple(cos_sin.shape[-2:]) != (32, 2) or cos_sin.shape[0] < rows - rope_start:
+            raise B200Error(f"ln_rope_heads64_: cos_sin must be contiguous [>= {rows - rope_start}, 32, 2], got {tuple(cos_sin.shape)}")
+    rc = load().b200_ln_rope_heads64(x0.data_ptr(), x0.stride(0), w0.data_ptr(), b0.data_ptr(), _p(x1), 0 if x1 is None else x1.stride(0), _p(w1), _p(b1),
+                                     rows, H, eps, _p(cos_sin), rope_start, _stream())
+    _check(rc, "b200_ln_rope_heads64")

@@ -512,7 +512,54 @@ def gen_distill_scheduler_fixture():
     print("wan_scheduler_step_distill", sch.timesteps.tolist(), sch.sigmas.tolist())
 
 
+def gen_cogvideox_fixture():
+    """REAL CogvideoxTransformerInfer + CogVideoXBlock weight classes (lightx2v/models/networks/cogvideox/infer/transformer_infer.py:45-145,
+    weights/transformers_weights.py:30-77; mm / LN ops "Default") on CPU: 2 blocks, 12 heads x 64, ff 3072, 40 text + 3x6x8 = 144 video
+    tokens.  Pins oracle/cogvideox_oracle.py (tests/test_oracle_golden.py) and is compared with the CUDA path (tests/test_gpu_cogvideox.py).
+    The rotary table has get_3d_rotary_pos_embed's shape and pair structure with synthetic angles (diffusers is not in the image)."""
+    from safetensors.torch import save_file
+
+    import lightx2v.common.ops  # noqa: F401
+    from lightx2v.common.ops import mm, norm  # noqa: F401
+    from lightx2v.models.networks.cogvideox.infer.transformer_infer import CogvideoxTransformerInfer
+    from lightx2v.models.networks.cogvideox.weights.transformers_weights import CogvideoxTransformerWeights
+
+    from oracle import cogvideox_oracle as C
+
+    layers, heads, hd, ff, Lt, grid = 2, 12, 64, 3072, 40, (3, 6, 8)
+    dim, Li = heads * hd, grid[0] * grid[1] * grid[2]
+    W = C.synth_weights(layers, dim, ff, hd, seed=42)
+    hidden, enc, temb = C.synth_inputs(Lt, Li, dim, seed=7)
+    rotary = C.rotary_table(*grid, head_dim=hd, seed=3)
+    cfg = Cfg(num_layers=layers, transformer_num_layers=layers, transformer_num_attention_heads=heads, transformer_attention_head_dim=hd, text_len=Lt)
+    weights = CogvideoxTransformerWeights(cfg)
+    weights.load_weights(W)
+    infer = CogvideoxTransformerInfer(cfg)
+
+    class Sched:
+        image_rotary_emb = rotary
+
+    infer.set_scheduler(Sched())
+    with torch.no_grad():
+        h_out, e_out = infer.infer(weights, hidden.clone(), enc.clone(), temb)
+        blk = weights.blocks_weights[0]
+        nh, ne, gate, enc_gate = infer.cogvideox_norm1(blk, hidden.clone(), enc.clone(), temb)
+        ah, ae = infer.cogvideox_attention(blk, nh.clone(), ne.clone(), rotary)
+    tensors = {"hidden_in": hidden, "enc_in": enc, "temb": temb, "cos": rotary[0], "sin": rotary[1], "hidden_out": h_out, "enc_out": e_out,
+               "probe.norm1_hidden": nh, "probe.norm1_enc": ne, "probe.gate": gate, "probe.attn_hidden": ah, "probe.attn_enc": ae}
+    meta = {"layers": str(layers), "heads": str(heads), "head_dim": str(hd), "ff": str(ff), "text_len": str(Lt), "grid": ",".join(map(str, grid)),
+            "weights_seed": "42", "inputs_seed": "7", "rotary_seed": "3", "generator": "oracle/gen_golden.py:gen_cogvideox_fixture",
+            "reference": "ModelTC/lightx2v@0591c35e"}
+    save_file({k: v.contiguous() for k, v in tensors.items()}, os.path.join(GOLD, "cogvideox_2blocks.safetensors"), metadata=meta)
+    print("cogvideox_2blocks hidden_out absmax", float(h_out.float().abs().max()), "bytes", os.path.getsize(os.path.join(GOLD, "cogvideox_2blocks.safetensors")))
+
+
 if __name__ == "__main__":
+    if os.environ.get("GOLDEN_ONLY", "") == "cogvideox":
+        install_shims()
+        os.makedirs(GOLD, exist_ok=True)
+        gen_cogvideox_fixture()
+        sys.exit(0)
     if os.environ.get("GOLDEN_ONLY", "") == "distill":
         install_shims()
         os.makedirs(GOLD, exist_ok=True)
@@ -575,3 +622,4 @@ if __name__ == "__main__":
         gen_teacache_fixture()
         gen_causvid_fixture()
         gen_prepost_fixture()
+        gen_cogvideox_fixture()

@@ -164,3 +164,23 @@ def test_prepost_oracle_matches_reference_fixture(golden_dir, task):
     assert torch.equal(embed, g("embed")) and torch.equal(x, g("x")) and torch.equal(embed0, g("embed0")) and torch.equal(ctx, g("context_out"))
     noise = O.post_infer(W, g("x_blocks").clone(), embed, grid)
     assert torch.equal(noise, g("noise_pred"))
+
+
+def test_cogvideox_oracle_matches_reference_fixture(golden_dir):
+    """oracle/cogvideox_oracle.py vs the fixture of the REAL CogvideoxTransformerInfer + CogVideoXBlock classes: bit for bit."""
+    from oracle import cogvideox_oracle as C
+
+    torch.set_num_threads(8)
+    T, meta = _load(os.path.join(golden_dir, "cogvideox_2blocks.safetensors"))
+    layers, heads, hd, ff = int(meta["layers"]), int(meta["heads"]), int(meta["head_dim"]), int(meta["ff"])
+    W = C.synth_weights(layers, heads * hd, ff, hd, seed=int(meta["weights_seed"]))
+    rotary = (T["cos"], T["sin"])
+    grid = [int(v) for v in meta["grid"].split(",")]
+    r2 = C.rotary_table(*grid, head_dim=hd, seed=int(meta["rotary_seed"]))
+    assert torch.equal(r2[0], T["cos"]) and torch.equal(r2[1], T["sin"])
+    nh, ne, gate, _ = C.norm_mod(W, "transformer_blocks.0.", "norm1", T["hidden_in"].clone(), T["enc_in"].clone(), T["temb"])
+    assert torch.equal(nh, T["probe.norm1_hidden"]) and torch.equal(ne, T["probe.norm1_enc"]) and torch.equal(gate, T["probe.gate"])
+    ah, ae = C.attention(W, "transformer_blocks.0.", nh.clone(), ne.clone(), rotary, heads)
+    assert torch.equal(ah, T["probe.attn_hidden"]) and torch.equal(ae, T["probe.attn_enc"])
+    h, e = C.infer_blocks(W, layers, T["hidden_in"].clone(), T["enc_in"].clone(), T["temb"], rotary, heads)
+    assert torch.equal(h, T["hidden_out"]) and torch.equal(e, T["enc_out"])
