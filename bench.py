@@ -697,7 +697,7 @@ def gpu_reference_sample(cfg, S, dev):
             rw = RefWeights(rcfg)
             rw.load(W)
             rinfer = RefInfer(rcfg)
-            gs, sl = torch.tensor([list(grid)]), torch.tensor([S])
+            gs, sl = torch.tensor([list(grid)]), torch.tensor([S], device=dev)
             run = lambda: rinfer.infer(rw, gs, None, x.clone(), embed0, sl, freqs, context)   # noqa: E731
             impl = "real LightX2V classes (baseline/_ref, unmodified): mm Default (torch.addmm), flash_attn2, torch norms"
         run()

@@ -16,6 +16,8 @@
 #include "host_util.cuh"
 #include "ptx.cuh"
 
+#include <stdlib.h>
+
 namespace b200 {
 
 constexpr int CONV_BLOCK_M = 128;            // voxels per tile: 32 (w) x 4 (h)
@@ -28,25 +30,33 @@ constexpr int CONV_STAGING_BYTES = CONV_BLOCK_M * 64 * 2;        // 16 KB (64 ou
 // (96 / 192 output channels) a 128-voxel tile gives only ~290 tensor cycles per pipeline stage, far below the TMA round trip;
 // two sub-tiles double the MMA work per byte of weight traffic and per barrier.
 //
-// Two K-chunk geometries: the Wan widths (96 / 192 / 384 channels) use 32-channel chunks (64-byte rows, SWIZZLE_64B), three per
-// pipeline stage (= one tap of the 96-channel stage); the power-of-two widths of the HunyuanVideo decoder (128 / 256 / 512) use
-// 64-channel chunks (128-byte rows, SWIZZLE_128B), one per stage, four stages.
-template <int BLOCK_N>
+// K-chunk geometries.  The TMA unit retires ~0.75 box rows per clock per SM whatever their width (round 2: the 128-byte-row GEMM
+// tiles and the 64-byte-row tiles below stall at the same rows / clock), so a stage should be made of 128-byte rows wherever the
+// channel count allows:
+//   CONV_WIDE    64-channel chunks (128-byte rows, SWIZZLE_128B), one per stage, four stages: cin % 64 == 0 (192 / 384 channels of the
+//                Wan decoder, 128 / 256 / 512 of the HunyuanVideo decoder);
+//   CONV_MIXED96 cin % 96 == 0 but not % 64 (the 96-channel stage of the Wan decoder): a stage is one 96-channel group of one tap,
+//                held as a 64-channel SWIZZLE_128B tile plus a 32-channel SWIZZLE_64B tile (two tensor maps over the same tensor);
+//   CONV_NARROW  32-channel chunks (64-byte rows, SWIZZLE_64B), three per stage: everything else (cin = 32 latent stem).
+enum : int { CONV_NARROW = 0, CONV_WIDE = 1, CONV_MIXED96 = 2 };
+
+template <int BLOCK_N, int MODE>
 struct ConvCfg {
-  static constexpr bool kWide = (BLOCK_N == 128 || BLOCK_N == 256);
-  static constexpr int kKC = kWide ? 64 : 32;                  // channels per K-chunk
-  static constexpr int kChunks = kWide ? 1 : 3;                // chunks per pipeline stage
-  static constexpr int kStages = kWide ? 4 : 3;
+  static constexpr int kMode = MODE;
+  static constexpr int kStages = MODE == CONV_WIDE ? 4 : 3;
   static constexpr int kMSub = (BLOCK_N <= 128) ? 2 : 1;
-  static constexpr int kAChunkBytes = CONV_BLOCK_M * kKC * 2;  // 8 KB / 16 KB
-  static constexpr int kBChunkBytes = BLOCK_N * kKC * 2;
-  static constexpr int kStageBytes = kChunks * (kMSub * kAChunkBytes + kBChunkBytes);
+  static constexpr int kKStage = MODE == CONV_NARROW ? 96 : (MODE == CONV_WIDE ? 64 : 96);   // channels of K consumed per pipeline stage
+  static constexpr int kASubBytes = CONV_BLOCK_M * kKStage * 2;        // A bytes per sub-tile per stage (24 / 16 / 24 KB)
+  static constexpr int kBBytes = BLOCK_N * kKStage * 2;                // B bytes per stage
+  static constexpr int kStageBytes = kMSub * kASubBytes + kBBytes;
   static constexpr int kAccCols = kMSub * BLOCK_N;                       // TMEM columns of one accumulator stage
   static constexpr int kTmemCols = (2 * kAccCols <= 128) ? 128 : (2 * kAccCols <= 256 ? 256 : 512);
   // epilogue staging buffers: two unless that would exceed the 227 KB of shared memory (BLOCK_N = 96 with two sub-tiles)
   static constexpr int kNumStaging = (kStages * kStageBytes + 2 * CONV_STAGING_BYTES + 1280 <= 232448) ? 2 : 1;
   static constexpr int kSmemBytes = kStages * kStageBytes + kNumStaging * CONV_STAGING_BYTES + 1024 + 256;
   static_assert(kSmemBytes <= 232448, "shared memory budget exceeded");
+  static_assert(2 * kAccCols <= 512, "two accumulator stages must fit the 512 TMEM columns");
+  static_assert(kStageBytes % 1024 == 0, "stages must keep the 1024-byte alignment of the swizzle-128B tiles");
 };
 
 struct ConvParams {
@@ -64,15 +74,21 @@ struct ConvParams {
 // 64-byte swizzle, K-major: 8-row groups 512 B apart.
 constexpr uint32_t kDescHiSw64 = (512u >> 4) | (1u << 14) | (4u << 29);
 
-template <int BLOCK_N>
+// tmIn / tmW: the 32-channel (NARROW) or 64-channel (WIDE, MIXED96) boxes; tmIn2 / tmW2: the 32-channel boxes of MIXED96 (unused otherwise).
+template <int BLOCK_N, int MODE>
 __global__ void __launch_bounds__(CONV_THREADS, 1)
-conv3d_igemm_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant__ CUtensorMap tmW,
-                    const __grid_constant__ CUtensorMap tmOut, const ConvParams p) {
-  using Cfg = ConvCfg<BLOCK_N>;
+conv3d_igemm_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmIn2,
+                    const __grid_constant__ CUtensorMap tmW2, const __grid_constant__ CUtensorMap tmOut, const ConvParams p) {
+  using Cfg = ConvCfg<BLOCK_N, MODE>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  constexpr int CONV_KC = Cfg::kKC, CONV_CHUNKS = Cfg::kChunks, CONV_STAGES = Cfg::kStages, CONV_A_CHUNK_BYTES = Cfg::kAChunkBytes;
-  constexpr uint32_t kDescHi = Cfg::kWide ? kDescHiSw128 : kDescHiSw64;
+  constexpr int CONV_STAGES = Cfg::kStages;
+  // sub-tile layout of one stage.  NARROW: three [128 x 32 ch] SW64 chunks per sub-tile (8 KB each), chunk-major: chunk c, sub-tile ms at
+  // (c * kMSub + ms) * 8 KB; B chunks of BLOCK_N * 64 B behind them.  WIDE: one [128 x 64 ch] SW128 tile per sub-tile (16 KB).
+  // MIXED96: [64-ch SW128 tiles of all sub-tiles][32-ch SW64 tiles of all sub-tiles][B 64-ch][B 32-ch].
+  constexpr int A32 = CONV_BLOCK_M * 32 * 2, A64 = CONV_BLOCK_M * 64 * 2;     // 8 KB, 16 KB
+  constexpr int B32 = BLOCK_N * 32 * 2, B64 = BLOCK_N * 64 * 2;
+  constexpr int kAStage = Cfg::kMSub * Cfg::kASubBytes;
   uint8_t* sStage = smem + CONV_STAGES * Cfg::kStageBytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(sStage + Cfg::kNumStaging * CONV_STAGING_BYTES);
   uint64_t* full_bar = bars;
@@ -86,9 +102,11 @@ conv3d_igemm_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_const
   const int tiles_per_frame = p.tiles_w * p.tiles_h;
   const int num_m_tiles = p.T * tiles_per_frame;
   const int num_tiles = num_m_tiles * p.num_n_blocks;
-  const int chunks_per_tap = p.cin / CONV_KC;
-  const int num_chunks = p.ntaps * chunks_per_tap;
-  const int num_stages_k = (num_chunks + CONV_CHUNKS - 1) / CONV_CHUNKS;
+  // K loop.  NARROW: stages of up to three consecutive 32-channel chunks of the flattened (tap, channel) axis.
+  // WIDE / MIXED96: one stage per (tap, group of 64 / 96 channels).
+  const int groups_per_tap = MODE == CONV_NARROW ? p.cin / 32 : p.cin / Cfg::kKStage;
+  const int num_chunks = p.ntaps * groups_per_tap;                         // NARROW: 32-channel chunks; otherwise: stages
+  const int num_stages_k = MODE == CONV_NARROW ? (num_chunks + 2) / 3 : num_chunks;
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmIn);
@@ -131,20 +149,37 @@ conv3d_igemm_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_const
         int n_blk, t, h0, w0;
         tile_coords(tile, n_blk, t, h0, w0);
         for (int ks = 0; ks < num_stages_k; ++ks) {
-          const int c_begin = ks * CONV_CHUNKS;
-          const int c_end = min(c_begin + CONV_CHUNKS, num_chunks);
           mbar_wait(&empty_bar[stage], phase ^ 1);
-          mbar_arrive_expect_tx(&full_bar[stage], (c_end - c_begin) * (Cfg::kMSub * CONV_A_CHUNK_BYTES + Cfg::kBChunkBytes));
           uint8_t* sA = smem + stage * Cfg::kStageBytes;
-          uint8_t* sB = sA + CONV_CHUNKS * Cfg::kMSub * CONV_A_CHUNK_BYTES;
-          for (int c = c_begin; c < c_end; ++c) {
-            const int tap = c / chunks_per_tap;
-            const int cc = (c - tap * chunks_per_tap) * CONV_KC;
+          uint8_t* sB = sA + kAStage;
+          if constexpr (MODE == CONV_NARROW) {
+            const int c_begin = ks * 3;
+            const int c_end = min(c_begin + 3, num_chunks);
+            mbar_arrive_expect_tx(&full_bar[stage], (c_end - c_begin) * (Cfg::kMSub * A32 + B32));
+            for (int c = c_begin; c < c_end; ++c) {
+              const int tap = c / groups_per_tap;
+              const int cc = (c - tap * groups_per_tap) * 32;
+#pragma unroll
+              for (int ms = 0; ms < Cfg::kMSub; ++ms)
+                tma_load_4d(sA + ((c - c_begin) * Cfg::kMSub + ms) * A32, &tmIn, &full_bar[stage], cc, w0 + p.dw[tap], h0 + ms * CONV_BH + p.dh[tap],
+                            t + p.dt[tap]);
+              tma_load_2d(sB + (c - c_begin) * B32, &tmW, &full_bar[stage], c * 32, n_blk * BLOCK_N);
+            }
+          } else {
+            const int tap = ks / groups_per_tap;
+            const int cc = (ks - tap * groups_per_tap) * Cfg::kKStage;
+            mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
 #pragma unroll
             for (int ms = 0; ms < Cfg::kMSub; ++ms)
-              tma_load_4d(sA + ((c - c_begin) * Cfg::kMSub + ms) * CONV_A_CHUNK_BYTES, &tmIn, &full_bar[stage], cc, w0 + p.dw[tap],
-                          h0 + ms * CONV_BH + p.dh[tap], t + p.dt[tap]);
-            tma_load_2d(sB + (c - c_begin) * Cfg::kBChunkBytes, &tmW, &full_bar[stage], c * CONV_KC, n_blk * BLOCK_N);
+              tma_load_4d(sA + ms * A64, &tmIn, &full_bar[stage], cc, w0 + p.dw[tap], h0 + ms * CONV_BH + p.dh[tap], t + p.dt[tap]);
+            tma_load_2d(sB, &tmW, &full_bar[stage], tap * p.cin + cc, n_blk * BLOCK_N);
+            if constexpr (MODE == CONV_MIXED96) {
+#pragma unroll
+              for (int ms = 0; ms < Cfg::kMSub; ++ms)
+                tma_load_4d(sA + Cfg::kMSub * A64 + ms * A32, &tmIn2, &full_bar[stage], cc + 64, w0 + p.dw[tap], h0 + ms * CONV_BH + p.dh[tap],
+                            t + p.dt[tap]);
+              tma_load_2d(sB + B64, &tmW2, &full_bar[stage], tap * p.cin + cc + 64, n_blk * BLOCK_N);
+            }
           }
           if (++stage == CONV_STAGES) {
             stage = 0;
@@ -167,22 +202,37 @@ conv3d_igemm_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_const
       tc_fence_after();
       const uint32_t d_tmem = tb + acc * Cfg::kAccCols;
       for (int ks = 0; ks < num_stages_k; ++ks) {
-        const int nch = min(CONV_CHUNKS, num_chunks - ks * CONV_CHUNKS);
         mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
         const uint32_t a_lo = s_lo0 + stage * (Cfg::kStageBytes >> 4);
-        const uint32_t b_lo = a_lo + ((CONV_CHUNKS * Cfg::kMSub * CONV_A_CHUNK_BYTES) >> 4);
+        const uint32_t b_lo = a_lo + (kAStage >> 4);
+        if constexpr (MODE == CONV_NARROW) {
+          const int nch = min(3, num_chunks - ks * 3);
 #pragma unroll
-        for (int c = 0; c < CONV_CHUNKS; ++c) {
-          if (c < nch) {
+          for (int c = 0; c < 3; ++c) {
+            if (c < nch) {
 #pragma unroll
-            for (int ms = 0; ms < Cfg::kMSub; ++ms) {
+              for (int ms = 0; ms < Cfg::kMSub; ++ms) {
 #pragma unroll
-              for (int k = 0; k < CONV_KC / 16; ++k) {   // K=16 MMAs per chunk: +32 B inside the swizzled row
-                const uint32_t accum = (ks | c | k) != 0 ? 1u : 0u;
-                mma_f16_ss_w(d_tmem + ms * BLOCK_N, a_lo + (c * Cfg::kMSub + ms) * (CONV_A_CHUNK_BYTES >> 4) + 2 * k, kDescHi,
-                             b_lo + c * (Cfg::kBChunkBytes >> 4) + 2 * k, kDescHi, idesc, accum);
+                for (int k = 0; k < 2; ++k) {   // K=16 MMAs per chunk: +32 B inside the swizzled row
+                  const uint32_t accum = (ks | c | k) != 0 ? 1u : 0u;
+                  mma_f16_ss_w(d_tmem + ms * BLOCK_N, a_lo + (c * Cfg::kMSub + ms) * (A32 >> 4) + 2 * k, kDescHiSw64, b_lo + c * (B32 >> 4) + 2 * k,
+                               kDescHiSw64, idesc, accum);
+                }
               }
+            }
+          }
+        } else {
+#pragma unroll
+          for (int ms = 0; ms < Cfg::kMSub; ++ms) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              mma_f16_ss_w(d_tmem + ms * BLOCK_N, a_lo + ms * (A64 >> 4) + 2 * k, kDescHiSw128, b_lo + 2 * k, kDescHiSw128, idesc, (ks | k) != 0 ? 1u : 0u);
+            if constexpr (MODE == CONV_MIXED96) {
+#pragma unroll
+              for (int k = 0; k < 2; ++k)
+                mma_f16_ss_w(d_tmem + ms * BLOCK_N, a_lo + ((Cfg::kMSub * A64 + ms * A32) >> 4) + 2 * k, kDescHiSw64, b_lo + (B64 >> 4) + 2 * k, kDescHiSw64,
+                             idesc, 1u);
             }
           }
         }
@@ -311,11 +361,11 @@ conv3d_igemm_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_const
   }
 }
 
-template <int BLOCK_N>
-static int launch_conv(const CUtensorMap& tmIn, const CUtensorMap& tmW, const CUtensorMap& tmOut, const ConvParams& p,
-                       cudaStream_t stream) {
-  using Cfg = ConvCfg<BLOCK_N>;
-  auto kern = conv3d_igemm_kernel<BLOCK_N>;
+template <int BLOCK_N, int MODE>
+static int launch_conv(const CUtensorMap& tmIn, const CUtensorMap& tmW, const CUtensorMap& tmIn2, const CUtensorMap& tmW2, const CUtensorMap& tmOut,
+                       const ConvParams& p, cudaStream_t stream) {
+  using Cfg = ConvCfg<BLOCK_N, MODE>;
+  auto kern = conv3d_igemm_kernel<BLOCK_N, MODE>;
   static bool attr_set = false;
   if (!attr_set) {
     B200_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
@@ -323,7 +373,7 @@ static int launch_conv(const CUtensorMap& tmIn, const CUtensorMap& tmW, const CU
   }
   const long long num_tiles = (long long)p.T * p.tiles_w * p.tiles_h * p.num_n_blocks;
   const int grid = (int)(num_tiles < num_sms() ? num_tiles : num_sms());
-  kern<<<grid, CONV_THREADS, Cfg::kSmemBytes, stream>>>(tmIn, tmW, tmOut, p); note_launch();
+  kern<<<grid, CONV_THREADS, Cfg::kSmemBytes, stream>>>(tmIn, tmW, tmIn2, tmW2, tmOut, p); note_launch();
   B200_CHECK_CUDA(cudaGetLastError());
   return B200_OK;
 }
@@ -349,34 +399,52 @@ int conv3d_cl(const void* in, long long in_st, long long in_sh, long long in_sw,
   B200_CHECK_ARG(((uintptr_t)in % 16 == 0) && ((uintptr_t)out % 16 == 0) && ((uintptr_t)wt % 16 == 0),
                  "b200_conv3d_cl: pointers must be 16-byte aligned");
 
-  int block_n;
-  if (cout % 256 == 0 && cin % 64 == 0) block_n = 256;
-  else if (cout % 128 == 0 && cin % 64 == 0) block_n = 128;
-  else if (cout % 192 == 0) block_n = 192;
-  else if (cout % 96 == 0) block_n = 96;
-  else if (cout <= 16) block_n = 16;
-  else if (cout % 64 == 0) block_n = 64;
+  int block_n, mode;
+  const bool c64 = cin % 64 == 0, c96 = cin % 96 == 0;
+  if (cout % 256 == 0 && c64) block_n = 256, mode = CONV_WIDE;
+  else if (cout % 128 == 0 && c64) block_n = 128, mode = CONV_WIDE;
+  else if (cout % 192 == 0) block_n = 192, mode = c64 ? CONV_WIDE : (c96 ? CONV_MIXED96 : CONV_NARROW);
+  else if (cout % 96 == 0) block_n = 96, mode = c64 ? CONV_WIDE : (c96 ? CONV_MIXED96 : CONV_NARROW);
+  else if (cout <= 16) block_n = 16, mode = c64 ? CONV_WIDE : (c96 ? CONV_MIXED96 : CONV_NARROW);
+  else if (cout % 64 == 0) block_n = 64, mode = CONV_NARROW;
   else {
     set_last_error("b200_conv3d_cl: unsupported cout %d (need 16, or a multiple of 64 / 96 / 192)", cout);
     return B200_ERR_UNSUPPORTED;
   }
+  {
+    static int force_narrow = -1;      // B200_CONV_NARROW=1: the round-1 32-channel-chunk tiles everywhere they apply (A/B measurements)
+    if (force_narrow < 0) {
+      const char* e = getenv("B200_CONV_NARROW");
+      force_narrow = (e && atoi(e)) ? 1 : 0;
+    }
+    if (force_narrow && block_n != 128 && block_n != 256) mode = CONV_NARROW;
+  }
 
-  const bool wide = block_n == 128 || block_n == 256;
-  const int kc = wide ? 64 : 32;
-  const CUtensorMapSwizzle swz = wide ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
-  CUtensorMap tmIn, tmW, tmOut;
+  const int kc = mode == CONV_NARROW ? 32 : 64;
+  const CUtensorMapSwizzle swz = mode == CONV_NARROW ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B;
+  CUtensorMap tmIn, tmW, tmIn2, tmW2, tmOut;
   int rc;
   {
     uint64_t dims[4] = {(uint64_t)cin, (uint64_t)in_W, (uint64_t)in_H, (uint64_t)in_T};
     uint64_t strides[3] = {(uint64_t)in_sw * 2, (uint64_t)in_sh * 2, (uint64_t)in_st * 2};
     uint32_t box[4] = {(uint32_t)kc, CONV_BW, CONV_BH, 1};
     if ((rc = encode_tmap(&tmIn, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, in, dims, strides, box, swz))) return rc;
+    tmIn2 = tmIn;
+    if (mode == CONV_MIXED96) {
+      uint32_t box2[4] = {32, CONV_BW, CONV_BH, 1};
+      if ((rc = encode_tmap(&tmIn2, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, in, dims, strides, box2, CU_TENSOR_MAP_SWIZZLE_64B))) return rc;
+    }
   }
   {
     uint64_t dims[2] = {(uint64_t)ntaps * cin, (uint64_t)cout};
     uint64_t strides[1] = {(uint64_t)ntaps * cin * 2};
     uint32_t box[2] = {(uint32_t)kc, (uint32_t)block_n};
     if ((rc = encode_tmap(&tmW, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, wt, dims, strides, box, swz))) return rc;
+    tmW2 = tmW;
+    if (mode == CONV_MIXED96) {
+      uint32_t box2[2] = {32, (uint32_t)block_n};
+      if ((rc = encode_tmap(&tmW2, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, wt, dims, strides, box2, CU_TENSOR_MAP_SWIZZLE_64B))) return rc;
+    }
   }
   {
     uint64_t dims[4] = {(uint64_t)cout, (uint64_t)W, (uint64_t)H, (uint64_t)T};
@@ -410,14 +478,23 @@ int conv3d_cl(const void* in, long long in_st, long long in_sh, long long in_sw,
   p.res_sh = res_sh;
   p.res_sw = res_sw;
   p.clamp_out = clamp_out;
-  switch (block_n) {
-    case 256: return launch_conv<256>(tmIn, tmW, tmOut, p, stream);
-    case 128: return launch_conv<128>(tmIn, tmW, tmOut, p, stream);
-    case 192: return launch_conv<192>(tmIn, tmW, tmOut, p, stream);
-    case 96: return launch_conv<96>(tmIn, tmW, tmOut, p, stream);
-    case 64: return launch_conv<64>(tmIn, tmW, tmOut, p, stream);
-    default: return launch_conv<16>(tmIn, tmW, tmOut, p, stream);
-  }
+#define B200_CONV_CASE(BN, MD) \
+  if (block_n == BN && mode == MD) return launch_conv<BN, MD>(tmIn, tmW, tmIn2, tmW2, tmOut, p, stream)
+  B200_CONV_CASE(256, CONV_WIDE);
+  B200_CONV_CASE(128, CONV_WIDE);
+  B200_CONV_CASE(192, CONV_WIDE);
+  B200_CONV_CASE(192, CONV_MIXED96);
+  B200_CONV_CASE(192, CONV_NARROW);
+  B200_CONV_CASE(96, CONV_WIDE);
+  B200_CONV_CASE(96, CONV_MIXED96);
+  B200_CONV_CASE(96, CONV_NARROW);
+  B200_CONV_CASE(64, CONV_NARROW);
+  B200_CONV_CASE(16, CONV_WIDE);
+  B200_CONV_CASE(16, CONV_MIXED96);
+  B200_CONV_CASE(16, CONV_NARROW);
+#undef B200_CONV_CASE
+  set_last_error("b200_conv3d_cl: no tile configuration for cout %d / cin %d", cout, cin);
+  return B200_ERR_UNSUPPORTED;
 }
 
 }  // namespace b200

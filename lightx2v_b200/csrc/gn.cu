@@ -14,12 +14,6 @@ namespace b200 {
 
 constexpr int GN_GROUPS = 32;
 
-__device__ __forceinline__ uint4 ld_nc_v4(const __nv_bfloat16* p) {
-  uint4 v;
-  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
-  return v;
-}
-
 // Deterministic two-level reduction (no atomics: the decode must be reproducible run to run and across tile-parallel ranks):
 // thread -> warp shuffles -> fixed-order sum over the 8 warps -> one partial per block; a second tiny kernel sums the block
 // partials in block order in fp64.
@@ -160,42 +154,45 @@ gn_apply_pad_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restri
       b[e] = 0.f;
     }
   }
+  // One output row (tp, hp) of the padded tensor = Wp voxels = Wp * LPV vectors of 16 bytes, contiguous in y; the source row (t, h) is
+  // contiguous in x.  Blocks take rows grid-stride; inside a row the 256 threads stride over the vectors (LPV divides 256, so every
+  // thread keeps its 8 channels - and its a[], b[] - for the whole kernel).  Index arithmetic is per ROW, not per vector: the previous
+  // version spent two 64-bit divisions per 16-byte vector, ~12 issue slots per element on a pass whose whole budget is ~14.
   const int Hp = H + 2 * ph, Wp = W + 2 * pw;
-  const long long pvox = (long long)(T + pt) * Hp * Wp;
-  const long long stride = (long long)gridDim.x * VPB;
-  constexpr int U = 4;   // independent 16-byte loads in flight per thread: an HBM-bound pass needs several MB outstanding chip-wide
-  for (long long v0 = (long long)blockIdx.x * VPB + sub; v0 < pvox; v0 += U * stride) {
-    uint4 raw[U];
+  const int rows = (T + pt) * Hp;
+  constexpr int VSTEP = 256 / LPV;            // voxels advanced per thread step
+  constexpr int U = 4;                        // independent 16-byte loads in flight per thread
+  for (int r = blockIdx.x; r < rows; r += gridDim.x) {
+    const int tp = r / Hp, hp = r - tp * Hp;
+    const int t = max(tp - pt, 0), h = min(max(hp - ph, 0), H - 1);
+    const __nv_bfloat16* xrow = x + ((long long)t * H + h) * (long long)W * C + l * 8;
+    __nv_bfloat16* yrow = y + (long long)r * Wp * C + l * 8;
+    for (int wp0 = sub; wp0 < Wp; wp0 += U * VSTEP) {
+      uint4 raw[U];
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const long long v = v0 + u * stride;
-      if (v < pvox) {
-        const int wp = (int)(v % Wp);
-        const long long r = v / Wp;
-        const int hp = (int)(r % Hp);
-        const int tp = (int)(r / Hp);
-        const int t = max(tp - pt, 0), h = min(max(hp - ph, 0), H - 1), w = min(max(wp - pw, 0), W - 1);
-        raw[u] = ld_nc_v4(x + (((long long)t * H + h) * W + w) * C + l * 8);
+      for (int u = 0; u < U; ++u) {
+        const int wp = wp0 + u * VSTEP;
+        if (wp < Wp) raw[u] = ld_nc_v4(xrow + (long long)min(max(wp - pw, 0), W - 1) * C);
       }
-    }
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const long long v = v0 + u * stride;
-      if (v < pvox) {
-        float f[8] = {bf16_lo(raw[u].x), bf16_hi(raw[u].x), bf16_lo(raw[u].y), bf16_hi(raw[u].y),
-                      bf16_lo(raw[u].z), bf16_hi(raw[u].z), bf16_lo(raw[u].w), bf16_hi(raw[u].w)};
-        if (sums != nullptr) {
+      for (int u = 0; u < U; ++u) {
+        const int wp = wp0 + u * VSTEP;
+        if (wp < Wp) {
+          float f[8] = {bf16_lo(raw[u].x), bf16_hi(raw[u].x), bf16_lo(raw[u].y), bf16_hi(raw[u].y),
+                        bf16_lo(raw[u].z), bf16_hi(raw[u].z), bf16_lo(raw[u].w), bf16_hi(raw[u].w)};
+          if (sums != nullptr) {
 #pragma unroll
-          for (int e = 0; e < 8; e += 2) {
-            float2 y_ = make_float2(fmaf(f[e], a[e], b[e]), fmaf(f[e + 1], a[e + 1], b[e + 1]));
-            if (apply_silu) y_ = silu2(y_);
-            f[e] = y_.x;
-            f[e + 1] = y_.y;
+            for (int e = 0; e < 8; e += 2) {
+              const float2 y_ = __ffma2_rn(make_float2(f[e], f[e + 1]), make_float2(a[e], a[e + 1]), make_float2(b[e], b[e + 1]));
+              f[e] = y_.x;
+              f[e + 1] = y_.y;
+            }
+            if (apply_silu) silu8(f);
           }
+          uint4 o;
+          o.x = pack_bf16(f[0], f[1]); o.y = pack_bf16(f[2], f[3]); o.z = pack_bf16(f[4], f[5]); o.w = pack_bf16(f[6], f[7]);
+          *reinterpret_cast<uint4*>(yrow + (long long)wp * C) = o;
         }
-        uint4 o;
-        o.x = pack_bf16(f[0], f[1]); o.y = pack_bf16(f[2], f[3]); o.z = pack_bf16(f[4], f[5]); o.w = pack_bf16(f[6], f[7]);
-        *reinterpret_cast<uint4*>(y + v * C + l * 8) = o;
       }
     }
   }
@@ -209,11 +206,9 @@ int gn_apply_pad_cl(const void* x, void* y, const double* sums, const float* gam
   const auto* xp = reinterpret_cast<const __nv_bfloat16*>(x);
   auto* yp = reinterpret_cast<__nv_bfloat16*>(y);
   const double inv_count = 1.0 / ((double)T * H * W * (C / GN_GROUPS));
-  const long long pvox = (long long)(T + pt) * (H + 2 * ph) * (W + 2 * pw);
-  const int vpb = 256 / (C / 8 > 0 ? C / 8 : 1);
-  const long long passes = (pvox + vpb - 1) / vpb;
+  const long long rows = (long long)(T + pt) * (H + 2 * ph);
   const int max_blocks = num_sms() * 8;
-  const int blocks = (int)(passes < max_blocks ? passes : max_blocks);
+  const int blocks = (int)(rows < max_blocks ? rows : max_blocks);
 #define B200_GN_LAUNCH(CC) \
   gn_apply_pad_kernel<CC><<<blocks, 256, 0, stream>>>(xp, yp, sums, gamma, beta, eps, inv_count, T, H, W, pt, ph, pw, apply_silu)
   switch (C) {

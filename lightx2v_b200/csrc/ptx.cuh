@@ -463,16 +463,41 @@ __device__ __forceinline__ float rcp_approx(float x) {
   return y;
 }
 
-// SiLU of two values, t / (1 + e^-t), sized for HBM-bound element-wise passes: at 4 bytes of traffic per element a B200 SM must
-// retire ~9 elements per clock, and `t / (1.f + __expf(-t))` costs two MUFU operations (ex2 + rcp) plus a Newton division per element
-// against a MUFU rate of 16 / clk / SM.  Here the exponential runs on the FMA pipe (exp2_poly2, relative error 7.5e-5, far below
-// the 2^-9 of the bf16 result) and only the reciprocal uses the MUFU.
-__device__ __forceinline__ float2 silu2(float2 t) {
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+// SiLU t / (1 + e^-t) sized for HBM-bound element-wise passes.  At 4 bytes of traffic per element a B200 SM must retire ~9 elements per
+// clock, i.e. the whole per-element instruction budget is ~14 issue slots; `t / (1.f + __expf(-t))` alone costs ~11 (the IEEE division
+// expands into a Newton iteration with a slow path) plus two MUFU operations against a MUFU rate of 16 / clk / SM.
+//   silu_fast : ex2.approx + rcp.approx, 5 instructions, 2 MUFU (relative error ~2^-21, far below the 2^-9 of the bf16 result);
+//               saturates correctly: t -> -inf gives t * rcp(inf) = -0, t -> +inf gives t * rcp(1) = t.
+//   silu2_poly: the exponential on the FMA pipe (exp2_poly2, relative error 7.5e-5), one MUFU per element; callers mix the two so that
+//               the MUFU stays below its rate while the issue slots stay below theirs.
+__device__ __forceinline__ float silu_fast(float t) { return t * rcp_approx(1.0f + ex2_approx(t * -1.4426950408889634f)); }
+__device__ __forceinline__ float2 silu2_fast(float2 t) { return make_float2(silu_fast(t.x), silu_fast(t.y)); }
+__device__ __forceinline__ float2 silu2_poly(float2 t) {
   float2 x = __fmul2_rn(t, make_float2(-1.4426950408889634f, -1.4426950408889634f));
   x.x = fminf(x.x, 126.f);
   x.y = fminf(x.y, 126.f);
   const float2 e = exp2_poly2(x);
   return make_float2(t.x * rcp_approx(1.0f + e.x), t.y * rcp_approx(1.0f + e.y));
+}
+// 8 values: one pair through the polynomial, three through the MUFU (1.75 MUFU operations per element)
+__device__ __forceinline__ void silu8(float* f) {
+  const float2 a = silu2_poly(make_float2(f[0], f[1]));
+  f[0] = a.x; f[1] = a.y;
+#pragma unroll
+  for (int e = 2; e < 8; ++e) f[e] = silu_fast(f[e]);
+}
+
+// streaming 16-byte load that does not allocate in L1 (read-once data of the HBM-bound passes)
+__device__ __forceinline__ uint4 ld_nc_v4(const __nv_bfloat16* p) {
+  uint4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+  return v;
 }
 
 // ----------------------------------------------------------------------------------------------

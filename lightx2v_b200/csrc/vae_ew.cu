@@ -8,20 +8,21 @@
 
 namespace b200 {
 
-// One warp handles `VPW` voxels per iteration; each lane owns 8 channels (16 bytes); C/8 lanes per voxel.
+// C = 96 / 192: 16 / 32 lanes reserved per voxel (12 / 24 of them own 8 channels = 16 bytes each), 2 / 1 voxels per warp pass, U = 4
+// passes in flight.  C = 384: a warp takes two voxels per pass = 96 vectors of 16 bytes = exactly three per lane (vector v = lane + 32 j,
+// voxel v / 48), so every lane is busy and 48 bytes per lane are in flight per pass.  Instruction budget: see silu_fast in ptx.cuh.
 template <int C>
 __global__ void __launch_bounds__(256)
 rms_silu_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, const float* __restrict__ gamma,
                 long long voxels, int apply_silu) {
-  constexpr int LPV = C / 8;                 // lanes per voxel
-  constexpr int G = (LPV <= 16) ? 16 : ((LPV <= 32) ? 32 : 64);   // lanes reserved per voxel (power of two)
-  static_assert(G <= 64, "C too large");
-  constexpr int VPW = (G <= 32) ? 32 / G : 1;                      // voxels per warp pass
   const int lane = threadIdx.x & 31;
   const long long warp_global = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
   const float sqrt_c = sqrtf((float)C);
-  if constexpr (G <= 32) {
+  if constexpr (C <= 256) {
+    constexpr int LPV = C / 8;                 // lanes per voxel
+    constexpr int G = (LPV <= 16) ? 16 : 32;   // lanes reserved per voxel (power of two)
+    constexpr int VPW = 32 / G;                // voxels per warp pass
     const int sub = lane / G, l = lane % G;
     float g[8];
     if (l < LPV) {
@@ -36,7 +37,7 @@ rms_silu_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__
       for (int u = 0; u < U; ++u) {
         const long long v = v0 + u * stride + sub;
         raw[u] = make_uint4(0, 0, 0, 0);
-        if (v < voxels && l < LPV) raw[u] = *reinterpret_cast<const uint4*>(x + v * C + l * 8);
+        if (v < voxels && l < LPV) raw[u] = ld_nc_v4(x + v * C + l * 8);
       }
 #pragma unroll
       for (int u = 0; u < U; ++u) {
@@ -44,20 +45,22 @@ rms_silu_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__
         const bool ok = v < voxels && l < LPV;
         float f[8] = {bf16_lo(raw[u].x), bf16_hi(raw[u].x), bf16_lo(raw[u].y), bf16_hi(raw[u].y),
                       bf16_lo(raw[u].z), bf16_hi(raw[u].z), bf16_lo(raw[u].w), bf16_hi(raw[u].w)};
-        float ss = 0.f;
+        float2 s2 = make_float2(0.f, 0.f);
 #pragma unroll
-        for (int e = 0; e < 8; ++e) ss += f[e] * f[e];
+        for (int e = 0; e < 8; e += 2) s2 = __ffma2_rn(make_float2(f[e], f[e + 1]), make_float2(f[e], f[e + 1]), s2);
+        float ss = s2.x + s2.y;
 #pragma unroll
         for (int o = G / 2; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
-        const float inv = 1.0f / fmaxf(sqrtf(ss), 1e-12f);        // F.normalize: x / max(||x||_2, eps)
+        const float inv = rcp_approx(fmaxf(sqrtf(ss), 1e-12f));        // F.normalize: x / max(||x||_2, eps)
         if (ok) {
+          const float2 inv2 = make_float2(inv, inv);
 #pragma unroll
           for (int e = 0; e < 8; e += 2) {
-            float2 t = make_float2(f[e] * inv * g[e], f[e + 1] * inv * g[e + 1]);
-            if (apply_silu) t = silu2(t);
+            const float2 t = __fmul2_rn(__fmul2_rn(make_float2(f[e], f[e + 1]), inv2), make_float2(g[e], g[e + 1]));
             f[e] = t.x;
             f[e + 1] = t.y;
           }
+          if (apply_silu) silu8(f);
           uint4 o;
           o.x = pack_bf16(f[0], f[1]); o.y = pack_bf16(f[2], f[3]); o.z = pack_bf16(f[4], f[5]); o.w = pack_bf16(f[6], f[7]);
           *reinterpret_cast<uint4*>(y + v * C + l * 8) = o;
@@ -65,41 +68,67 @@ rms_silu_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__
       }
     }
   } else {
-    // C = 384: 48 lanes' worth of data per voxel -> each lane takes 2 x 8 channels (lanes 0..23 active twice)
-    for (long long v = warp_global; v < voxels; v += nwarps) {
-      float f[2][8];
-      float ss = 0.f;
+    static_assert(C == 384, "the three-vectors-per-lane mapping is written for C = 384");
+    // vector v = lane + 32 j (j = 0, 1, 2) of a voxel PAIR: voxel v / 48, channels 8 (v % 48) ..
+    int vox_of[3], c0_of[3];
+    float g[3][8];
 #pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        const int c0 = (lane + h * 32) * 8;
-        uint4 raw = make_uint4(0, 0, 0, 0);
-        if (c0 < C) raw = *reinterpret_cast<const uint4*>(x + v * C + c0);
-        const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
+    for (int j = 0; j < 3; ++j) {
+      const int v = lane + 32 * j;
+      vox_of[j] = v / 48;
+      c0_of[j] = (v % 48) * 8;
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          f[h][2 * e] = bf16_lo(w[e]);
-          f[h][2 * e + 1] = bf16_hi(w[e]);
-          ss += f[h][2 * e] * f[h][2 * e] + f[h][2 * e + 1] * f[h][2 * e + 1];
+      for (int e = 0; e < 8; ++e) g[j][e] = gamma[c0_of[j] + e] * sqrt_c;
+    }
+    constexpr int U = 2;
+    const long long pairs = (voxels + 1) / 2;
+    for (long long p0 = warp_global; p0 < pairs; p0 += U * nwarps) {
+      uint4 raw[U][3];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const long long pr = p0 + u * nwarps;
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+          const long long v = 2 * pr + vox_of[j];
+          raw[u][j] = make_uint4(0, 0, 0, 0);
+          if (pr < pairs && v < voxels) raw[u][j] = ld_nc_v4(x + v * C + c0_of[j]);
         }
       }
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
-      const float inv = sqrt_c / fmaxf(sqrtf(ss), 1e-12f);
+      for (int u = 0; u < U; ++u) {
+        const long long pr = p0 + u * nwarps;
+        float f[3][8];
+        float s0 = 0.f, s1 = 0.f;     // partial sums of squares of voxel 0 / voxel 1 of the pair
 #pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        const int c0 = (lane + h * 32) * 8;
-        if (c0 < C) {
-          float o8[8];
+        for (int j = 0; j < 3; ++j) {
+          const uint32_t w[4] = {raw[u][j].x, raw[u][j].y, raw[u][j].z, raw[u][j].w};
+          float ss = 0.f;
 #pragma unroll
-          for (int e = 0; e < 8; e += 2) {
-            float2 t = make_float2(f[h][e] * inv * gamma[c0 + e], f[h][e + 1] * inv * gamma[c0 + e + 1]);
-            if (apply_silu) t = silu2(t);
-            o8[e] = t.x;
-            o8[e + 1] = t.y;
+          for (int e = 0; e < 4; ++e) {
+            f[j][2 * e] = bf16_lo(w[e]);
+            f[j][2 * e + 1] = bf16_hi(w[e]);
+            ss += f[j][2 * e] * f[j][2 * e] + f[j][2 * e + 1] * f[j][2 * e + 1];
           }
-          uint4 o;
-          o.x = pack_bf16(o8[0], o8[1]); o.y = pack_bf16(o8[2], o8[3]); o.z = pack_bf16(o8[4], o8[5]); o.w = pack_bf16(o8[6], o8[7]);
-          *reinterpret_cast<uint4*>(y + v * C + c0) = o;
+          if (vox_of[j] == 0) s0 += ss; else s1 += ss;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          s0 += __shfl_xor_sync(0xffffffffu, s0, o);
+          s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+        }
+        const float inv0 = rcp_approx(fmaxf(sqrtf(s0), 1e-12f)), inv1 = rcp_approx(fmaxf(sqrtf(s1), 1e-12f));
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+          const long long v = 2 * pr + vox_of[j];
+          if (pr < pairs && v < voxels) {
+            const float inv = vox_of[j] == 0 ? inv0 : inv1;
+#pragma unroll
+            for (int e = 0; e < 8; ++e) f[j][e] = f[j][e] * inv * g[j][e];
+            if (apply_silu) silu8(f[j]);
+            uint4 o;
+            o.x = pack_bf16(f[j][0], f[j][1]); o.y = pack_bf16(f[j][2], f[j][3]); o.z = pack_bf16(f[j][4], f[j][5]); o.w = pack_bf16(f[j][6], f[j][7]);
+            *reinterpret_cast<uint4*>(y + v * C + c0_of[j]) = o;
+          }
         }
       }
     }

@@ -112,7 +112,7 @@ def test_b200_infer_vs_the_references_own_gpu_path(ref, record):
     rcfg = R.ref_config(dim, heads, ffn, 1, "t2v", mm_type=None, attn_type="flash_attn2")
     rw = RefWeights(rcfg)
     rw.load(W)
-    want = RefInfer(rcfg).infer(rw, g, None, x.clone(), embed0, torch.tensor([S]), freqs.cuda(), context)
+    want = RefInfer(rcfg).infer(rw, g, None, x.clone(), embed0, torch.tensor([S], device="cuda"), freqs.cuda(), context)   # seq_lens on the device: flash-attn cu_seqlens derive from it
     cfg = dict(task="t2v", num_layers=1, num_heads=heads, dim=dim, ffn_dim=ffn, mm_config={})
     weights = WanTransformerWeights(cfg)
     weights.load(W)
