@@ -246,8 +246,9 @@ int b200_rms_silu_cl(const void* x, void* y, const float* gamma, int64_t voxels,
 int b200_latent_to_cl(const float* z, void* out, const float* mean, const float* inv_std, int64_t voxels, int CZ, int CP,
                       b200_stream_t stream);
 
-/* channels-last bf16 [voxels, CP] (3 valid channels) -> fp32 [3, voxels]  (the `.float()` video tensor, vae.py:951). */
-int b200_cl_to_video(const void* in, float* out, int64_t voxels, int CP, b200_stream_t stream);
+/* channels-last bf16 [voxels, CP] (3 valid channels) -> fp32 [3, voxels]  (the `.float()` video tensor, vae.py:951); the three channel planes
+ * are out_channel_stride elements apart (0 = voxels), so a chunk of frames can be written into its slot of the full [3, T, H, W] video. */
+int b200_cl_to_video(const void* in, float* out, int64_t voxels, int CP, int64_t out_channel_stride, b200_stream_t stream);
 
 #ifdef __cplusplus
 }

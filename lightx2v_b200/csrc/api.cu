@@ -45,7 +45,7 @@ int gn_apply_pad_cl(const void* x, void* y, const double* sums, const float* gam
 int rms_silu_cl(const void* x, void* y, const float* gamma, long long voxels, int C, int apply_silu, cudaStream_t stream);
 int latent_to_cl(const float* z, void* out, const float* mean, const float* inv_std, long long voxels, int CZ, int CP,
                  cudaStream_t stream);
-int cl_to_video(const void* in, float* out, long long voxels, int CP, cudaStream_t stream);
+int cl_to_video(const void* in, float* out, long long voxels, int CP, long long out_channel_stride, cudaStream_t stream);
 int rms_rope_scatter(const void* qkv, long long ld, const void* wq, const void* wk, long long rows, int D, float eps,
                      const void* cos_sin, long long rope_rows, void* const* peers, int world, int rank,
                      long long rows_per_rank, cudaStream_t stream);
@@ -174,8 +174,8 @@ int b200_latent_to_cl(const float* z, void* out, const float* mean, const float*
   return b200::latent_to_cl(z, out, mean, inv_std, voxels, CZ, CP, reinterpret_cast<cudaStream_t>(stream));
 }
 
-int b200_cl_to_video(const void* in, float* out, int64_t voxels, int CP, b200_stream_t stream) {
-  return b200::cl_to_video(in, out, voxels, CP, reinterpret_cast<cudaStream_t>(stream));
+int b200_cl_to_video(const void* in, float* out, int64_t voxels, int CP, int64_t out_channel_stride, b200_stream_t stream) {
+  return b200::cl_to_video(in, out, voxels, CP, out_channel_stride, reinterpret_cast<cudaStream_t>(stream));
 }
 
 int b200_rms_rope_scatter(const void* qkv, int64_t ld, const void* wq, const void* wk, int64_t rows, int D, float eps,

@@ -174,19 +174,22 @@ int latent_to_cl(const float* z, void* out, const float* mean, const float* inv_
   return B200_OK;
 }
 
-// in [voxels, CP] bf16 (first 3 channels valid) -> out [3, voxels] fp32
-__global__ void cl_to_video_kernel(const __nv_bfloat16* __restrict__ in, float* __restrict__ out, long long voxels, int CP) {
+// in [voxels, CP] bf16 (first 3 channels valid) -> out [3, voxels] fp32, channel planes `cstride` elements apart (>= voxels: a frame
+// range of a larger [3, T, H, W] video when the decode is chunked along T)
+__global__ void cl_to_video_kernel(const __nv_bfloat16* __restrict__ in, float* __restrict__ out, long long voxels, int CP, long long cstride) {
   const long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (v >= voxels) return;
   const __nv_bfloat16* p = in + v * CP;
   out[v] = __bfloat162float(p[0]);
-  out[voxels + v] = __bfloat162float(p[1]);
-  out[2 * voxels + v] = __bfloat162float(p[2]);
+  out[cstride + v] = __bfloat162float(p[1]);
+  out[2 * cstride + v] = __bfloat162float(p[2]);
 }
 
-int cl_to_video(const void* in, float* out, long long voxels, int CP, cudaStream_t stream) {
+int cl_to_video(const void* in, float* out, long long voxels, int CP, long long out_channel_stride, cudaStream_t stream) {
   B200_CHECK_ARG(in && out && voxels > 0 && CP >= 3, "b200_cl_to_video: bad arguments");
-  cl_to_video_kernel<<<(unsigned)((voxels + 255) / 256), 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(in), out, voxels, CP); note_launch();
+  const long long cstride = out_channel_stride > 0 ? out_channel_stride : voxels;
+  B200_CHECK_ARG(cstride >= voxels, "b200_cl_to_video: channel stride %lld smaller than the plane (%lld voxels)", cstride, voxels);
+  cl_to_video_kernel<<<(unsigned)((voxels + 255) / 256), 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(in), out, voxels, CP, cstride); note_launch();
   B200_CHECK_CUDA(cudaGetLastError());
   return B200_OK;
 }

@@ -8,7 +8,10 @@ two special cases that are reproduced here:
   * `upsample3d`: the first latent frame skips the temporal convolution and yields one frame; every later frame t yields two
     frames from time_conv(f[t-2], f[t-1], f[t]) where the history starts at frame 1 (frames < 1 read as zero) (vae.py:107-138);
   * every other conv simply sees zeros before frame 0 (vae.py:35-44).
-Whole-sequence processing turns 21 x ~35 small cuDNN launches + torch.cat cache copies into ~60 large tensor-core launches.
+Processing CHUNKS of latent frames (default 3, `chunk_frames`) instead of one turns 21 x ~35 small cuDNN launches + torch.cat cache
+copies into 7 x ~60 large tensor-core launches, while every temporal convolution carries the last two frames of its input from chunk to
+chunk - the reference's feat_cache protocol with a chunk size > 1 - so peak memory is bounded by the chunk (~10 GB at 720p) instead of
+the whole 81-frame sequence (67 GB in round 1).  `chunk_frames=None` decodes the whole sequence in one piece (bit-identical result).
 Further fusions: the 3x3 conv on the nearest-2x-upsampled image is evaluated as four 2x2 phase convolutions on the ORIGINAL
 resolution (pre-summed weights): 2.25x fewer FLOPs and the 4x larger upsampled tensor is never materialised; residual adds,
 bias and the final clamp live in the conv epilogue.  Activations are channels-last bf16 (the reference computes in fp32 / TF32).
@@ -56,6 +59,8 @@ class _Conv:
             bias[:cout] = b.float().cpu()
         self.bias = bias.to(torch.bfloat16).to(device)
         self.taps = taps
+        self.taps_hist = [(dt + 2, dh, dw) for dt, dh, dw in taps]     # the same taps addressed into a view that starts two frames earlier
+        self.temporal = any(dt != 0 for dt, _, _ in taps)
         self.cin, self.cout = cin_p, cout_p
 
     def __call__(self, x: torch.Tensor, out: Optional[torch.Tensor] = None, residual: Optional[torch.Tensor] = None, clamp: bool = False):
@@ -63,6 +68,15 @@ class _Conv:
         if out is None:
             out = torch.empty((T, H, W, self.cout), dtype=torch.bfloat16, device=x.device)
         return lib.conv3d_cl(x, self.weight, self.bias, out, self.taps, residual=residual, clamp_out=clamp)
+
+    def causal(self, buf: torch.Tensor, out: Optional[torch.Tensor] = None, residual: Optional[torch.Tensor] = None, clamp: bool = False):
+        """buf [T + 2, H, W, cin] = the two input frames that precede the chunk (zeros at the start of the sequence: the causal padding of
+        CausalConv3d, vae.py:35-44; the cached frames of the reference's feat_cache afterwards, :203-217) followed by the chunk's T frames
+        -> the convolution's output for those T frames."""
+        Tp, H, W, _ = buf.shape
+        if out is None:
+            out = torch.empty((Tp - 2, H, W, self.cout), dtype=torch.bfloat16, device=buf.device)
+        return lib.conv3d_cl_padded(buf, self.weight, self.bias, out, self.taps_hist, residual=residual, clamp_out=clamp)
 
 
 class _UpsampleConv:
@@ -96,9 +110,12 @@ class _UpsampleConv:
 
 class WanVAEDecoderB200:
     def __init__(self, state_dict: Dict[str, torch.Tensor], device="cuda", dim=96, z_dim=16, dim_mult=(1, 2, 4, 4), num_res_blocks=2,
-                 temperal_upsample=(True, True, False)):
+                 temperal_upsample=(True, True, False), chunk_frames: Optional[int] = 3):
         W = state_dict
         self.device = torch.device(device)
+        self.chunk_frames = chunk_frames           # latent frames decoded per pass (None: the whole sequence at once)
+        self._hist: Dict[int, torch.Tensor] = {}   # id(conv) -> last two frames of that conv's input (chunked decode only)
+        self._streaming = False
         self.z_dim = z_dim
         dev = self.device
         dims = [dim * u for u in [dim_mult[-1]] + list(dim_mult[::-1])]
@@ -143,12 +160,32 @@ class WanVAEDecoderB200:
         self.head_g = g("decoder.head.0.gamma")
         self.head = _Conv(W["decoder.head.2.weight"], W["decoder.head.2.bias"], dev, cout_pad=16)
 
+    # ------------------------------------------------------------------ temporal convolutions with a two-frame history
+    def _tconv(self, conv: _Conv, T: int, H: int, W: int, fill, **kw) -> torch.Tensor:
+        """Run the causal convolution `conv` on a chunk of T frames whose input is produced by `fill(dst)` (dst = the [T, H, W, cin] slot the
+        producer writes into - no concatenation copy).  Whole-sequence mode: plain zero-padded convolution.  Streaming mode: the two frames
+        before the chunk come from the previous chunk (zeros for the first one) and the chunk's last two frames are kept for the next."""
+        dev = self.device
+        if not self._streaming:
+            x = torch.empty((T, H, W, conv.cin), dtype=torch.bfloat16, device=dev)
+            fill(x)
+            return conv(x, **kw)
+        buf = torch.empty((T + 2, H, W, conv.cin), dtype=torch.bfloat16, device=dev)
+        prev = self._hist.get(id(conv))
+        if prev is None:
+            buf[:2].zero_()
+        else:
+            buf[:2].copy_(prev)
+        fill(buf[2:])
+        self._hist[id(conv)] = buf[-2:].clone()
+        return conv.causal(buf, **kw)
+
     # ------------------------------------------------------------------ blocks
-    @staticmethod
-    def _res(d, x):
+    def _res(self, d, x):
+        T, H, W, _ = x.shape
         h = x if d["sc"] is None else d["sc"](x)
-        a = d["c1"](lib.rms_silu_cl(x, d["g0"]))
-        return d["c2"](lib.rms_silu_cl(a, d["g1"]), residual=h)
+        a = self._tconv(d["c1"], T, H, W, lambda dst: lib.rms_silu_cl(x, d["g0"], out=dst))
+        return self._tconv(d["c2"], T, H, W, lambda dst: lib.rms_silu_cl(a, d["g1"], out=dst), residual=h)
 
     def _attention(self, x):
         """AttentionBlock.forward (vae.py:245-262): per-frame single-head attention over the H*W positions, width C."""
@@ -159,15 +196,22 @@ class WanVAEDecoderB200:
         o = F.scaled_dot_product_attention(q, k, v).squeeze(1).reshape(T, H, W, C).contiguous()
         return self.attn["proj"](o, residual=x)
 
-    @staticmethod
-    def _upsample(up, x):
+    def _upsample(self, up, x, first_chunk: bool = True):
+        """Resample (vae.py:70-159).  upsample3d: the first latent frame of the SEQUENCE skips the temporal convolution and yields one
+        frame ("Rep", :110-112); every later frame t yields two frames from time_conv over (f[t-2], f[t-1], f[t]) where the history
+        starts at frame 1 (earlier frames read as zero).  `first_chunk` says whether x[0] is that first frame."""
         if up["time"] is not None:
             T, H, W, C = x.shape
-            y = torch.empty((1 + 2 * (T - 1), H, W, C), dtype=torch.bfloat16, device=x.device)
-            y[0].copy_(x[0])                                              # first frame: no temporal conv ("Rep", vae.py:110-112)
-            if T > 1:
+            skip = 1 if first_chunk else 0                                # frames of this chunk that bypass the time_conv
+            y = torch.empty((skip + 2 * (T - skip), H, W, C), dtype=torch.bfloat16, device=x.device)
+            if skip:
+                y[0].copy_(x[0])
+            if T > skip:
                 for g_, conv in enumerate(up["time"]):
-                    conv(x[1:], out=y[1 + g_::2])                         # history starts at frame 1: earlier frames read as zero
+                    self._tconv(conv, T - skip, H, W, lambda dst: dst.copy_(x[skip:]), out=y[skip + g_::2])
+            elif self._streaming:
+                for conv in up["time"]:                                   # a one-frame first chunk: the history of the time_conv stays empty
+                    self._hist.pop(id(conv), None)
             x = y
         return up["conv"](x)
 
@@ -216,13 +260,38 @@ class WanVAEDecoderB200:
     @torch.no_grad()
     def _decode_local(self, zs: torch.Tensor) -> torch.Tensor:
         zs = zs.to(self.device, torch.float32)
+        Tl, Hl, Wl = zs.shape[1], zs.shape[2], zs.shape[3]
+        chunk = self.chunk_frames
+        if chunk is None or chunk >= Tl:
+            self._streaming = False
+            return lib.cl_to_video(self._decode_frames(zs, True)).unsqueeze(0)
+        n_t = sum(1 for kind, layer in self.layers if kind == "up" and layer["time"] is not None)
+        total = Tl
+        for _ in range(n_t):
+            total = 1 + 2 * (total - 1)
+        video = torch.empty((3, total, Hl * 8, Wl * 8), dtype=torch.float32, device=self.device)
+        self._streaming, self._hist = True, {}
+        try:
+            t_out = 0
+            for t0 in range(0, Tl, chunk):
+                x = self._decode_frames(zs[:, t0:t0 + chunk].contiguous(), t0 == 0)
+                lib.cl_to_video(x, out=video[:, t_out:t_out + x.shape[0]])
+                t_out += x.shape[0]
+                del x
+            assert t_out == total, (t_out, total)
+        finally:
+            self._streaming, self._hist = False, {}
+        return video.unsqueeze(0)
+
+    def _decode_frames(self, zs: torch.Tensor, first_chunk: bool) -> torch.Tensor:
+        """Latent frames [16, T, H, W] fp32 -> channels-last bf16 video frames [T', 8H, 8W, 16] (3 valid channels, clamped to [-1, 1])."""
         x = lib.latent_to_cl(zs, self.mean, self.inv_std, cp=32)
-        x = self.conv2(x)
-        x = self.conv1(x)
+        T, H, W, _ = x.shape
+        x = self._tconv(self.conv1, T, H, W, lambda dst: self.conv2(x, out=dst))
         x = self._res(self.mid0, x)
         x = self._attention(x)
         x = self._res(self.mid2, x)
         for kind, layer in self.layers:
-            x = self._res(layer, x) if kind == "res" else self._upsample(layer, x)
-        x = self.head(lib.rms_silu_cl(x, self.head_g), clamp=True)
-        return lib.cl_to_video(x).unsqueeze(0)
+            x = self._res(layer, x) if kind == "res" else self._upsample(layer, x, first_chunk)
+        T, H, W, _ = x.shape
+        return self._tconv(self.head, T, H, W, lambda dst: lib.rms_silu_cl(x, self.head_g, out=dst), clamp=True)

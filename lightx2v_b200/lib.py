@@ -50,7 +50,7 @@ SIGNATURES = {
     "b200_gn_apply_pad_cl": (_i32, [_ptr, _ptr, _ptr, _ptr, _ptr, _f32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _ptr]),
     "b200_rms_silu_cl": (_i32, [_ptr, _ptr, _ptr, _i64, _i32, _i32, _ptr]),
     "b200_latent_to_cl": (_i32, [_ptr, _ptr, _ptr, _ptr, _i64, _i32, _i32, _ptr]),
-    "b200_cl_to_video": (_i32, [_ptr, _ptr, _i64, _i32, _ptr]),
+    "b200_cl_to_video": (_i32, [_ptr, _ptr, _i64, _i32, _i64, _ptr]),
 }
 
 EPI_BIAS, EPI_BIAS_GELU, EPI_GATE_RESIDUAL, EPI_RESIDUAL = 0, 1, 2, 3
@@ -437,11 +437,15 @@ def latent_to_cl(z: torch.Tensor, mean: torch.Tensor, inv_std: torch.Tensor, cp:
     return out
 
 
-def cl_to_video(x: torch.Tensor) -> torch.Tensor:
+def cl_to_video(x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """x [T, H, W, CP] bf16 (3 valid channels) -> fp32 [3, T, H, W]; `out` may be a frame range `video[:, t0:t0 + T]` of a larger video."""
     _req(x, "x")
     T, H, W, CP = x.shape
-    out = torch.empty((3, T, H, W), dtype=torch.float32, device=x.device)
-    rc = load().b200_cl_to_video(x.contiguous().data_ptr(), out.data_ptr(), T * H * W, CP, _stream())
+    if out is None:
+        out = torch.empty((3, T, H, W), dtype=torch.float32, device=x.device)
+    if tuple(out.shape) != (3, T, H, W) or out.dtype != torch.float32 or out.stride(3) != 1 or out.stride(2) != W or out.stride(1) != H * W:
+        raise B200Error(f"cl_to_video: out must be fp32 [3, {T}, {H}, {W}] with contiguous frames, got {tuple(out.shape)} / {out.stride()}")
+    rc = load().b200_cl_to_video(x.contiguous().data_ptr(), out.data_ptr(), T * H * W, CP, out.stride(0), _stream())
     _check(rc, "b200_cl_to_video")
     return out
 

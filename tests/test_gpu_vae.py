@@ -107,3 +107,50 @@ def test_decoder_vs_oracle_on_gpu_larger():
     p = psnr(out, ref)
     print(f"VAE decode 17x192x320 vs oracle on GPU: PSNR {p:.1f} dB, max abs err {(out - ref).abs().max():.4f}")
     assert p > 35
+
+
+@pytest.mark.parametrize("shape,chunk", [((16, 7, 12, 16), 3), ((16, 5, 8, 33), 1), ((16, 4, 10, 12), 2)])
+def test_chunked_decode_is_bit_identical_to_whole_sequence(shape, chunk):
+    """Streaming decode (chunks of latent frames, every temporal convolution carrying the last two frames of its input: the reference's
+    feat_cache protocol with a chunk size > 1) == the whole-sequence causal convolution, bit for bit; chunk = 1 is the reference's own
+    one-latent-frame-per-iteration schedule (vae.py:723-737)."""
+    from lightx2v_b200.host.wan_vae import WanVAEDecoderB200
+
+    W = V.synth_vae_weights(2, device="cuda")
+    g = torch.Generator(device="cuda").manual_seed(3)
+    zs = torch.randn(*shape, generator=g, device="cuda")
+    whole = WanVAEDecoderB200(W, device="cuda", chunk_frames=None).decode(zs)
+    chunked = WanVAEDecoderB200(W, device="cuda", chunk_frames=chunk).decode(zs)
+    assert whole.shape == chunked.shape == (1, 3, 1 + 4 * (shape[1] - 1), shape[2] * 8, shape[3] * 8)
+    assert torch.equal(whole, chunked), (whole - chunked).abs().max()
+
+
+def test_bf16_decode_error_is_bounded_against_an_fp64_decode(record, golden_dir):
+    """The reference decodes in fp32 (cuDNN: TF32 tensor cores by default); this path keeps bf16 activations.  Both are measured against a
+    float64 evaluation of the same decoder ("truth") at the committed fixture's latent and at 17 x 192 x 320: PSNR and max error of
+       (a) this bf16 path,  (b) the reference's GPU arithmetic (the frame-by-frame oracle in fp32 with TF32 convolutions),
+    recorded to the parity-numbers file.  Floors: PSNR(bf16, truth) > 40 dB and max error < 0.1 on the [-1, 1] image."""
+    from lightx2v_b200.host.wan_vae import WanVAEDecoderB200
+
+    with safe_open(os.path.join(golden_dir, "wan_vae_decode_small.safetensors"), framework="pt") as f:
+        zs_fix = f.get_tensor("zs").cuda()
+    g = torch.Generator(device="cuda").manual_seed(7)
+    cases = {"fixture": (0, zs_fix), "17x192x320": (1, torch.randn(16, 5, 24, 40, generator=g, device="cuda"))}
+    for name, (seed, zs) in cases.items():
+        W = V.synth_vae_weights(seed, device="cuda")
+        W64 = {k: v.double() for k, v in W.items()}
+        truth = V.vae_decode(W64, zs.double())
+        torch.backends.cudnn.allow_tf32 = True
+        torch.backends.cuda.matmul.allow_tf32 = True
+        tf32 = V.vae_decode(W, zs.float())
+        torch.backends.cudnn.allow_tf32 = False
+        torch.backends.cuda.matmul.allow_tf32 = False
+        fp32 = V.vae_decode(W, zs.float())
+        ours = WanVAEDecoderB200(W, device="cuda").decode(zs)
+        stats = {}
+        for tag, t in (("bf16_b200", ours), ("reference_tf32", tf32), ("reference_fp32", fp32)):
+            stats[tag + "_psnr_db"] = psnr(t, truth)
+            stats[tag + "_max_err"] = (t.double() - truth.double()).abs().max().item()
+        print(name, {k: round(v, 4) for k, v in stats.items()})
+        record(**{f"{name}.{k}": v for k, v in stats.items()})
+        assert stats["bf16_b200_psnr_db"] > 40 and stats["bf16_b200_max_err"] < 0.1, stats
