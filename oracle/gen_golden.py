@@ -554,7 +554,76 @@ def gen_cogvideox_fixture():
     print("cogvideox_2blocks hidden_out absmax", float(h_out.float().abs().max()), "bytes", os.path.getsize(os.path.join(GOLD, "cogvideox_2blocks.safetensors")))
 
 
+def gen_hunyuan_prepost_fixture():
+    """REAL HunyuanPreInfer methods (time_in / guidance_in / vector_in / img_in, pre_infer.py:68-80, 139-152) and the REAL HunyuanPostInfer
+    (post_infer.py:11-33) with the reference's own weight classes (MM "Default" / "Default-Force-FP32", Conv3d "Default") on CPU at width
+    1536, latent [1, 16, 3, 8, 12].  `infer_text_in` is left out: the reference's own call raises at this snapshot (see the oracle)."""
+    from safetensors.torch import save_file
+
+    import lightx2v.common.ops  # noqa: F401
+    from lightx2v.common.ops import conv, mm  # noqa: F401
+    from lightx2v.models.networks.hunyuan.infer.post_infer import HunyuanPostInfer
+    from lightx2v.models.networks.hunyuan.infer.pre_infer import HunyuanPreInfer
+    from lightx2v.models.networks.hunyuan.weights.post_weights import HunyuanPostWeights
+    from lightx2v.models.networks.hunyuan.weights.pre_weights import HunyuanPreWeights
+
+    from oracle import hunyuan_oracle as HO
+
+    hidden = 1536
+    cfg = Cfg(task="t2v", mm_config={}, cpu_offload=False)
+    W = HO.synth_prepost_weights(hidden, seed=11)
+    # the pre-weights tree also declares the token refiner's tensors: give them placeholders (never used by the methods run here)
+    full = dict(W)
+    pre_w = HunyuanPreWeights(cfg)
+
+    def names(mod):
+        for child in mod._modules.values():
+            for a in ("weight_name", "bias_name"):
+                n = getattr(child, a, None)
+                if n is not None:
+                    yield n
+
+    for n in names(pre_w):
+        if n not in full:
+            full[n] = torch.zeros(8, 8, dtype=torch.bfloat16) if n.endswith("weight") else torch.zeros(8, dtype=torch.bfloat16)
+    pre_w.load(full)
+    post_w = HunyuanPostWeights(cfg)
+    post_w.load(W)
+    g = torch.Generator().manual_seed(5)
+    latents = torch.randn(1, 16, 3, 8, 12, generator=g).to(torch.bfloat16)
+    t = torch.tensor(713.0)
+    guidance = torch.tensor([6.0], dtype=torch.bfloat16) * 1000.0
+    text_states_2 = torch.randn(1, 768, generator=g).to(torch.bfloat16)
+    pre = HunyuanPreInfer(cfg)
+    time_out = pre.infer_time_in(pre_w, t)
+    guid_out = pre.infer_guidance_in(pre_w, guidance)
+    vec_out = pre.infer_vector_in(pre_w, text_states_2)
+    img_out = pre.infer_img_in(pre_w, latents)
+    vec = time_out + vec_out + guid_out
+    img = torch.randn(3 * 4 * 6, hidden, generator=g).to(torch.bfloat16)
+
+    class Sched:
+        pass
+
+    sched = Sched()
+    sched.latents = latents
+    post = HunyuanPostInfer(cfg)
+    post.set_scheduler(sched)
+    out = post.infer(post_w, img, vec)
+    save_file({"latents": latents, "t": t.reshape(1), "guidance": guidance, "text_states_2": text_states_2, "time_out": time_out, "guidance_out": guid_out,
+               "vector_out": vec_out, "img_out": img_out.contiguous(), "vec": vec, "img": img, "post_out": out.contiguous()},
+              os.path.join(GOLD, "hunyuan_prepost.safetensors"),
+              metadata={"hidden": str(hidden), "weights_seed": "11", "generator": "oracle/gen_golden.py:gen_hunyuan_prepost_fixture",
+                        "reference": "ModelTC/lightx2v@0591c35e"})
+    print("hunyuan_prepost post_out", tuple(out.shape), out.dtype, float(out.abs().max()))
+
+
 if __name__ == "__main__":
+    if os.environ.get("GOLDEN_ONLY", "") == "hunyuan_prepost":
+        install_shims()
+        os.makedirs(GOLD, exist_ok=True)
+        gen_hunyuan_prepost_fixture()
+        sys.exit(0)
     if os.environ.get("GOLDEN_ONLY", "") == "cogvideox":
         install_shims()
         os.makedirs(GOLD, exist_ok=True)
@@ -623,3 +692,4 @@ if __name__ == "__main__":
         gen_causvid_fixture()
         gen_prepost_fixture()
         gen_cogvideox_fixture()
+        gen_hunyuan_prepost_fixture()

@@ -150,3 +150,89 @@ def synth_inputs(img_len: int, txt_len: int, txt_valid: int, hidden: int, seed=7
     sin = ang.sin().repeat_interleave(2, dim=1).to(torch.bfloat16).to(device)
     cu = [0, img_len + txt_valid, img_len + txt_len]
     return img, txt, vec, cu, (cos, sin)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# pre-infer / post-infer (lightx2v/models/networks/hunyuan/infer/pre_infer.py, post_infer.py), t2v
+# Pinned by tests/golden/hunyuan_prepost.safetensors, produced by the REAL HunyuanPreInfer / HunyuanPostInfer methods
+# (oracle/gen_golden.py:gen_hunyuan_prepost_fixture).  `infer_text_in` (the two-block token refiner, pre_infer.py:83-138) is NOT restated:
+# at this snapshot the reference's own call raises (it hands [1, L, H, D] tensors to TorchSDPAWeight.apply, which unsqueezes again,
+# attn_weight.py:229-235), so there is no reference output to pin a restatement to.
+# ---------------------------------------------------------------------------------------------------------------
+def _timestep_embedding(t: torch.Tensor) -> torch.Tensor:
+    """pre_infer.py:69-71 / 84-86 / 146-148: 256-wide sinusoidal embedding, fp32 math, one rounding to bf16."""
+    import math
+    freqs = torch.exp(-math.log(10000) * torch.arange(start=0, end=128, dtype=torch.float32) / 128).to(device=t.device)
+    args = t.float() * freqs[None]
+    return torch.cat([torch.cos(args), torch.sin(args)], dim=-1).to(dtype=torch.bfloat16)
+
+
+def infer_time_in(W, t):
+    """pre_infer.py:68-75 (t: 0-d tensor)."""
+    emb = _timestep_embedding(t.unsqueeze(0).unsqueeze(0))
+    return mm_named(W, "time_in.mlp.2", F.silu(mm_named(W, "time_in.mlp.0", emb)))
+
+
+def infer_guidance_in(W, guidance):
+    """pre_infer.py:145-152 (guidance: [1] bf16 tensor = embedded_guidance_scale * 1000)."""
+    emb = _timestep_embedding(guidance)
+    return mm_named(W, "guidance_in.mlp.2", F.silu(mm_named(W, "guidance_in.mlp.0", emb)))
+
+
+def infer_vector_in(W, text_states_2):
+    """pre_infer.py:139-143."""
+    return mm_named(W, "vector_in.out_layer", F.silu(mm_named(W, "vector_in.in_layer", text_states_2)))
+
+
+def infer_img_in(W, x):
+    """pre_infer.py:77-80: Conv3d(16 -> hidden, kernel = stride = (1, 2, 2)) on [1, 16, T, H, W], flattened to [1, T*H/2*W/2, hidden]."""
+    out = F.conv3d(x, W["img_in.proj.weight"], W["img_in.proj.bias"], stride=(1, 2, 2))
+    return out.flatten(2).transpose(1, 2)
+
+
+def cu_seqlens(text_mask: torch.Tensor, img_seq_len: int):
+    """pre_infer.py:45-58 (host ints)."""
+    bs, L = text_mask.shape
+    text_len = text_mask.sum(dim=1)
+    max_len = L + img_seq_len
+    cu = [0] * (2 * bs + 1)
+    for i in range(bs):
+        cu[2 * i + 1] = i * max_len + int(text_len[i]) + img_seq_len
+        cu[2 * i + 2] = (i + 1) * max_len
+    return cu
+
+
+def post_infer(W, img, vec, latent_shape):
+    """post_infer.py:11-33: adaLN (shift, scale) from silu(vec), LayerNorm(no affine, eps 1e-6) * (1 + scale) + shift in bf16, the
+    final linear in FP32 (MM_WEIGHT "Default-Force-FP32", post_weights.py:10), unpatchify to [1, 16, T, H, W] fp32."""
+    out = mm_named(W, "final_layer.adaLN_modulation.1", F.silu(vec))
+    shift, scale = out.chunk(2, dim=1)
+    out = F.layer_norm(img, (img.shape[1],), None, None, 1e-6)
+    out = out * (1 + scale) + shift
+    out = torch.addmm(W["final_layer.linear.bias"].float(), out.to(torch.float32), W["final_layer.linear.weight"].float().t())
+    _, _, ot, oh, ow = latent_shape
+    tt, th, tw = ot, oh // 2, ow // 2
+    out = out.reshape(shape=(1, tt, th, tw, 16, 1, 2, 2))
+    out = torch.einsum("nthwcopq->nctohpwq", out)
+    return out.reshape(shape=(1, 16, tt, th * 2, tw * 2))
+
+
+def synth_prepost_weights(hidden: int = 3072, seed: int = 11, device="cpu") -> Dict[str, torch.Tensor]:
+    g = torch.Generator().manual_seed(seed)
+    W: Dict[str, torch.Tensor] = {}
+
+    def lin(name, n, k):
+        W[name + ".weight"] = (torch.randn(n, k, generator=g) * k ** -0.5).to(torch.bfloat16).to(device)
+        W[name + ".bias"] = (torch.randn(n, generator=g) * 0.02).to(torch.bfloat16).to(device)
+
+    lin("time_in.mlp.0", hidden, 256)
+    lin("time_in.mlp.2", hidden, hidden)
+    lin("guidance_in.mlp.0", hidden, 256)
+    lin("guidance_in.mlp.2", hidden, hidden)
+    lin("vector_in.in_layer", hidden, 768)
+    lin("vector_in.out_layer", hidden, hidden)
+    W["img_in.proj.weight"] = (torch.randn(hidden, 16, 1, 2, 2, generator=g) * 64 ** -0.5).to(torch.bfloat16).to(device)
+    W["img_in.proj.bias"] = (torch.randn(hidden, generator=g) * 0.02).to(torch.bfloat16).to(device)
+    lin("final_layer.adaLN_modulation.1", 2 * hidden, hidden)
+    lin("final_layer.linear", 64, hidden)
+    return W

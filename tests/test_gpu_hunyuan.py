@@ -89,3 +89,41 @@ def test_two_segment_varlen_vs_oracle_on_gpu():
     # elements between ANY two bf16 implementations (flash-attn vs this FMHA, cuBLAS vs this GEMM); single blocks are pinned at
     # 2e-3 against the real reference above.  Gate: <= 2 % outside the tolerance, no element beyond 0.13, PSNR >= 45 dB.
     assert f < 2e-2 and m < 0.13 and p > 45
+
+
+def test_hunyuan_pre_and_post_infer_vs_reference_fixture(golden_dir, record):
+    """host/hunyuan_prepost.py on the CUDA kernels vs the fixture of the REAL HunyuanPreInfer methods (time / guidance / vector embedders,
+    patch embedding) and the REAL HunyuanPostInfer (adaLN + FP32 projection + unpatchify)."""
+    import os
+
+    from safetensors import safe_open
+
+    from lightx2v_b200.host.hunyuan_prepost import HunyuanPostInfer, HunyuanPreInfer
+    from oracle import hunyuan_oracle as HO
+
+    with safe_open(os.path.join(golden_dir, "hunyuan_prepost.safetensors"), framework="pt") as f:
+        T = {k: f.get_tensor(k).cuda() for k in f.keys()}
+        meta = f.metadata()
+    W = {k: v.cuda() for k, v in HO.synth_prepost_weights(int(meta["hidden"]), seed=int(meta["weights_seed"])).items()}
+    cfg = dict(task="t2v", mm_config={})
+    pre = HunyuanPreInfer(cfg)
+
+    def close(got, ref, name, rtol=1e-2, atol=1e-2):
+        err = (got.float() - ref.float()).abs()
+        bad = (err > atol + rtol * ref.float().abs()).float().mean().item()
+        record(**{name + "_bad_frac": bad, name + "_max": err.max().item()})
+        assert bad < 1e-3, (name, bad, err.max().item())
+
+    close(pre.infer_time_in(W, T["t"][0]), T["time_out"], "time_in")
+    close(pre.infer_guidance_in(W, T["guidance"]), T["guidance_out"], "guidance_in")
+    close(pre.infer_vector_in(W, T["text_states_2"]), T["vector_out"], "vector_in")
+    close(pre.infer_img_in(W, T["latents"]), T["img_out"], "img_in")
+
+    class Sched:
+        latents = T["latents"]
+
+    post = HunyuanPostInfer(cfg)
+    post.set_scheduler(Sched())
+    out = post.infer(W, T["img"], T["vec"])
+    assert out.dtype == torch.float32 and out.shape == T["post_out"].shape
+    close(out, T["post_out"], "post_infer")

@@ -184,3 +184,19 @@ def test_cogvideox_oracle_matches_reference_fixture(golden_dir):
     assert torch.equal(ah, T["probe.attn_hidden"]) and torch.equal(ae, T["probe.attn_enc"])
     h, e = C.infer_blocks(W, layers, T["hidden_in"].clone(), T["enc_in"].clone(), T["temb"], rotary, heads)
     assert torch.equal(h, T["hidden_out"]) and torch.equal(e, T["enc_out"])
+
+
+def test_hunyuan_prepost_oracle_matches_reference_fixture(golden_dir):
+    """oracle/hunyuan_oracle.py pre/post-infer functions vs the REAL HunyuanPreInfer / HunyuanPostInfer methods: bit for bit."""
+    from oracle import hunyuan_oracle as HO
+
+    T, meta = _load(os.path.join(golden_dir, "hunyuan_prepost.safetensors"))
+    W = HO.synth_prepost_weights(int(meta["hidden"]), seed=int(meta["weights_seed"]))
+    assert torch.equal(HO.infer_time_in(W, T["t"][0]), T["time_out"])
+    assert torch.equal(HO.infer_guidance_in(W, T["guidance"]), T["guidance_out"])
+    assert torch.equal(HO.infer_vector_in(W, T["text_states_2"]), T["vector_out"])
+    assert torch.equal(HO.infer_img_in(W, T["latents"]), T["img_out"])
+    assert torch.equal(HO.post_infer(W, T["img"], T["vec"], T["latents"].shape), T["post_out"])
+    mask = torch.zeros(1, 256, dtype=torch.int64)
+    mask[0, :77] = 1
+    assert HO.cu_seqlens(mask, 1000) == [0, 1077, 1256]
