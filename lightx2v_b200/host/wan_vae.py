@@ -295,3 +295,139 @@ class WanVAEDecoderB200:
             x = self._res(layer, x) if kind == "res" else self._upsample(layer, x, first_chunk)
         T, H, W, _ = x.shape
         return self._tconv(self.head, T, H, W, lambda dst: lib.rms_silu_cl(x, self.head_g, out=dst), clamp=True)
+
+
+# ============================================================================================================================
+# Encoder (image-to-video conditioning: WanVAE.encode, vae.py:867-880 -> WanVAE_.encode :684-711 -> Encoder3d :264-376)
+# ============================================================================================================================
+class _DownConv:
+    """nn.ZeroPad2d((0, 1, 0, 1)) + nn.Conv2d(dim, dim, 3, stride 2) (vae.py:99-104) on the stride-1 implicit-GEMM kernel: the input is
+    read through its four (row, column) parity views x[:, ph::2, pw::2] (strides doubled, no copy); in view coordinates the nine taps
+    become 4 + 2 + 2 + 1 unit-stride taps, issued as four launches that accumulate through the residual epilogue.  Reads past the end
+    of a view return zero, which is the bottom / right zero padding."""
+
+    def __init__(self, w: torch.Tensor, b: torch.Tensor, device):
+        w = w.float().cpu()                                   # [cout, cin, 3, 3]
+        self.cout = w.shape[0]
+        self.parts = []
+        first = True
+        for ph in (0, 1):
+            for pw in (0, 1):
+                taps, mats = [], []
+                for dh in range(ph, 3, 2):
+                    for dw in range(pw, 3, 2):
+                        taps.append((0, dh // 2, dw // 2))
+                        mats.append(w[:, :, dh, dw])
+                self.parts.append((ph, pw, _Conv(torch.stack(mats, dim=1), b if first else None, device, taps=taps)))
+                first = False
+
+    def __call__(self, x: torch.Tensor) -> torch.Tensor:
+        T, H, W, _ = x.shape
+        Ho, Wo = (H + 1 - 3) // 2 + 1, (W + 1 - 3) // 2 + 1
+        out = torch.empty((T, Ho, Wo, self.cout), dtype=torch.bfloat16, device=x.device)
+        for i, (ph, pw, conv) in enumerate(self.parts):
+            lib.conv3d_cl_padded(x[:, ph::2, pw::2], conv.weight, conv.bias, out, conv.taps, residual=out if i else None)
+        return out
+
+
+class _TimeDownConv:
+    """CausalConv3d(dim, dim, (3, 1, 1), stride (2, 1, 1), padding 0) as the reference applies it across its 1, 4, 4, ... frame chunks
+    (Resample.forward downsample3d, vae.py:144-158): y[0] = x[0]; y[k] = W0 x[2k-2] + W1 x[2k-1] + W2 x[2k] for k >= 1.  Two launches on
+    the even / odd frame views: y[1 + k'] = W0 x_even[k'] + W2 x_even[k' + 1]  (+)  W1 x_odd[k']."""
+
+    def __init__(self, w: torch.Tensor, b: torch.Tensor, device):
+        w = w.float().cpu()                                   # [cout, cin, 3, 1, 1]
+        self.even = _Conv(torch.stack([w[:, :, 0, 0, 0], w[:, :, 2, 0, 0]], dim=1), b, device, taps=[(0, 0, 0), (1, 0, 0)])
+        self.odd = _Conv(w[:, :, 1, 0, 0].unsqueeze(1), None, device, taps=[(0, 0, 0)])
+
+    def __call__(self, x: torch.Tensor) -> torch.Tensor:
+        T, H, W, C = x.shape
+        if T % 2 != 1:
+            raise lib.B200Error(f"WanVAE encoder: temporal downsampling needs an odd frame count (1 + 2k), got {T}")
+        To = 1 + (T - 1) // 2
+        y = torch.empty((To, H, W, self.even.cout), dtype=torch.bfloat16, device=x.device)
+        y[0].copy_(x[0])
+        if To > 1:
+            lib.conv3d_cl_padded(x[0::2], self.even.weight, self.even.bias, y[1:], self.even.taps)
+            lib.conv3d_cl_padded(x[1::2], self.odd.weight, self.odd.bias, y[1:], self.odd.taps, residual=y[1:])
+        return y
+
+
+class WanVAEEncoderB200:
+    """`encode(video [3, T, H, W] in [-1, 1], T = 1 + 4k) -> normalised latent mean [16, 1 + k, H/8, W/8] fp32`
+    (WanVAE.encode, vae.py:867-880; the reference feeds 1, 4, 4, ... frames with per-convolution caches, which is the whole-sequence
+    causal convolution computed here).  Same kernels and layer helpers as the decoder; activations bf16 (the reference: fp32)."""
+
+    def __init__(self, state_dict: Dict[str, torch.Tensor], device="cuda", dim=96, z_dim=16, dim_mult=(1, 2, 4, 4), num_res_blocks=2,
+                 temperal_downsample=(False, True, True)):
+        W = state_dict
+        self.device = dev = torch.device(device)
+        self.z_dim = z_dim
+        self.mean = torch.tensor(MEAN, dtype=torch.float32, device=dev)
+        self.inv_std = 1.0 / torch.tensor(STD, dtype=torch.float32, device=dev)
+        self._zero3, self._one3 = torch.zeros(3, device=dev), torch.ones(3, device=dev)
+
+        def g(name):
+            return W[name].float().reshape(-1).to(dev).contiguous()
+
+        def res(p, cin, cout):
+            d = {"g0": g(p + ".residual.0.gamma"), "c1": _Conv(W[p + ".residual.2.weight"], W[p + ".residual.2.bias"], dev),
+                 "g1": g(p + ".residual.3.gamma"), "c2": _Conv(W[p + ".residual.6.weight"], W[p + ".residual.6.bias"], dev), "sc": None}
+            if cin != cout:
+                d["sc"] = _Conv(W[p + ".shortcut.weight"], W[p + ".shortcut.bias"], dev)
+            return d
+
+        dims = [dim * u for u in [1] + list(dim_mult)]
+        self.conv_in = _Conv(W["encoder.conv1.weight"], W["encoder.conv1.bias"], dev, cin_pad=32)       # 3 -> 96 (input zero-padded to 32 channels)
+        self.layers = []
+        n, out_dim = 0, dims[0]
+        for i, (in_dim, out_dim) in enumerate(zip(dims[:-1], dims[1:])):
+            for _ in range(num_res_blocks):
+                self.layers.append(("res", res(f"encoder.downsamples.{n}", in_dim, out_dim)))
+                in_dim = out_dim
+                n += 1
+            if i != len(dim_mult) - 1:
+                p = f"encoder.downsamples.{n}"
+                down = {"conv": _DownConv(W[p + ".resample.1.weight"], W[p + ".resample.1.bias"], dev), "time": None}
+                if temperal_downsample[i]:
+                    down["time"] = _TimeDownConv(W[p + ".time_conv.weight"], W[p + ".time_conv.bias"], dev)
+                self.layers.append(("down", down))
+                n += 1
+        self.mid0 = res("encoder.middle.0", out_dim, out_dim)
+        self.attn = {"g": g("encoder.middle.1.norm.gamma"),
+                     "qkv": _Conv(W["encoder.middle.1.to_qkv.weight"], W["encoder.middle.1.to_qkv.bias"], dev),
+                     "proj": _Conv(W["encoder.middle.1.proj.weight"], W["encoder.middle.1.proj.bias"], dev)}
+        self.mid2 = res("encoder.middle.2", out_dim, out_dim)
+        self.head_g = g("encoder.head.0.gamma")
+        self.head = _Conv(W["encoder.head.2.weight"], W["encoder.head.2.bias"], dev, cout_pad=64)        # 384 -> 2 z_dim = 32 (padded to 64)
+        self.conv1 = _Conv(W["conv1.weight"], W["conv1.bias"], dev, cin_pad=64, cout_pad=64)            # 1x1x1 in front of the mu / log_var split
+
+    @staticmethod
+    def _res(d, x):
+        h = x if d["sc"] is None else d["sc"](x)
+        a = d["c1"](lib.rms_silu_cl(x, d["g0"]))
+        return d["c2"](lib.rms_silu_cl(a, d["g1"]), residual=h)
+
+    _attention = WanVAEDecoderB200._attention
+
+    @torch.no_grad()
+    def encode(self, video: torch.Tensor) -> torch.Tensor:
+        video = video.to(self.device, torch.float32)
+        if video.dim() == 5:
+            video = video[0]
+        x = lib.latent_to_cl(video.contiguous(), self._zero3, self._one3, cp=32)      # [3, T, H, W] fp32 -> channels-last bf16, zero-padded channels
+        x = self.conv_in(x)
+        for kind, layer in self.layers:
+            if kind == "res":
+                x = self._res(layer, x)
+            else:
+                x = layer["conv"](x)
+                if layer["time"] is not None:
+                    x = layer["time"](x)
+        x = self._res(self.mid0, x)
+        x = self._attention(x)
+        x = self._res(self.mid2, x)
+        x = self.head(lib.rms_silu_cl(x, self.head_g))
+        x = self.conv1(x)                                                               # [T', H/8, W/8, 64]: channels [0, 16) = mu
+        mu = x[..., : self.z_dim].permute(3, 0, 1, 2).float()
+        return (mu - self.mean.view(-1, 1, 1, 1)) * self.inv_std.view(-1, 1, 1, 1)

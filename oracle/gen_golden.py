@@ -618,7 +618,36 @@ def gen_hunyuan_prepost_fixture():
     print("hunyuan_prepost post_out", tuple(out.shape), out.dtype, float(out.abs().max()))
 
 
+def gen_vae_encode_fixture():
+    """Real WanVAE_.encode (lightx2v/models/video_encoders/hf/wan/vae.py:684-711; Encoder3d :264-376) on CPU in fp32, seeded synthetic
+    weights loaded through its own state_dict: video [3, 9, 32, 48] -> mu [16, 3, 4, 6]; pins oracle/vae_oracle.py:vae_encode."""
+    from safetensors.torch import save_file
+
+    from lightx2v.models.video_encoders.hf.wan.vae import WanVAE_
+
+    from oracle import vae_oracle as V
+
+    W = V.synth_vae_encoder_weights(seed=0)
+    model = WanVAE_(dim=96, z_dim=16, dim_mult=[1, 2, 4, 4], num_res_blocks=2, attn_scales=[], temperal_downsample=[False, True, True], dropout=0.0).eval()
+    res = model.load_state_dict(W, strict=False)
+    assert not res.unexpected_keys, res.unexpected_keys
+    assert all(k.startswith("decoder.") or k.startswith("conv2.") for k in res.missing_keys), res.missing_keys
+    g = torch.Generator().manual_seed(6)
+    video = torch.rand(3, 9, 32, 48, generator=g) * 2 - 1
+    scale = [torch.tensor(V.MEAN), 1.0 / torch.tensor(V.STD)]
+    with torch.no_grad():
+        mu = model.encode(video.unsqueeze(0), scale).float()[0]
+    save_file({"video": video, "mu": mu.contiguous()}, os.path.join(GOLD, "wan_vae_encode_small.safetensors"),
+              metadata={"weights_seed": "0", "generator": "oracle/gen_golden.py:gen_vae_encode_fixture", "reference": "ModelTC/lightx2v@0591c35e"})
+    print("wan_vae_encode_small", tuple(mu.shape), "absmax", float(mu.abs().max()))
+
+
 if __name__ == "__main__":
+    if os.environ.get("GOLDEN_ONLY", "") == "vae_encode":
+        install_shims()
+        os.makedirs(GOLD, exist_ok=True)
+        gen_vae_encode_fixture()
+        sys.exit(0)
     if os.environ.get("GOLDEN_ONLY", "") == "hunyuan_prepost":
         install_shims()
         os.makedirs(GOLD, exist_ok=True)
@@ -693,3 +722,4 @@ if __name__ == "__main__":
         gen_prepost_fixture()
         gen_cogvideox_fixture()
         gen_hunyuan_prepost_fixture()
+        gen_vae_encode_fixture()

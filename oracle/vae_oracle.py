@@ -201,3 +201,121 @@ def vae_decode(W: Dict[str, torch.Tensor], zs: torch.Tensor, dim=96, z_dim=16) -
     for i in range(z.shape[2]):
         outs.append(decoder3d(W, x[:, :, i : i + 1], feat_cache, [0], layers))
     return torch.cat(outs, dim=2).float().clamp_(-1, 1)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Encoder (lightx2v/models/video_encoders/hf/wan/vae.py: Encoder3d :264-376, Resample downsample2d / downsample3d :70-159,
+# WanVAE_.encode :684-711).  Pinned by tests/golden/wan_vae_encode_small.safetensors (oracle/gen_golden.py:gen_vae_encode_fixture,
+# REAL WanVAE_.encode on CPU in fp32).  Weight keys: `encoder.conv1.*`, `encoder.downsamples.N.*`, `encoder.middle.{0,1,2}.*`,
+# `encoder.head.{0,2}.*`, `conv1.*` (the 1x1x1 conv in front of the mu / log_var split).
+# ---------------------------------------------------------------------------------------------------------------
+def encoder_layout(dim=96, dim_mult=(1, 2, 4, 4), num_res_blocks=2, temperal_downsample=(False, True, True)):
+    """Module list of Encoder3d.downsamples (vae.py:291-305): [("res", in, out) | ("down2d"/"down3d", dim)], and the final width."""
+    dims = [dim * u for u in [1] + list(dim_mult)]
+    layers = []
+    out_dim = dims[0]
+    for i, (in_dim, out_dim) in enumerate(zip(dims[:-1], dims[1:])):
+        for _ in range(num_res_blocks):
+            layers.append(("res", in_dim, out_dim))
+            in_dim = out_dim
+        if i != len(dim_mult) - 1:
+            layers.append(("down3d" if temperal_downsample[i] else "down2d", out_dim))
+    return dims[0], layers, out_dim
+
+
+def synth_vae_encoder_weights(seed=0, dim=96, z_dim=16, device="cpu", dtype=torch.float32) -> Dict[str, torch.Tensor]:
+    g = torch.Generator().manual_seed(seed + 1000)
+    W: Dict[str, torch.Tensor] = {}
+
+    def conv(name, cout, cin, k):
+        fan = cin * math.prod(k)
+        W[name + ".weight"] = (torch.randn(cout, cin, *k, generator=g) * (1.0 / math.sqrt(fan))).to(dtype).to(device)
+        W[name + ".bias"] = (torch.randn(cout, generator=g) * 0.05).to(dtype).to(device)
+
+    def gamma(name, c, images):
+        shape = (c, 1, 1) if images else (c, 1, 1, 1)
+        W[name] = (1.0 + 0.1 * torch.randn(shape, generator=g)).to(dtype).to(device)
+
+    def res(prefix, cin, cout):
+        gamma(prefix + ".residual.0.gamma", cin, False)
+        conv(prefix + ".residual.2", cout, cin, (3, 3, 3))
+        gamma(prefix + ".residual.3.gamma", cout, False)
+        conv(prefix + ".residual.6", cout, cout, (3, 3, 3))
+        if cin != cout:
+            conv(prefix + ".shortcut", cout, cin, (1, 1, 1))
+
+    d0, layers, d_out = encoder_layout(dim)
+    conv("encoder.conv1", d0, 3, (3, 3, 3))
+    for n, layer in enumerate(layers):
+        p = f"encoder.downsamples.{n}"
+        if layer[0] == "res":
+            res(p, layer[1], layer[2])
+        else:
+            conv(p + ".resample.1", layer[1], layer[1], (3, 3))
+            if layer[0] == "down3d":
+                conv(p + ".time_conv", layer[1], layer[1], (3, 1, 1))
+    res("encoder.middle.0", d_out, d_out)
+    gamma("encoder.middle.1.norm.gamma", d_out, True)
+    conv("encoder.middle.1.to_qkv", 3 * d_out, d_out, (1, 1))
+    conv("encoder.middle.1.proj", d_out, d_out, (1, 1))
+    res("encoder.middle.2", d_out, d_out)
+    gamma("encoder.head.0.gamma", d_out, False)
+    conv("encoder.head.2", 2 * z_dim, d_out, (3, 3, 3))
+    conv("conv1", 2 * z_dim, 2 * z_dim, (1, 1, 1))
+    return W
+
+
+def resample_down(W, p, x, mode, feat_cache, feat_idx):
+    """Resample.forward, downsample2d / downsample3d (vae.py:139-159): ZeroPad2d((0, 1, 0, 1)) + Conv2d(3, stride 2) per frame; then
+    (down3d) the first chunk passes through and is cached, later chunks run time_conv (3x1x1, stride 2 in time, no padding) over
+    [last cached frame ; chunk]."""
+    b, c, t, h, w = x.shape
+    x = x.permute(0, 2, 1, 3, 4).reshape(b * t, c, h, w)
+    x = F.conv2d(F.pad(x, (0, 1, 0, 1)), W[p + ".resample.1.weight"], W[p + ".resample.1.bias"], stride=(2, 2))
+    x = x.reshape(b, t, c, x.shape[-2], x.shape[-1]).permute(0, 2, 1, 3, 4)
+    if mode == "down3d":
+        idx = feat_idx[0]
+        if feat_cache[idx] is None:
+            feat_cache[idx] = x.clone()
+            feat_idx[0] += 1
+        else:
+            cache_x = x[:, :, -1:, :, :].clone()
+            x = F.conv3d(torch.cat([feat_cache[idx][:, :, -1:, :, :], x], 2), W[p + ".time_conv.weight"], W[p + ".time_conv.bias"], stride=(2, 1, 1))
+            feat_cache[idx] = cache_x
+            feat_idx[0] += 1
+    return x
+
+
+def encoder3d(W, x, feat_cache, feat_idx, layers):
+    """Encoder3d.forward (vae.py:323-376)."""
+    x = _cached_conv(x, W["encoder.conv1.weight"], W["encoder.conv1.bias"], feat_cache, feat_idx)
+    for n, layer in enumerate(layers):
+        p = f"encoder.downsamples.{n}"
+        if layer[0] == "res":
+            x = residual_block(W, p, x, feat_cache, feat_idx)
+        else:
+            x = resample_down(W, p, x, layer[0], feat_cache, feat_idx)
+    x = residual_block(W, "encoder.middle.0", x, feat_cache, feat_idx)
+    x = attention_block(W, "encoder.middle.1", x)
+    x = residual_block(W, "encoder.middle.2", x, feat_cache, feat_idx)
+    x = F.silu(rms_norm(x, W["encoder.head.0.gamma"]))
+    return _cached_conv(x, W["encoder.head.2.weight"], W["encoder.head.2.bias"], feat_cache, feat_idx)
+
+
+def vae_encode(W: Dict[str, torch.Tensor], video: torch.Tensor, dim=96, z_dim=16) -> torch.Tensor:
+    """WanVAE_.encode (vae.py:684-711): video [3, T, H, W] in [-1, 1], T = 1 + 4k -> normalised mu [16, 1 + k, H/8, W/8]; frames are
+    fed as 1, 4, 4, ... with the per-convolution caches carried across the chunks."""
+    _, layers, _ = encoder_layout(dim)
+    x = video.unsqueeze(0)
+    n_cache = 64                                        # upper bound on the CausalConv3d count (count_conv3d, vae.py:492-497)
+    feat_cache: List[Optional[torch.Tensor]] = [None] * n_cache
+    t = x.shape[2]
+    outs = []
+    for i in range(1 + (t - 1) // 4):
+        chunk = x[:, :, :1] if i == 0 else x[:, :, 1 + 4 * (i - 1): 1 + 4 * i]
+        outs.append(encoder3d(W, chunk, feat_cache, [0], layers))
+    out = torch.cat(outs, 2)
+    mu, _ = causal_conv3d(out, W["conv1.weight"], W["conv1.bias"]).chunk(2, dim=1)
+    mean = torch.tensor(MEAN, dtype=mu.dtype, device=mu.device).view(1, z_dim, 1, 1, 1)
+    inv_std = (1.0 / torch.tensor(STD, dtype=mu.dtype, device=mu.device)).view(1, z_dim, 1, 1, 1)
+    return ((mu - mean) * inv_std)[0]

@@ -154,3 +154,49 @@ def test_bf16_decode_error_is_bounded_against_an_fp64_decode(record, golden_dir)
         print(name, {k: round(v, 4) for k, v in stats.items()})
         record(**{f"{name}.{k}": v for k, v in stats.items()})
         assert stats["bf16_b200_psnr_db"] > 40 and stats["bf16_b200_max_err"] < 0.1, stats
+
+
+def test_strided_and_temporal_downsample_convs_vs_torch(lib):
+    """_DownConv (ZeroPad2d + Conv2d stride 2 through four parity views) and _TimeDownConv (3x1x1, stride 2 in time, first frame passed
+    through) against torch on bf16-rounded operands."""
+    from lightx2v_b200.host.wan_vae import _DownConv, _TimeDownConv
+
+    g = torch.Generator(device="cuda").manual_seed(4)
+    C, T, H, W = 96, 5, 14, 36
+    x = torch.randn(C, T, H, W, generator=g, device="cuda")
+    w = torch.randn(C, C, 3, 3, generator=g, device="cuda") / (C * 9) ** 0.5
+    b = torch.randn(C, generator=g, device="cuda") * 0.1
+    xb, wb, bb = x.to(torch.bfloat16).float(), w.to(torch.bfloat16).float(), b.to(torch.bfloat16).float()
+    torch.backends.cudnn.allow_tf32 = False
+    ref = F.conv2d(F.pad(xb.permute(1, 0, 2, 3), (0, 1, 0, 1)), wb, bb, stride=2).permute(1, 0, 2, 3)          # [C, T, H/2, W/2]
+    got = _DownConv(w, b, "cuda")(_cl(x)).permute(3, 0, 1, 2).float()
+    assert got.shape == ref.shape and psnr(got, ref) > 42, psnr(got, ref)
+    wt = torch.randn(C, C, 3, 1, 1, generator=g, device="cuda") / (C * 3) ** 0.5
+    wtb = wt.to(torch.bfloat16).float()
+    y = F.conv3d(torch.cat([xb[:, :1], xb[:, 1:]], 1).unsqueeze(0), wtb, bb, stride=(2, 1, 1))[0]     # windows (0,1,2), (2,3,4)
+    ref_t = torch.cat([xb[:, :1], y], dim=1)
+    got_t = _TimeDownConv(wt, b, "cuda")(_cl(x)).permute(3, 0, 1, 2).float()
+    assert got_t.shape == ref_t.shape == (C, 3, H, W)
+    assert torch.equal(got_t[:, 0], xb[:, 0]) and psnr(got_t, ref_t) > 42, psnr(got_t, ref_t)
+
+
+def test_encoder_vs_reference_fixture_and_oracle(golden_dir, record):
+    """WanVAEEncoderB200 vs (a) the fixture of the REAL WanVAE_.encode (fp32 CPU) and (b) the oracle at [3, 9, 96, 160] on the GPU;
+    bf16 activations vs the reference's fp32 -> PSNR of the latent mean, recorded."""
+    from lightx2v_b200.host.wan_vae import WanVAEEncoderB200
+
+    with safe_open(os.path.join(golden_dir, "wan_vae_encode_small.safetensors"), framework="pt") as f:
+        video, mu = f.get_tensor("video"), f.get_tensor("mu")
+    W = V.synth_vae_encoder_weights(0)
+    out = WanVAEEncoderB200(W, device="cuda").encode(video.cuda()).cpu()
+    assert out.shape == mu.shape
+    p1 = psnr(out, mu)
+    Wg = V.synth_vae_encoder_weights(1, device="cuda")
+    g = torch.Generator(device="cuda").manual_seed(8)
+    vid = torch.rand(3, 9, 96, 160, generator=g, device="cuda") * 2 - 1
+    ref = V.vae_encode(Wg, vid)
+    got = WanVAEEncoderB200(Wg, device="cuda").encode(vid)
+    p2 = psnr(got, ref)
+    print(f"VAE encode: PSNR vs real-reference fixture {p1:.1f} dB, vs oracle at 9x96x160 {p2:.1f} dB")
+    record(psnr_fixture_db=p1, psnr_oracle_db=p2, max_err_fixture=(out - mu).abs().max())
+    assert p1 > 35 and p2 > 35

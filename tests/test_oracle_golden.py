@@ -200,3 +200,13 @@ def test_hunyuan_prepost_oracle_matches_reference_fixture(golden_dir):
     mask = torch.zeros(1, 256, dtype=torch.int64)
     mask[0, :77] = 1
     assert HO.cu_seqlens(mask, 1000) == [0, 1077, 1256]
+
+
+def test_vae_encoder_oracle_matches_reference_fixture(golden_dir):
+    """oracle/vae_oracle.py:vae_encode vs the REAL WanVAE_.encode (fp32 CPU): bit for bit."""
+    from oracle import vae_oracle as V
+
+    torch.set_num_threads(8)
+    T, _ = _load(os.path.join(golden_dir, "wan_vae_encode_small.safetensors"))
+    out = V.vae_encode(V.synth_vae_encoder_weights(0), T["video"])
+    assert torch.equal(out, T["mu"])
