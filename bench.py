@@ -276,9 +276,13 @@ def run_ours(args):
     cfg["b200_native_block"] = not args.per_op
     W = synth_weights(cfg, dev)
     model = WanModel.from_weight_dict(cfg, W)
+    graphed = bool(args.graph) and world == 1 and not cfg.get("distill")
     if cfg.get("distill"):
         from lightx2v_b200.host.wan_scheduler import WanStepDistillScheduler
         sched = WanStepDistillScheduler(cfg, device=dev)
+    elif graphed:
+        from lightx2v_b200.host.wan_graph import WanSchedulerDevice
+        sched = WanSchedulerDevice(cfg, device=dev)
     else:
         sched = WanScheduler(cfg, device=dev)
     sched.prepare()
@@ -305,8 +309,16 @@ def run_ours(args):
     else:
         sp_mode = "none"
 
+    den = None
+    if graphed:
+        from lightx2v_b200.host.wan_graph import GraphedDenoiser
+        den = GraphedDenoiser(model, sched, inputs)
+
     def one_step(i):
         i = i % max(1, sched.infer_steps - 1)
+        if den is not None:                      # one CUDA graph per step kind (host/wan_graph.py); the history of step 0 is reset by its kind
+            den.step(i)
+            return
         if i == 0 and not cfg.get("distill"):
             sched.set_timesteps(sched.infer_steps, shift=sched.sample_shift)   # fresh multistep history when the 50-step grid wraps
         sched.step_pre(i)
@@ -331,12 +343,16 @@ def run_ours(args):
     clocks = ClockSampler(local_rank)
     if rank == 0:
         clocks.start()
-    lib.prof_fmha_begin(8192)
+    if den is None:
+        lib.prof_fmha_begin(8192)          # (events recorded inside a captured graph would be overwritten by every replay)
     l0 = lib.launch_count()
+    g0 = den.replayed_launches if den is not None else 0
     torch.cuda.nvtx.range_push("timed")          # ncu --nvtx --nvtx-include "timed/" captures exactly this region
     ms_resident = timed_loop(step, args.steps, world)
     torch.cuda.nvtx.range_pop()
     launches = lib.launch_count() - l0
+    if den is not None:
+        launches = den.replayed_launches - g0
     prof = lib.prof_fmha_end(8192)
     clk = clocks.stop() if rank == 0 else None
     log(f"timed region: {args.steps} steps, {ms_resident:.1f} ms/step (this rank), {launches} launches; budget left {budget.left():.0f} s")
@@ -354,8 +370,13 @@ def run_ours(args):
     d2h = h_out.numel() * 4
 
     def e2e_step():
-        sched.latents = h_lat.to(dev, non_blocking=True)
-        inputs["text_encoder_output"] = {k: v.to(dev, non_blocking=True) for k, v in h_ctx.items()}
+        if den is not None:                  # graph replay reads static buffers: the H2D copies land in them
+            sched.s_lat.copy_(h_lat, non_blocking=True)
+            for k, v in h_ctx.items():
+                ctx[k].copy_(v, non_blocking=True)
+        else:
+            sched.latents = h_lat.to(dev, non_blocking=True)
+            inputs["text_encoder_output"] = {k: v.to(dev, non_blocking=True) for k, v in h_ctx.items()}
         step()
         h_out.copy_(sched.latents.float(), non_blocking=True)
 
@@ -376,7 +397,7 @@ def run_ours(args):
             "data": "synthetic latents/prompt embeddings, random-init weights of the named shapes",
             "config": {"workload": args.workload, "tokens": S, "forwards_per_step": 2 if cfg["enable_cfg"] else 1, "blocks": cfg["num_layers"],
                        "parallelism": (sp_mode if sp_mode.startswith("cfg2") else f"ulysses{world}") if world > 1 else "single", "sp_exchange": sp_mode,
-                       "block_schedule": "library default: one native b200_wan_block_fwd call per block" if native else "per-op C-ABI entry points",
+                       "block_schedule": ("one CUDA graph per denoise step (host/wan_graph.py), " if den is not None else "") + ("library default: one native b200_wan_block_fwd call per block" if native else "per-op C-ABI entry points"),
                        "l2": "activations (774 MB/tensor) and weights (28 GB) exceed the 126 MB L2",
                        "scheduler": "step-distill 4-step (x0 re-noising)" if cfg.get("distill") else "UniPC order 2 (flow), 50-step sigma grid"},
             "achieved_tflops": round(flops_step / (ms_resident * 1e-3) / 1e12, 1),
@@ -485,6 +506,8 @@ def run_hunyuan(args):
     l0 = lib.launch_count()
     ms = timed_loop(step, args.steps, world)
     launches = lib.launch_count() - l0
+    if den is not None:
+        launches = den.replayed_launches - g0
     prof = lib.prof_fmha_end(8192)
     clk = clocks.stop() if rank == 0 else None
     log(f"timed region: {ms:.1f} ms/step; budget left {budget.left():.0f} s")
@@ -749,6 +772,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false")
     ap.add_argument("--no-gpu-reference", dest="gpu_reference", action="store_false")
     ap.add_argument("--no-vae", dest="vae", action="store_false")
+    ap.add_argument("--graph", action="store_true", help="N = 1: replay each denoise step as a CUDA graph with the device-resident scheduler (host/wan_graph.py)")
     ap.add_argument("--per-op", action="store_true", help="drive the per-op C-ABI entry points from Python instead of the native per-block call")
     ap.add_argument("--sp", default="fused", choices=["fused", "nccl"], help="Ulysses exchange: peer-memory kernels (default) or NCCL all-to-all")
     ap.add_argument("--parallel", default="ulysses", choices=["ulysses", "cfg"],

@@ -48,6 +48,7 @@ class WanPreInfer:
         self.scheduler = None
         self._t_table = None
         self._ctx_cache = {}
+        self.use_static_t_embed = False      # host/wan_graph.py: read the embedding row from the scheduler's static buffer (CUDA-graph replay)
 
     def set_scheduler(self, scheduler):
         self.scheduler = scheduler
@@ -82,6 +83,8 @@ class WanPreInfer:
         """Sinusoidal embedding of the current timestep (pre_infer.py:56-58).  The fp64 table for ALL timesteps of the schedule is built
         once on the host (same element-wise math as the per-step call of the reference) and indexed on the device afterwards, so a
         denoise step has no device->host synchronisation."""
+        if self.use_static_t_embed:
+            return self.scheduler.t_embed_static
         ts = self.scheduler.timesteps
         if self._t_table is None or self._t_table[0] is not ts or self._t_table[1] != ts._version:      # keyed on the tensor object (kept alive here)
             self._t_table = (ts, ts._version, sinusoidal_embedding_1d(self.freq_dim, ts.flatten().cpu()).to(device))

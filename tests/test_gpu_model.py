@@ -80,3 +80,55 @@ def test_model_cfg_combine_and_step():
     before = sched.latents.clone()
     sched.step_post()
     assert torch.isfinite(sched.latents).all() and not torch.equal(sched.latents.float(), before.float())
+
+
+def _small_model(dev, scheduler_cls, steps=6):
+    import bench as B
+    from lightx2v_b200.host.wan_model import WanModel
+
+    cfg = dict(dim=1536, num_heads=12, ffn_dim=8960, num_layers=2, target_shape=(16, 3, 16, 16), infer_steps=steps, enable_cfg=True, sample_guide_scale=5.0,
+               sample_shift=5.0, task="t2v", freq_dim=256, text_len=512, in_dim=16, out_dim=16, seed=42, mm_config={}, patch_size=(1, 2, 2))
+    W = B.synth_weights(cfg, dev)
+    gen = torch.Generator(device=dev).manual_seed(7)
+    ctx = {"context": torch.randn(100, 4096, generator=gen, device=dev).to(torch.bfloat16), "context_null": torch.randn(512, 4096, generator=gen, device=dev).to(torch.bfloat16)}
+    inputs = {"text_encoder_output": ctx, "image_encoder_output": None}
+    model = WanModel.from_weight_dict(cfg, W)
+    sched = scheduler_cls(cfg, device=dev)
+    sched.prepare()
+    model.set_scheduler(sched)
+    return model, sched, inputs
+
+
+def test_device_scheduler_and_cuda_graph_step_are_bit_identical_to_the_eager_loop():
+    """host/wan_graph.py: WanSchedulerDevice (coefficients from a device table, state in static buffers) driven eagerly, and the same
+    steps replayed as CUDA graphs (one per step kind), must reproduce the eager WanScheduler loop bit for bit over a whole 6-step schedule
+    (first step, second step, steady state, last step = all four graph kinds)."""
+    from lightx2v_b200.host.wan_graph import GraphedDenoiser, WanSchedulerDevice
+    from lightx2v_b200.host.wan_scheduler import WanScheduler
+
+    dev = torch.device("cuda")
+    steps = 6
+    model, sched, inputs = _small_model(dev, WanScheduler, steps)
+    want = []
+    for i in range(steps):
+        sched.step_pre(i)
+        model.infer(inputs)
+        sched.step_post()
+        want.append(sched.latents.float().clone())
+    # device scheduler, eager loop
+    model_d, sched_d, inputs_d = _small_model(dev, WanSchedulerDevice, steps)
+    assert sched_d.kinds == [(0, 1), (1, 2), (2, 2), (2, 2), (2, 2), (2, 1)]
+    for i in range(steps):
+        sched_d.load_step(i)
+        sched_d.step_pre()
+        model_d.infer(inputs_d)
+        sched_d.step_post()
+        assert torch.equal(sched_d.latents.float(), want[i]), (i, (sched_d.latents.float() - want[i]).abs().max())
+    # CUDA graphs
+    model_g, sched_g, inputs_g = _small_model(dev, WanSchedulerDevice, steps)
+    den = GraphedDenoiser(model_g, sched_g, inputs_g)
+    for i in range(steps):
+        den.step(i)
+        torch.cuda.synchronize()
+        assert torch.equal(sched_g.latents.float(), want[i]), (i, (sched_g.latents.float() - want[i]).abs().max())
+    assert len(den.graphs) == 4
