@@ -303,3 +303,65 @@ def test_step_distill_scheduler_matches_reference_fixture(golden_dir):
         sch.step_post()
         assert sch.latents.dtype == T[f"latents_post_{i}"].dtype
         assert torch.equal(sch.latents, T[f"latents_post_{i}"]), i
+
+
+def test_wan_model_reference_constructor_and_infer_class_selection(tmp_path):
+    """WanModel(model_path, config, device) like the reference (wan/model.py:33-59): loads *.safetensors, picks the transformer infer class
+    from feature_caching / model_cls (_init_infer_class, :61-75), and set_scheduler reaches the transformer infer (:180-185)."""
+    from safetensors.torch import save_file
+
+    from lightx2v_b200.host.wan_causvid import WanTransformerInferCausVid
+    from lightx2v_b200.host.wan_infer import WanTransformerInfer
+    from lightx2v_b200.host.wan_model import WanModel
+    from lightx2v_b200.host.wan_teacache import WanTransformerInferTeaCaching
+
+    dim, ffn = 256, 512
+    W = O.synth_block_weights(1, dim, ffn, seed=3)
+    W.update(O.synth_prepost_weights(dim, 16, "t2v", seed=4))
+    save_file({k: v.contiguous() for k, v in W.items()}, str(tmp_path / "model.safetensors"))
+    base = dict(task="t2v", num_layers=1, num_heads=2, dim=dim, ffn_dim=ffn, freq_dim=256, text_len=512, in_dim=16, out_dim=16, mm_config={},
+                target_shape=(16, 1, 4, 4))
+    m = WanModel(str(tmp_path), dict(base, feature_caching="NoCaching"), "cpu")
+    assert type(m.transformer_infer) is WanTransformerInfer
+    assert set(m.W.keys()) == set(W.keys()) and all(torch.equal(m.W[k], W[k]) for k in W)
+    tea = WanModel(str(tmp_path), dict(base, feature_caching="Tea", teacache_thresh=0.2, coefficients=[[1.0, 0.0], [1.0, 0.0]], use_ret_steps=False,
+                                       infer_steps=4, enable_cfg=True), "cpu")
+    assert type(tea.transformer_infer) is WanTransformerInferTeaCaching
+    cv = WanModel(str(tmp_path), dict(base, model_cls="wan2.1_causvid", num_frames=3, num_frame_per_block=1, frame_seq_length=4), "cpu")
+    assert type(cv.transformer_infer) is WanTransformerInferCausVid
+    with pytest.raises(NotImplementedError):
+        WanModel(str(tmp_path), dict(base, feature_caching="TaylorSeer"), "cpu")
+    with pytest.raises(FileNotFoundError):
+        WanModel(str(tmp_path / "nope"), dict(base), "cpu")
+
+    class Sched:
+        infer_steps = 4
+
+    s = Sched()
+    for model in (m, tea, cv):
+        model.set_scheduler(s)
+        assert model.pre_infer.scheduler is s and model.post_infer.scheduler is s and model.transformer_infer.scheduler is s
+    assert s.caching_records == [True] * 4                      # TeaCache installs its per-step records on the scheduler (schedulers/scheduler.py:11)
+
+
+def test_weight_cache_is_rebuilt_when_the_weights_change():
+    """derived tensors (concatenated QKV, native pointer struct, cached text K/V) are keyed on the phase object AND a fingerprint
+    of its weight tensors, so a reload / replacement on the same tree cannot keep computing with the old tensors."""
+    from lightx2v_b200.host.wan_infer import WanTransformerInfer
+    from lightx2v_b200.host.wan_weights import WanTransformerWeights
+
+    dim, ffn = 256, 512
+    cfg = dict(task="t2v", num_layers=1, num_heads=2, dim=dim, ffn_dim=ffn, mm_config={})
+    tree = WanTransformerWeights(cfg)
+    tree.load(O.synth_block_weights(1, dim, ffn, seed=5))
+    infer = WanTransformerInfer(cfg)
+    sa = tree.blocks[0].compute_phases[1]
+    c1 = infer._cache(sa)
+    assert infer._cache(sa) is c1                              # stable while nothing changes
+    tree.load(O.synth_block_weights(1, dim, ffn, seed=6))      # new tensors on the same tree
+    c2 = infer._cache(sa)
+    assert c2 is not c1 and c2.owner is sa
+    sa.self_attn_q.bias.add_(1)                                # in-place edit bumps _version
+    assert infer._cache(sa) is not c2
+    infer.clear_weight_caches()
+    assert not infer._caches
