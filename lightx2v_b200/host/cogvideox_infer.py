@@ -20,6 +20,7 @@ import torch
 import torch.nn.functional as F
 
 from .. import lib
+from . import ops  # noqa: F401  (registers the op classes under their keys)
 from .registry import LN_WEIGHT_REGISTER, MM_KEY, MM_WEIGHT_REGISTER
 
 
