@@ -250,6 +250,12 @@ int b200_latent_to_cl(const float* z, void* out, const float* mean, const float*
  * are out_channel_stride elements apart (0 = voxels), so a chunk of frames can be written into its slot of the full [3, T, H, W] video. */
 int b200_cl_to_video(const void* in, float* out, int64_t voxels, int CP, int64_t out_channel_stride, b200_stream_t stream);
 
+/* Hardware probe (debug; no reference counterpart, not on any product path): D[128, 64] fp32 = A[r0 : r0 + 128, :] * B^T for A [136, k] and
+ * B [64, k] bf16 (k = 64: 128-byte rows / SWIZZLE_128B, k = 32: 64-byte rows / SWIZZLE_64B), with the UMMA descriptor of A starting r0 rows into
+ * the TMA-written shared-memory tile; mode 1 also sets the descriptor's base_offset field to r0 % 8.  tools/probe_rowshift.py reports which
+ * addressing the tensor core honours (the precondition for taking a convolution's dw taps as row-shifted views of one halo tile). */
+int b200_debug_umma_rowshift(const void* A, const void* B, float* D, int k_elems, int r0, int mode, b200_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif
