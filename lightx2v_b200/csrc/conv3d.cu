@@ -378,6 +378,11 @@ static int launch_conv(const CUtensorMap& tmIn, const CUtensorMap& tmW, const CU
   return B200_OK;
 }
 
+int conv3d_cl_halo(const void* in, long long in_st, long long in_sh, long long in_sw, int in_T, int in_H, int in_W, const void* wt,
+                   const void* bias, void* out, long long out_st, long long out_sh, long long out_sw, const void* residual, long long res_st,
+                   long long res_sh, long long res_sw, int T, int H, int W, int cin, int cout, int ntaps, const int* taps, int clamp_out,
+                   cudaStream_t stream);   // conv3d_halo.cu
+
 // in  : channels-last view  [T, H, W, cin]  bf16, element strides (in_st, in_sh, in_sw), channels contiguous
 // out : channels-last view  [T, H, W, cout] bf16, element strides (out_st, out_sh, out_sw)
 // wt  : [cout, ntaps * cin] bf16 row-major (tap-major K order)
@@ -398,6 +403,13 @@ int conv3d_cl(const void* in, long long in_st, long long in_sh, long long in_sw,
                  "b200_conv3d_cl: strides must be multiples of 8 elements");
   B200_CHECK_ARG(((uintptr_t)in % 16 == 0) && ((uintptr_t)out % 16 == 0) && ((uintptr_t)wt % 16 == 0),
                  "b200_conv3d_cl: pointers must be 16-byte aligned");
+
+  // wide 3 x 3 x 3 stages: halo-staged tiles (each input voxel fetched 3 times instead of 27), conv3d_halo.cu
+  {
+    const int hr = conv3d_cl_halo(in, in_st, in_sh, in_sw, in_T, in_H, in_W, wt, bias, out, out_st, out_sh, out_sw, residual, res_st, res_sh, res_sw, T, H,
+                                  W, cin, cout, ntaps, taps, clamp_out, stream);
+    if (hr != 1) return hr;
+  }
 
   int block_n, mode;
   const bool c64 = cin % 64 == 0, c96 = cin % 96 == 0;

@@ -5,6 +5,11 @@ mkdir -p gpurun_out
 export PYTHONUNBUFFERED=1
 echo "== pytest -m gpu (full)"; timeout 900 python -m pytest tests -m gpu -q -rs > gpurun_out/s4_pytest.log 2>&1; echo "pytest rc=$?"; tail -6 gpurun_out/s4_pytest.log
 echo "== UMMA row-shift probe"; timeout 120 python tools/probe_rowshift.py 2>&1 | tee gpurun_out/s4_probe_rowshift.txt | tail -6
+echo "== halo conv parity + timing"
+for bo in 1 0; do
+  echo "-- B200_CONV_HALO=1 B200_HALO_BASE_OFFSET=$bo"
+  B200_CONV_HALO=1 B200_HALO_BASE_OFFSET=$bo timeout 300 python tools/check_halo_conv.py 2>&1 | tail -8
+done | tee gpurun_out/s4_halo.txt
 echo "== conv A/B"
 for args in "96 8 720 1280" "192 8 360 640" "384 8 180 320" "192 8 360 640 96" "96 8 720 1280 16"; do
   timeout 120 python tools/prof_conv.py $args 2>&1 | tail -1
