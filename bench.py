@@ -506,8 +506,6 @@ def run_hunyuan(args):
     l0 = lib.launch_count()
     ms = timed_loop(step, args.steps, world)
     launches = lib.launch_count() - l0
-    if den is not None:
-        launches = den.replayed_launches - g0
     prof = lib.prof_fmha_end(8192)
     clk = clocks.stop() if rank == 0 else None
     log(f"timed region: {ms:.1f} ms/step; budget left {budget.left():.0f} s")
