@@ -36,6 +36,12 @@ int b200_num_sms(void);
  * b200_wan_block_fwd).  bench.py reports the difference over its timed region as `gpu_launches`. */
 int64_t b200_launch_count(void);
 
+/* Runtime A/B switches (measurements and tests; initial values from the environment variables of the same meaning): "conv_halo" (halo-staged
+ * tiles for the wide 3x3x3 VAE convolutions, B200_CONV_HALO), "halo_base_offset" (B200_HALO_BASE_OFFSET), "conv_narrow" (round-1 32-channel-chunk
+ * tiles, B200_CONV_NARROW).  b200_get_option returns the current value, -1 for an unknown name. */
+int b200_set_option(const char* name, int value);
+int b200_get_option(const char* name);
+
 /* Attention launch profiler for bench.py's roofline: after b200_prof_fmha_begin(capacity) every b200_fmha_fwd_* launch (also the ones
  * issued inside b200_wan_block_fwd) is bracketed by a CUDA event pair on ITS stream, up to `capacity` launches.
  * b200_prof_fmha_end waits for them, writes ms[i] and meta[4 i + {0,1,2,3}] = {sq, sk, heads, head_dim} for the first `capacity`

@@ -3,6 +3,8 @@
 
 #include "host_util.cuh"
 
+#include <string.h>
+
 namespace b200 {
 const char* last_error();
 int gemm_bf16(const void* A, long long lda, const void* B, long long ldb, void* C, long long ldc, const void* bias,
@@ -65,6 +67,13 @@ const char* b200_last_error(void) { return b200::last_error(); }
 int b200_version(void) { return 100; }
 int b200_num_sms(void) { return b200::num_sms(); }
 int64_t b200_launch_count(void) { return b200::launch_count(); }
+int b200_set_option(const char* name, int value) { return b200::set_option(name, value); }
+int b200_get_option(const char* name) {
+  static const char* const names[b200::OPT_COUNT] = {"conv_halo", "halo_base_offset", "conv_narrow"};
+  for (int i = 0; name && i < b200::OPT_COUNT; ++i)
+    if (strcmp(name, names[i]) == 0) return b200::get_option(i);
+  return -1;
+}
 int b200_prof_fmha_begin(int capacity) { return b200::prof_fmha_begin(capacity); }
 int b200_prof_fmha_end(float* ms, int64_t* meta, int capacity) {
   static_assert(sizeof(long long) == sizeof(int64_t), "int64_t is long long on this ABI");

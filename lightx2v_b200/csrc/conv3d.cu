@@ -423,14 +423,7 @@ int conv3d_cl(const void* in, long long in_st, long long in_sh, long long in_sw,
     set_last_error("b200_conv3d_cl: unsupported cout %d (need 16, or a multiple of 64 / 96 / 192)", cout);
     return B200_ERR_UNSUPPORTED;
   }
-  {
-    static int force_narrow = -1;      // B200_CONV_NARROW=1: the round-1 32-channel-chunk tiles everywhere they apply (A/B measurements)
-    if (force_narrow < 0) {
-      const char* e = getenv("B200_CONV_NARROW");
-      force_narrow = (e && atoi(e)) ? 1 : 0;
-    }
-    if (force_narrow && block_n != 128 && block_n != 256) mode = CONV_NARROW;
-  }
+  if (get_option(OPT_CONV_NARROW) && block_n != 128 && block_n != 256) mode = CONV_NARROW;   // round-1 tiles (A/B measurements)
 
   const int kc = mode == CONV_NARROW ? 32 : 64;
   const CUtensorMapSwizzle swz = mode == CONV_NARROW ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B;

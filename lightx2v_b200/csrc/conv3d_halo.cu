@@ -33,10 +33,6 @@ constexpr int HALO_A_SLOTS = 2;
 constexpr int HALO_THREADS = 256;
 constexpr int HALO_STAGING_BYTES = 128 * 64 * 2;            // 16 KB: 128 voxels x 64 output channels
 
-#ifndef B200_CONV_HALO_DEFAULT
-#define B200_CONV_HALO_DEFAULT 0                // off until the row-shift probe and the parity tests have passed on hardware (B200_CONV_HALO=1 to enable)
-#endif
-
 // HaloParams::base_offset_mode: 1 = descriptor base_offset field = start row % 8, 0 = leave it zero (tools/probe_rowshift.py decides;
 // B200_HALO_BASE_OFFSET overrides for experiments)
 
@@ -365,14 +361,8 @@ int conv3d_cl_halo(const void* in, long long in_st, long long in_sh, long long i
                    const void* bias, void* out, long long out_st, long long out_sh, long long out_sw, const void* residual, long long res_st,
                    long long res_sh, long long res_sw, int T, int H, int W, int cin, int cout, int ntaps, const int* taps, int clamp_out,
                    cudaStream_t stream) {
-  static int enabled = -1, bo_mode = 1;
-  if (enabled < 0) {
-    const char* e = getenv("B200_CONV_HALO");
-    enabled = e ? (atoi(e) != 0) : B200_CONV_HALO_DEFAULT;
-    const char* b = getenv("B200_HALO_BASE_OFFSET");
-    if (b) bo_mode = atoi(b) != 0;
-  }
-  if (!enabled || ntaps != 27 || W < 512) return 1;
+  const int bo_mode = get_option(OPT_HALO_BASE_OFFSET);
+  if (!get_option(OPT_CONV_HALO) || ntaps != 27 || W < 512) return 1;
   if (!(cin % 64 == 0 || cin % 64 == 32) || cin < 64) return 1;
   int block_n;
   if (cout % 192 == 0) block_n = 192;

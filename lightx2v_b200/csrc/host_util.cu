@@ -1,6 +1,7 @@
 #include "host_util.cuh"
 
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <atomic>
@@ -28,6 +29,37 @@ int num_sms() {
     if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) sms = 148;
   }
   return sms;
+}
+
+// ---- runtime options ---------------------------------------------------------------------------------------------------------
+#ifndef B200_CONV_HALO_DEFAULT
+#define B200_CONV_HALO_DEFAULT 0     // conv3d_halo.cu: off until verified on hardware (tools/check_halo_conv.py); flip here to make it the default
+#endif
+static const char* const kOptNames[OPT_COUNT] = {"conv_halo", "halo_base_offset", "conv_narrow"};
+static const char* const kOptEnv[OPT_COUNT] = {"B200_CONV_HALO", "B200_HALO_BASE_OFFSET", "B200_CONV_NARROW"};
+static const int kOptDefault[OPT_COUNT] = {B200_CONV_HALO_DEFAULT, 1, 0};
+static std::atomic<int> g_opts[OPT_COUNT];
+static std::once_flag g_opts_once;
+
+static void init_options() {
+  for (int i = 0; i < OPT_COUNT; ++i) {
+    const char* e = getenv(kOptEnv[i]);
+    g_opts[i].store(e ? (atoi(e) != 0) : kOptDefault[i]);
+  }
+}
+int get_option(int opt) {
+  std::call_once(g_opts_once, init_options);
+  return (opt >= 0 && opt < OPT_COUNT) ? g_opts[opt].load(std::memory_order_relaxed) : 0;
+}
+int set_option(const char* name, int value) {
+  std::call_once(g_opts_once, init_options);
+  for (int i = 0; name && i < OPT_COUNT; ++i)
+    if (strcmp(name, kOptNames[i]) == 0) {
+      g_opts[i].store(value != 0);
+      return B200_OK;
+    }
+  set_last_error("b200_set_option: unknown option '%s' (conv_halo, halo_base_offset, conv_narrow)", name ? name : "(null)");
+  return B200_ERR_INVALID;
 }
 
 static std::atomic<long long> g_launches{0};

@@ -37,6 +37,12 @@ void set_last_error(const char* fmt, ...);
 
 int num_sms();
 
+// Runtime options (b200_set_option): A/B switches for measurements and tests.  Initial values come from the environment
+// (B200_CONV_HALO, B200_HALO_BASE_OFFSET, B200_CONV_NARROW) the first time an option is read.
+enum Option : int { OPT_CONV_HALO = 0, OPT_HALO_BASE_OFFSET = 1, OPT_CONV_NARROW = 2, OPT_COUNT = 3 };
+int get_option(int opt);
+int set_option(const char* name, int value);
+
 // Launch accounting for bench.py's `gpu_launches` (b200_launch_count): every kernel launch of this library calls note_launch().
 void note_launch(int n = 1);
 long long launch_count();

@@ -22,6 +22,8 @@ SIGNATURES = {
     "b200_version": (_i32, []),
     "b200_num_sms": (_i32, []),
     "b200_launch_count": (_i64, []),
+    "b200_set_option": (_i32, [ctypes.c_char_p, _i32]),
+    "b200_get_option": (_i32, [ctypes.c_char_p]),
     "b200_prof_fmha_begin": (_i32, [_i32]),
     "b200_prof_fmha_end": (_i32, [_ptr, _ptr, _i32]),
     "b200_fmha_fwd_d64": (_i32, [_ptr, _i64, _ptr, _i64, _ptr, _i64, _ptr, _i64, _i64, _i64, _i32, _f32, _ptr]),
@@ -174,6 +176,15 @@ def fmha(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, *, softmax_scale: Op
     rc = fn(q.data_ptr(), q.stride(0), k.data_ptr(), k.stride(0), v.data_ptr(), v.stride(0), out.data_ptr(), out.stride(0), sq, sk, H, scale, _stream())
     _check(rc, f"b200_fmha_fwd_d{d}")
     return out
+
+
+def set_option(name: str, value: int) -> None:
+    """Runtime A/B switch of the library ("conv_halo", "halo_base_offset", "conv_narrow")."""
+    _check(load().b200_set_option(name.encode(), int(value)), "b200_set_option")
+
+
+def get_option(name: str) -> int:
+    return int(load().b200_get_option(name.encode()))
 
 
 def launch_count() -> int:
