@@ -10,9 +10,10 @@
 // temporal tap) instead of 27, and 128-byte rows are used throughout (the 96-channel tensors are read as a 64-channel chunk plus a second
 // 64-channel box whose upper 32 channels lie outside the tensor and are zero-filled by the TMA unit; only its two valid K-steps are issued).
 //
-// Row-shifted descriptors: the TMA unit swizzles by absolute shared-memory address bits (tile bases are 1024-byte aligned), the tensor
-// core by the descriptor's own row phase plus its `base_offset` field - csrc/probe.cu / tools/probe_rowshift.py measure which on hardware;
-// `kBaseOffsetMode` below encodes the outcome.
+// Row-shifted descriptors: measured on B200 with csrc/probe.cu / tools/probe_rowshift.py (profiles/r02_probe_rowshift.txt): a K-major
+// swizzled operand whose descriptor start address is moved by whole rows (128-byte rows / SWIZZLE_128B and 64-byte rows / SWIZZLE_64B,
+// shifts 0..8) is read correctly with base_offset = 0 - the tensor core, like the TMA unit, derives the swizzle phase from ABSOLUTE
+// shared-memory address bits - and incorrectly with base_offset = row % 8.  So a row-shifted view is just "start address + rows * 128".
 //
 // Work per pipeline slot (N = 96): A halo 68 KB feeds 9 taps x 2 rows x 4 K-steps = 72 MMAs (3456 tensor clocks); the nine 12 KB weight
 // tiles stream through their own ring.  Bytes per tensor clock: 51 (conv3d.cu MIXED96: 115), TMA rows per clock: 0.41 (1.22).
@@ -33,8 +34,8 @@ constexpr int HALO_A_SLOTS = 2;
 constexpr int HALO_THREADS = 256;
 constexpr int HALO_STAGING_BYTES = 128 * 64 * 2;            // 16 KB: 128 voxels x 64 output channels
 
-// HaloParams::base_offset_mode: 1 = descriptor base_offset field = start row % 8, 0 = leave it zero (tools/probe_rowshift.py decides;
-// B200_HALO_BASE_OFFSET overrides for experiments)
+// HaloParams::base_offset_mode: 0 (default, correct) leaves the descriptor's base_offset field zero; 1 sets it to start row % 8 (kept as a
+// switch for the probe experiment, option "halo_base_offset")
 
 template <int BLOCK_N>
 struct HaloCfg {

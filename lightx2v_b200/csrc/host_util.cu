@@ -33,11 +33,11 @@ int num_sms() {
 
 // ---- runtime options ---------------------------------------------------------------------------------------------------------
 #ifndef B200_CONV_HALO_DEFAULT
-#define B200_CONV_HALO_DEFAULT 0     // conv3d_halo.cu: off until verified on hardware (tools/check_halo_conv.py); flip here to make it the default
+#define B200_CONV_HALO_DEFAULT 1     // conv3d_halo.cu: verified on hardware in round 2 (profiles/r02_probe_rowshift.txt, r02_halo_parity.txt)
 #endif
 static const char* const kOptNames[OPT_COUNT] = {"conv_halo", "halo_base_offset", "conv_narrow"};
 static const char* const kOptEnv[OPT_COUNT] = {"B200_CONV_HALO", "B200_HALO_BASE_OFFSET", "B200_CONV_NARROW"};
-static const int kOptDefault[OPT_COUNT] = {B200_CONV_HALO_DEFAULT, 1, 0};
+static const int kOptDefault[OPT_COUNT] = {B200_CONV_HALO_DEFAULT, 0, 0};   // halo_base_offset 0: the tensor core swizzles by absolute address bits (probe)
 static std::atomic<int> g_opts[OPT_COUNT];
 static std::once_flag g_opts_once;
 

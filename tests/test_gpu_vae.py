@@ -200,3 +200,39 @@ def test_encoder_vs_reference_fixture_and_oracle(golden_dir, record):
     print(f"VAE encode: PSNR vs real-reference fixture {p1:.1f} dB, vs oracle at 9x96x160 {p2:.1f} dB")
     record(psnr_fixture_db=p1, psnr_oracle_db=p2, max_err_fixture=(out - mu).abs().max())
     assert p1 > 35 and p2 > 35
+
+
+@pytest.mark.parametrize("cin,cout,T,H,W", [(96, 96, 3, 7, 640), (192, 192, 2, 6, 512), (96, 16, 2, 5, 700), (192, 96, 2, 4, 512), (384, 384, 2, 3, 512)])
+def test_halo_staged_conv_vs_torch_and_vs_per_tap_tiles(lib, cin, cout, T, H, W):
+    """csrc/conv3d_halo.cu (wide 3x3x3 stages: one staged halo tile, nine taps as row-shifted UMMA views) against fp32 torch on the
+    bf16-rounded operands, with ragged H / W, the residual epilogue and the streaming (two-frame history) tap set - and against the per-tap
+    tiles of conv3d.cu, which must agree to the last bit of accumulation-order noise (same products, same fp32 accumulator, different order
+    of the 27 x cin terms)."""
+    from lightx2v_b200.host.wan_vae import _Conv
+
+    g = torch.Generator(device="cuda").manual_seed(1)
+    x = torch.randn(cin, T, H, W, generator=g, device="cuda")
+    w = torch.randn(cout, cin, 3, 3, 3, generator=g, device="cuda") / (cin * 27) ** 0.5
+    b = torch.randn(cout, generator=g, device="cuda") * 0.1
+    xb, wb, bb = x.to(torch.bfloat16).float(), w.to(torch.bfloat16).float(), b.to(torch.bfloat16).float()
+    torch.backends.cudnn.allow_tf32 = False
+    ref = V.causal_conv3d(xb.unsqueeze(0), wb, bb)[0]
+    conv = _Conv(w, b, "cuda")
+    res = torch.randn(T, H, W, conv.cout, generator=g, device="cuda").to(torch.bfloat16)
+    buf = torch.zeros(T + 2, H, W, conv.cin, dtype=torch.bfloat16, device="cuda")
+    buf[2:] = _cl(x)
+    outs = {}
+    prev = lib.get_option("conv_halo")
+    try:
+        for halo in (1, 0):
+            lib.set_option("conv_halo", halo)
+            outs[halo] = (conv(_cl(x)).clone(), conv(_cl(x), residual=res).clone(), conv.causal(buf).clone())
+    finally:
+        lib.set_option("conv_halo", prev)
+    got, got_r, got_h = (t.permute(3, 0, 1, 2).float()[:cout] for t in outs[1])
+    assert psnr(got, ref) > 45 and (got - ref).abs().max() <= 2e-2 + 1e-2 * ref.abs().max()
+    assert psnr(got_r, ref + res.permute(3, 0, 1, 2).float()[:cout]) > 45
+    assert torch.equal(outs[1][0], outs[1][2])                         # history form == zero-padded form
+    for a, b_ in zip(outs[1], outs[0]):                                # halo tiles vs per-tap tiles: bf16 outputs at most one ulp apart
+        d = (a.float() - b_.float()).abs()
+        assert d.max() <= 2.0 ** -6 * max(1.0, b_.float().abs().max().item()) and (d > 0).float().mean() < 0.05
