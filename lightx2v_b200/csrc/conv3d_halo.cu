@@ -365,10 +365,15 @@ int conv3d_cl_halo(const void* in, long long in_st, long long in_sh, long long i
   const int bo_mode = get_option(OPT_HALO_BASE_OFFSET);
   if (!get_option(OPT_CONV_HALO) || ntaps != 27 || W < 512) return 1;
   if (!(cin % 64 == 0 || cin % 64 == 32) || cin < 64) return 1;
+  // Measured on B200 (profiles/r02_conv_halo_ab.txt, r02_halo{96,192}_ncu_summary.txt): the halo tile halves the L2 traffic of every
+  // shape (lts throughput 57 % -> 27 % at N = 96), but only the 192-wide tiles were bound by it (1366 -> 1545 TFLOP/s, 77 % tensor pipe).
+  // At N = 96 / 16 the tensor core is limited by its shared-memory operand reads - (128 + N) x 32 B per 128 x N x 16 MMA = 149 B/clk at
+  // N = 96 against the ~90 B/clk the GEMM and FMHA tiles sustain - so those shapes stay on conv3d.cu's tiles (same speed, fewer
+  // resources; the 96 -> 16 head is faster there).  "conv_halo" = 2 forces the halo tiles for every eligible width (A/B runs, tests).
   int block_n;
   if (cout % 192 == 0) block_n = 192;
-  else if (cout % 96 == 0) block_n = 96;
-  else if (cout == 16) block_n = 16;
+  else if (get_option(OPT_CONV_HALO) >= 2 && cout % 96 == 0) block_n = 96;
+  else if (get_option(OPT_CONV_HALO) >= 2 && cout == 16) block_n = 16;
   else return 1;
   // taps must be the full 3 x 3 x 3 stencil in (temporal, dh, dw) order with dh, dw in {-1, 0, 1}
   for (int kt = 0; kt < 3; ++kt)

@@ -44,7 +44,7 @@ static std::once_flag g_opts_once;
 static void init_options() {
   for (int i = 0; i < OPT_COUNT; ++i) {
     const char* e = getenv(kOptEnv[i]);
-    g_opts[i].store(e ? (atoi(e) != 0) : kOptDefault[i]);
+    g_opts[i].store(e ? atoi(e) : kOptDefault[i]);
   }
 }
 int get_option(int opt) {
@@ -55,7 +55,7 @@ int set_option(const char* name, int value) {
   std::call_once(g_opts_once, init_options);
   for (int i = 0; name && i < OPT_COUNT; ++i)
     if (strcmp(name, kOptNames[i]) == 0) {
-      g_opts[i].store(value != 0);
+      g_opts[i].store(value);
       return B200_OK;
     }
   set_last_error("b200_set_option: unknown option '%s' (conv_halo, halo_base_offset, conv_narrow)", name ? name : "(null)");
