@@ -206,22 +206,21 @@ class HunyuanVAEB200:
 
     # ------------------------------------------------------------------ tile scheduling (single GPU: every tile is local)
     def _decode_tile(self, z: torch.Tensor) -> torch.Tensor:
-        """Decode one tile here, or - in a tile-parallel decode (decode_dist) - on the rank that owns it, then broadcast the result.
-        Tiles are independent units of work (the reference decodes them one after another), so sharding them needs no collective on
-        the compute path; the only exchange is the hand-over of finished tiles for the blends."""
+        """Decode one tile here, or - in a tile-parallel decode (decode_dist) - hand out the tile that the owning rank decoded.
+        Tiles are independent units of work (the reference decodes them one after another), so sharding them needs no collective on the
+        compute path.  decode_dist runs the tiling traversal twice: a PLAN pass that only records the tile inputs in traversal order,
+        then (after every rank has decoded its own tiles back to back and the finished tiles have been exchanged) the real pass, which
+        pops the finished tiles in the same order and performs the blends."""
         if self._dist is None:
             return self.decoder.decode_tile(z)
-        import torch.distributed as dist
-
-        world, rank, group = self._dist
-        owner = self._tile_counter % world
+        mode = self._dist[3]
+        if mode == "plan":
+            self._plan.append(z)
+            _, t, h, w = z.shape
+            return torch.empty((3, 1 + 4 * (t - 1), 0, 0), dtype=torch.float32, device=self.device)      # shape carrier only (no blends in the plan pass)
+        out = self._done[self._tile_counter]
+        self._done[self._tile_counter] = None
         self._tile_counter += 1
-        _, t, h, w = z.shape
-        if owner == rank:
-            out = self.decoder.decode_tile(z)
-        else:
-            out = torch.empty((3, 1 + 4 * (t - 1), 8 * h, 8 * w), dtype=torch.float32, device=self.device)
-        dist.broadcast(out, src=dist.get_global_rank(group, owner) if group is not None else owner, group=group)
         return out
 
     def _spatial_tiled(self, z: torch.Tensor) -> torch.Tensor:
@@ -231,6 +230,8 @@ class HunyuanVAEB200:
         rows = []
         for i in range(0, z.shape[-2], step):
             rows.append([self._decode_tile(z[:, :, i:i + self.tile_latent, j:j + self.tile_latent]) for j in range(0, z.shape[-1], step)])
+        if self._dist is not None and self._dist[3] == "plan":
+            return rows[0][0]
         out_rows = []
         for i, row in enumerate(rows):
             out = []
@@ -257,6 +258,8 @@ class HunyuanVAEB200:
             if i > 0:
                 dec = dec[:, 1:]
             row.append(dec)
+        if self._dist is not None and self._dist[3] == "plan":
+            return row[0]
         out = []
         for i, tile in enumerate(row):
             if i > 0:
@@ -266,32 +269,52 @@ class HunyuanVAEB200:
                 out.append(tile[:, :limit + 1])
         return torch.cat(out, dim=1)
 
+    def _traverse(self, z: torch.Tensor) -> torch.Tensor:
+        if z.shape[1] > self.tile_tlatent:
+            return self._temporal_tiled(z)
+        if z.shape[-1] > self.tile_latent or z.shape[-2] > self.tile_latent:
+            return self._spatial_tiled(z)
+        return self._decode_tile(z)
+
     @torch.no_grad()
     def decode_device(self, latents: torch.Tensor) -> torch.Tensor:
         """latents [1, 16, T, H, W] -> [1, 3, T', 8H, 8W] fp32 in [0, 1], still on the GPU."""
         z = latents.to(self.device, torch.float32)[0]
-        if z.shape[1] > self.tile_tlatent:
-            img = self._temporal_tiled(z)
-        elif z.shape[-1] > self.tile_latent or z.shape[-2] > self.tile_latent:
-            img = self._spatial_tiled(z)
-        else:
-            img = self._decode_tile(z)
-        return img.mul_(0.5).add_(0.5).clamp_(0, 1).unsqueeze(0)
+        return self._traverse(z).mul_(0.5).add_(0.5).clamp_(0, 1).unsqueeze(0)
 
     @torch.no_grad()
     def decode_dist(self, latents: torch.Tensor, group=None, to_cpu: bool = True) -> torch.Tensor:
         """Tile-parallel decode over the ranks of `group`: tile k of the reference's (temporal, row, column) tile order is decoded by
-        rank k mod P and broadcast; every rank then performs the same blends and returns the same video (bit-identical to `decode`,
-        since each tile is computed by the same kernels on the same inputs).  The reference has no parallel Hunyuan VAE (its Wan VAE has
-        `parallel_vae`, hf/wan/vae.py:883-929); with 84 independent tiles at 720p x 129f this is the natural B200 sharding."""
+        rank k mod P; every rank decodes ITS tiles back to back (no communication in between), then the finished tiles are exchanged
+        (one broadcast per tile, all enqueued together) and every rank performs the same blends and returns the same video -
+        bit-identical to `decode`, since each tile is computed by the same kernels on the same inputs.  (Round 1 interleaved one
+        broadcast after every tile, which serialised the ranks behind each other: 33 MPix/s on 8 GPUs against 29 on one.)  The
+        reference has no parallel Hunyuan VAE (its Wan VAE has `parallel_vae`, hf/wan/vae.py:883-929); with 84 independent tiles at
+        720p x 129f this is the natural B200 sharding."""
         import torch.distributed as dist
 
-        self._dist = (dist.get_world_size(group), dist.get_rank(group), group)
-        self._tile_counter = 0
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
+        z = latents.to(self.device, torch.float32)[0]
+        self._plan, self._done, self._tile_counter = [], [], 0
         try:
-            img = self.decode_device(latents)
+            self._dist = (world, rank, group, "plan")
+            self._traverse(z)                                            # records the tile inputs in traversal order
+            tiles = self._plan
+            done = [None] * len(tiles)
+            for k, zt in enumerate(tiles):                               # my tiles, back to back
+                if k % world == rank:
+                    done[k] = self.decoder.decode_tile(zt)
+            for k, zt in enumerate(tiles):                               # hand-over of the finished tiles
+                if done[k] is None:
+                    _, t, h, w = zt.shape
+                    done[k] = torch.empty((3, 1 + 4 * (t - 1), 8 * h, 8 * w), dtype=torch.float32, device=self.device)
+                owner = k % world
+                dist.broadcast(done[k], src=dist.get_global_rank(group, owner) if group is not None else owner, group=group)
+            self._done, self._tile_counter = done, 0
+            self._dist = (world, rank, group, "blend")
+            img = self._traverse(z).mul_(0.5).add_(0.5).clamp_(0, 1).unsqueeze(0)
         finally:
-            self._dist = None
+            self._dist, self._plan, self._done = None, [], []
         return img.cpu().float() if to_cpu else img
 
     @torch.no_grad()
