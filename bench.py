@@ -406,6 +406,10 @@ def run_ours(args):
                     "d2h_bytes_per_step": d2h},
             "gpu_launches": int(launches),
             "gpu_launches_source": "b200_launch_count(): counted inside libb200dit.so at every kernel launch (this rank)",
+            # where the step goes: the self-attention launches (CUDA events inside the library) vs everything else (GEMMs, row-wise kernels,
+            # pre/post-infer, scheduler, and - at N > 1 - the exchange kernels and the two symmetric-memory barriers per block)
+            "step_breakdown_ms": (lambda fm: {"self_attention": round(fm, 1), "everything_else": round(ms_resident - fm, 1)})(
+                sum(r[0] for r in prof if r[1] == r[2] and r[1] >= S and r[0] > 0) / max(1, args.steps)),
             "clocks": clk,
             "roofline": roof,
         }
