@@ -10,7 +10,10 @@ the two varlen segments of cu_seqlens = [0, img+txt_valid, img+txt_pad] (pre_inf
 `x + gate * proj(attn)` and `x + gate * fc2(...)` are GEMM epilogues; GELU(tanh) is the fc1 epilogue.
 Single block: linear1 is issued as two GEMMs on row-slices of its weight (qkv part, mlp part with GELU epilogue) into an [L, 8D] buffer
 laid out [q | k | v | attn | gelu(mlp)] so that linear2 reads its [attn | mlp] operand in place (no torch.cat, :368).
-i2v token replacement (token_replace_vec) is not implemented on this path (t2v configs only)."""
+i2v token replacement (token_replace_vec, frist_frame_token_num; :100-103, 192-209, 281-286, 316-328, 373-378): the tokens of the conditioning
+frame follow the t = 0 embedding, i.e. the first rows of the image stream take their shift / scale / gate from `mod(silu(token_replace_vec))` -
+here simply a second `ln_modulate` / GEMM-epilogue call on that row range (like the reference, phase 3 of the double block gates every image
+row with the ordinary gate)."""
 from __future__ import annotations
 
 from typing import Dict, Tuple
@@ -92,17 +95,19 @@ class HunyuanTransformerInfer:
         self.scheduler = scheduler
 
     def infer(self, weights, img, txt, vec, cu_seqlens_qkv, max_seqlen_qkv, freqs_cis, token_replace_vec=None, frist_frame_token_num=None):
-        if token_replace_vec is not None:
-            raise lib.B200Error("HunyuanTransformerInfer(B200): i2v token replacement is not implemented on this path")
+        if token_replace_vec is not None and self.parallel_attention is not None:
+            raise lib.B200Error("HunyuanTransformerInfer(B200): token replacement together with sequence parallelism is not implemented")
         return self.infer_func(weights, img, txt, vec, cu_seqlens_qkv, max_seqlen_qkv, freqs_cis, token_replace_vec, frist_frame_token_num)
 
     def _infer_without_offload(self, weights, img, txt, vec, cu_seqlens_qkv, max_seqlen_qkv, freqs_cis, token_replace_vec, frist_frame_token_num):
         img_seq_len = img.shape[0]
         for i in range(self.double_blocks_num):
-            img, txt = self.infer_double_block(weights.double_blocks[i], img, txt, vec, cu_seqlens_qkv, max_seqlen_qkv, freqs_cis)
+            img, txt = self.infer_double_block(weights.double_blocks[i], img, txt, vec, cu_seqlens_qkv, max_seqlen_qkv, freqs_cis, token_replace_vec,
+                                               frist_frame_token_num)
         x = torch.cat((img, txt), 0)
         for i in range(self.single_blocks_num):
-            x = self.infer_single_block(weights.single_blocks[i], x, vec, txt.shape[0], cu_seqlens_qkv, max_seqlen_qkv, freqs_cis)
+            x = self.infer_single_block(weights.single_blocks[i], x, vec, txt.shape[0], cu_seqlens_qkv, max_seqlen_qkv, freqs_cis, token_replace_vec,
+                                        frist_frame_token_num)
         return x[:img_seq_len, ...], vec
 
     # ------------------------------------------------------------------ helpers
@@ -131,6 +136,24 @@ class HunyuanTransformerInfer:
         w = mm.weight.t()
         return w if w.is_contiguous() else w.contiguous()
 
+    @staticmethod
+    def _ln_rows(x, mod, tr, first, i_scale, i_shift, out):
+        """LayerNorm (no affine) + modulation into `out`; with token replacement the first `first` rows use the `tr` vectors."""
+        if tr is None or not first:
+            return lib.ln_modulate(x, scale=mod[i_scale], shift=mod[i_shift], out=out)
+        lib.ln_modulate(x[:first], scale=tr[i_scale], shift=tr[i_shift], out=out[:first])
+        lib.ln_modulate(x[first:], scale=mod[i_scale], shift=mod[i_shift], out=out[first:])
+        return out
+
+    def _gated_linear(self, a, mm, x, mod, tr, first, i_gate):
+        """x += gate * (a @ W^T + b) as a GEMM epilogue; two row ranges when the first rows carry the token-replace gate."""
+        w = self._nk(mm)
+        if tr is None or not first:
+            return lib.gemm_bf16(a, w, mm.bias, out=x, epilogue=lib.EPI_GATE_RESIDUAL, gate=mod[i_gate])
+        lib.gemm_bf16(a[:first], w, mm.bias, out=x[:first], epilogue=lib.EPI_GATE_RESIDUAL, gate=tr[i_gate])
+        lib.gemm_bf16(a[first:], w, mm.bias, out=x[first:], epilogue=lib.EPI_GATE_RESIDUAL, gate=mod[i_gate])
+        return x
+
     def _attention(self, qkv3, bounds, out, o_cols, txt_len=None):
         """qkv3: [L, 3, H, 128] view; out: [L, *] buffer whose columns o_cols hold the attention output [L, H*128].
         With `parallel_attention` set (Ulysses, host/ulysses.py:HunyuanUlyssesAttention) the image rows are this rank's shard,
@@ -154,8 +177,10 @@ class HunyuanTransformerInfer:
         vec_silu = F.silu(vec)
         im = weights.img_mod.apply(vec_silu).reshape(6, D)            # shift1, scale1, gate1, shift2, scale2, gate2   (:89-97)
         tm = weights.txt_mod.apply(vec_silu).reshape(6, D)
+        tr = weights.img_mod.apply(F.silu(token_replace_vec)).reshape(6, D) if token_replace_vec is not None else None     # :100-103
+        first = int(frist_frame_token_num) if tr is not None else 0
         qkv = self._buf("qkv", (L, 3 * D), dev)                       # joint [img; txt] buffer: no torch.cat of q, k, v
-        n_img = lib.ln_modulate(img, scale=im[1], shift=im[0], out=self._buf("n_img", (Li, D), dev))
+        n_img = self._ln_rows(img, im, tr, first, 1, 0, self._buf("n_img", (Li, D), dev))
         lib.gemm_bf16(n_img, self._nk(weights.img_attn_qkv), weights.img_attn_qkv.bias, out=qkv[:Li])
         n_txt = lib.ln_modulate(txt, scale=tm[1], shift=tm[0], out=self._buf("n_txt", (Lt, D), dev))
         lib.gemm_bf16(n_txt, self._nk(weights.txt_attn_qkv), weights.txt_attn_qkv.bias, out=qkv[Li:])
@@ -168,10 +193,10 @@ class HunyuanTransformerInfer:
         attn = self._buf("attn", (L, D), dev)
         self._attention(q3, self._bounds(cu_seqlens_qkv), attn, (0, D), txt_len=Lt)
         # x = x + proj(attn) * gate1  -> GEMM epilogue, in place on the stream tensors (the reference makes new tensors, same values)
-        lib.gemm_bf16(attn[:Li], self._nk(weights.img_attn_proj), weights.img_attn_proj.bias, out=img, epilogue=lib.EPI_GATE_RESIDUAL, gate=im[2])
+        self._gated_linear(attn[:Li], weights.img_attn_proj, img, im, tr, first, 2)
         lib.gemm_bf16(attn[Li:], self._nk(weights.txt_attn_proj), weights.txt_attn_proj.bias, out=txt, epilogue=lib.EPI_GATE_RESIDUAL, gate=tm[2])
         for x, mod, fc1, fc2, nm in ((img, im, weights.img_mlp_fc1, weights.img_mlp_fc2, "img"), (txt, tm, weights.txt_mlp_fc1, weights.txt_mlp_fc2, "txt")):
-            n = lib.ln_modulate(x, scale=mod[4], shift=mod[3], out=self._buf("n_" + nm, tuple(x.shape), dev))
+            n = self._ln_rows(x, mod, tr if nm == "img" else None, first, 4, 3, self._buf("n_" + nm, tuple(x.shape), dev))
             h = lib.gemm_bf16(n, self._nk(fc1), fc1.bias, out=self._buf("h_" + nm, (x.shape[0], self.mlp_hidden_dim), dev), epilogue=lib.EPI_BIAS_GELU)
             lib.gemm_bf16(h, self._nk(fc2), fc2.bias, out=x, epilogue=lib.EPI_GATE_RESIDUAL, gate=mod[5])
         return img, txt
@@ -182,7 +207,9 @@ class HunyuanTransformerInfer:
         L = x.shape[0]
         dev = x.device
         mod = weights.modulation.apply(F.silu(vec)).reshape(3, D)     # shift, scale, gate   (:309-311)
-        n = lib.ln_modulate(x, scale=mod[1], shift=mod[0], out=self._buf("n_x", (L, D), dev))
+        tr = weights.modulation.apply(F.silu(token_replace_vec)).reshape(3, D) if token_replace_vec is not None else None    # :313-316
+        first = int(frist_frame_token_num) if tr is not None else 0
+        n = self._ln_rows(x, mod, tr, first, 1, 0, self._buf("n_x", (L, D), dev))
         w1, b1 = self._nk(weights.linear1), weights.linear1.bias
         buf = self._buf("lin1", (L, 4 * D + M), dev)                  # [q | k | v | attn | gelu(mlp)]
         lib.gemm_bf16(n, w1[: 3 * D], b1[: 3 * D], out=buf[:, : 3 * D])
@@ -193,5 +220,5 @@ class HunyuanTransformerInfer:
         lib.rms_rope_heads_(q3[:, 0], weights.q_norm.weight, q3[:, 1], weights.k_norm.weight, eps=weights.q_norm.eps, cos_sin=cs, rope_rows=Li)
         self._attention(q3, self._bounds(cu_seqlens_qkv), buf, (3 * D, 4 * D), txt_len=txt_seq_len)
         # x = x + linear2([attn | gelu(mlp)]) * gate
-        lib.gemm_bf16(buf[:, 3 * D:], self._nk(weights.linear2), weights.linear2.bias, out=x, epilogue=lib.EPI_GATE_RESIDUAL, gate=mod[2])
+        self._gated_linear(buf[:, 3 * D:], weights.linear2, x, mod, tr, first, 2)
         return x

@@ -642,7 +642,46 @@ def gen_vae_encode_fixture():
     print("wan_vae_encode_small", tuple(mu.shape), "absmax", float(mu.abs().max()))
 
 
+def gen_hunyuan_i2v_fixture():
+    """Real HunyuanTransformerInfer with i2v token replacement (token_replace_vec, frist_frame_token_num; transformer_infer.py:100-103,
+    192-209, 281-286, 316-328, 373-378): one double + one single block at width 3072, 96 image tokens of which the first 24 (the
+    conditioning frame) follow the t = 0 embedding, 32 text tokens."""
+    from safetensors.torch import save_file
+
+    import lightx2v.common.ops  # noqa: F401
+    from lightx2v.models.networks.hunyuan.infer.transformer_infer import HunyuanTransformerInfer
+    from lightx2v.models.networks.hunyuan.weights.transformer_weights import HunyuanTransformerDoubleBlock, HunyuanTransformerSingleBlock
+
+    from oracle import hunyuan_oracle as HO
+
+    hidden, mlp, heads, first = 3072, 12288, 24, 24
+    cfg = Cfg(cpu_offload=False, do_mm_calib=False, mm_config={}, attention_type="torch_sdpa", task="i2v")
+    W = HO.synth_weights(1, 1, hidden, mlp, seed=42)
+    img, txt, vec, cu, freqs = HO.synth_inputs(96, 32, 32, hidden, seed=7)
+    trv = torch.randn(1, hidden, generator=torch.Generator().manual_seed(9)).to(torch.bfloat16)
+    dbl, sgl = HunyuanTransformerDoubleBlock(0, cfg), HunyuanTransformerSingleBlock(0, cfg)
+    dbl.load(W)
+    sgl.load(W)
+    infer = HunyuanTransformerInfer(cfg)
+    cu_t = torch.tensor(cu, dtype=torch.int32)
+    max_len = img.shape[0] + txt.shape[0]
+    img1, txt1 = infer.infer_double_block(dbl, img.clone(), txt.clone(), vec, cu_t, max_len, freqs, trv, first)
+    x = torch.cat((img1, txt1), 0)
+    x2 = infer.infer_single_block(sgl, x, vec, txt.shape[0], cu_t, max_len, freqs, trv, first)
+    save_file({"img": img, "txt": txt, "vec": vec, "token_replace_vec": trv, "cos": freqs[0], "sin": freqs[1], "img_after_double": img1.contiguous(),
+               "txt_after_double": txt1.contiguous(), "x_after_single": x2.contiguous()},
+              os.path.join(GOLD, "hunyuan_blocks_i2v_small.safetensors"),
+              metadata={"hidden": str(hidden), "mlp": str(mlp), "heads": str(heads), "weights_seed": "42", "inputs_seed": "7", "txt_valid": "32",
+                        "first_frame_tokens": str(first), "generator": "oracle/gen_golden.py:gen_hunyuan_i2v_fixture", "reference": "ModelTC/lightx2v@0591c35e"})
+    print("hunyuan_blocks_i2v_small", float(x2.float().abs().max()), os.path.getsize(os.path.join(GOLD, "hunyuan_blocks_i2v_small.safetensors")))
+
+
 if __name__ == "__main__":
+    if os.environ.get("GOLDEN_ONLY", "") == "hunyuan_i2v":
+        install_shims()
+        os.makedirs(GOLD, exist_ok=True)
+        gen_hunyuan_i2v_fixture()
+        sys.exit(0)
     if os.environ.get("GOLDEN_ONLY", "") == "vae_encode":
         install_shims()
         os.makedirs(GOLD, exist_ok=True)
@@ -723,3 +762,4 @@ if __name__ == "__main__":
         gen_cogvideox_fixture()
         gen_hunyuan_prepost_fixture()
         gen_vae_encode_fixture()
+        gen_hunyuan_i2v_fixture()

@@ -44,15 +44,33 @@ def _qkv_heads(qkv, heads):
     return qkv.view(L, 3, heads, -1).unbind(1)                         # "L (K H D) -> K L H D"
 
 
-def infer_double_block(W: Dict[str, torch.Tensor], i: int, img, txt, vec, cu_seqlens, freqs_cis, heads: int, attn="torch_sdpa"):
-    """transformer_infer.py:234-277 (phases :86-232)."""
+def _mod_rows(h, mod, tr, first, i_scale, i_shift):
+    """`norm * (1 + scale) + shift` with the token-replace modulation on the first `first` rows (i2v: the tokens of the conditioning
+    frame follow the t = 0 embedding) - transformer_infer.py:204-209, 281-286, 323-328."""
+    if tr is None:
+        return h * (1 + mod[i_scale]) + mod[i_shift]
+    return torch.concat((h[:first] * (1 + tr[i_scale]) + tr[i_shift], h[first:] * (1 + mod[i_scale]) + mod[i_shift]), dim=0)
+
+
+def _gate_rows(out, mod, tr, first, i_gate):
+    """`out * gate` with the token-replace gate on the first rows - transformer_infer.py:192-198, 373-378."""
+    if tr is None:
+        return out * mod[i_gate]
+    return torch.concat((out[:first] * tr[i_gate], out[first:] * mod[i_gate]), dim=0)
+
+
+def infer_double_block(W: Dict[str, torch.Tensor], i: int, img, txt, vec, cu_seqlens, freqs_cis, heads: int, attn="torch_sdpa", token_replace_vec=None,
+                       first_frame_tokens=None):
+    """transformer_infer.py:234-277 (phases :86-232).  NOTE: with token replacement the reference's phase 3 (:224-232) applies the ORDINARY
+    img_mod2_gate to every image row (tr_img_mod2_gate is computed and returned by phase 1 but never used) - restated as is."""
     p = f"double_blocks.{i}."
     vec_silu = F.silu(vec)
     im = mm_named(W, p + "img_mod.linear", vec_silu).chunk(6, dim=-1)      # shift1, scale1, gate1, shift2, scale2, gate2
     tm = mm_named(W, p + "txt_mod.linear", vec_silu).chunk(6, dim=-1)
+    tr = mm_named(W, p + "img_mod.linear", F.silu(token_replace_vec)).chunk(6, dim=-1) if token_replace_vec is not None else None     # :100-103
 
     def pre_atten(x, mod, pre, rope):
-        x_mod = F.layer_norm(x, (x.shape[1],), None, None, 1e-6) * (1 + mod[1]) + mod[0]                     # :280-286
+        x_mod = _mod_rows(F.layer_norm(x, (x.shape[1],), None, None, 1e-6), mod, tr if rope else None, first_frame_tokens, 1, 0)   # :280-286
         q, k, v = _qkv_heads(mm_named(W, p + pre + "_attn_qkv", x_mod), heads)
         q = rms_norm(q, W[p + pre + "_attn_q_norm.weight"])
         k = rms_norm(k, W[p + pre + "_attn_k_norm.weight"])
@@ -69,8 +87,9 @@ def infer_double_block(W: Dict[str, torch.Tensor], i: int, img, txt, vec, cu_seq
     txt_out = mm_named(W, p + "txt_attn_proj", txt_attn)
 
     def mlp(x, out, mod, pre):
-        x = x + out * mod[2]                                                                                   # :192-199 / :215-216
-        h = F.layer_norm(x, (x.shape[1],), None, None, 1e-6) * (1 + mod[4]) + mod[3]
+        t = tr if pre == "img" else None
+        x = x + _gate_rows(out, mod, t, first_frame_tokens, 2)                                                 # :192-199 / :215-216
+        h = _mod_rows(F.layer_norm(x, (x.shape[1],), None, None, 1e-6), mod, t, first_frame_tokens, 4, 3)
         h = F.gelu(mm_named(W, p + pre + "_mlp.fc1", h), approximate="tanh")
         h = mm_named(W, p + pre + "_mlp.fc2", h)
         return x + h * mod[5]                                                                                  # phase 3 :224-232
@@ -78,11 +97,14 @@ def infer_double_block(W: Dict[str, torch.Tensor], i: int, img, txt, vec, cu_seq
     return mlp(img, img_out, im, "img"), mlp(txt, txt_out, tm, "txt")
 
 
-def infer_single_block(W, i: int, x, vec, txt_seq_len: int, cu_seqlens, freqs_cis, heads: int, hidden: int, attn="torch_sdpa"):
+def infer_single_block(W, i: int, x, vec, txt_seq_len: int, cu_seqlens, freqs_cis, heads: int, hidden: int, attn="torch_sdpa", token_replace_vec=None,
+                       first_frame_tokens=None):
     """transformer_infer.py:308-384."""
     p = f"single_blocks.{i}."
-    mod_shift, mod_scale, mod_gate = mm_named(W, p + "modulation.linear", F.silu(vec)).chunk(3, dim=-1)
-    x_mod = F.layer_norm(x, (x.shape[1],), None, None, 1e-6) * (1 + mod_scale) + mod_shift
+    mod = mm_named(W, p + "modulation.linear", F.silu(vec)).chunk(3, dim=-1)                     # shift, scale, gate
+    tr = mm_named(W, p + "modulation.linear", F.silu(token_replace_vec)).chunk(3, dim=-1) if token_replace_vec is not None else None
+    mod_gate = mod[2]
+    x_mod = _mod_rows(F.layer_norm(x, (x.shape[1],), None, None, 1e-6), mod, tr, first_frame_tokens, 1, 0)
     x_mod = mm_named(W, p + "linear1", x_mod)
     qkv, mlp = torch.split(x_mod, [3 * hidden, x_mod.shape[1] - 3 * hidden], dim=-1)
     q, k, v = _qkv_heads(qkv, heads)
@@ -95,17 +117,18 @@ def infer_single_block(W, i: int, x, vec, txt_seq_len: int, cu_seqlens, freqs_ci
     attn_out = varlen_attention(q, k, v, cu_seqlens, attn)
     out = torch.cat((attn_out, F.gelu(mlp, approximate="tanh")), 1)
     out = mm_named(W, p + "linear2", out)
-    return x + out * mod_gate                                                                                  # :371-379
+    return x + _gate_rows(out, mod, tr, first_frame_tokens, 2)                                                 # :371-379
 
 
-def infer_blocks(W, n_double: int, n_single: int, img, txt, vec, cu_seqlens, freqs_cis, heads: int, attn="torch_sdpa"):
+def infer_blocks(W, n_double: int, n_single: int, img, txt, vec, cu_seqlens, freqs_cis, heads: int, attn="torch_sdpa", token_replace_vec=None,
+                 first_frame_tokens=None):
     """_infer_without_offload — transformer_infer.py:71-84."""
     hidden = img.shape[1]
     for i in range(n_double):
-        img, txt = infer_double_block(W, i, img, txt, vec, cu_seqlens, freqs_cis, heads, attn)
+        img, txt = infer_double_block(W, i, img, txt, vec, cu_seqlens, freqs_cis, heads, attn, token_replace_vec, first_frame_tokens)
     x = torch.cat((img, txt), 0)
     for i in range(n_single):
-        x = infer_single_block(W, i, x, vec, txt.shape[0], cu_seqlens, freqs_cis, heads, hidden, attn)
+        x = infer_single_block(W, i, x, vec, txt.shape[0], cu_seqlens, freqs_cis, heads, hidden, attn, token_replace_vec, first_frame_tokens)
     return x[: img.shape[0]]
 
 

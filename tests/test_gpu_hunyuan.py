@@ -127,3 +127,29 @@ def test_hunyuan_pre_and_post_infer_vs_reference_fixture(golden_dir, record):
     out = post.infer(W, T["img"], T["vec"])
     assert out.dtype == torch.float32 and out.shape == T["post_out"].shape
     close(out, T["post_out"], "post_infer")
+
+
+def test_i2v_token_replace_blocks_vs_reference_fixture(golden_dir, record):
+    """HunyuanVideo i2v: the first rows of the image stream (the conditioning frame's tokens) take their modulation from
+    mod(silu(token_replace_vec)); CUDA path vs the fixture of the REAL HunyuanTransformerInfer (one double + one single block)."""
+    with safe_open(os.path.join(golden_dir, "hunyuan_blocks_i2v_small.safetensors"), framework="pt") as f:
+        T = {k: f.get_tensor(k) for k in f.keys()}
+        meta = f.metadata()
+    hidden, mlp, first = int(meta["hidden"]), int(meta["mlp"]), int(meta["first_frame_tokens"])
+    W = HO.synth_weights(1, 1, hidden, mlp, seed=int(meta["weights_seed"]))
+    weights, infer = _build(W, 1, 1)
+    Li, Lt = T["img"].shape[0], T["txt"].shape[0]
+    cu = [0, Li + int(meta["txt_valid"]), Li + Lt]
+    freqs = (T["cos"].cuda(), T["sin"].cuda())
+    trv = T["token_replace_vec"].cuda()
+    img, txt = infer.infer_double_block(weights.double_blocks[0], T["img"].cuda().clone(), T["txt"].cuda().clone(), T["vec"].cuda(), cu, Li + Lt, freqs, trv, first)
+    f1, m1 = _bad(img, T["img_after_double"])
+    f2, m2 = _bad(txt, T["txt_after_double"])
+    x = infer.infer_single_block(weights.single_blocks[0], torch.cat((T["img_after_double"], T["txt_after_double"])).cuda(), T["vec"].cuda(), Lt, cu, Li + Lt,
+                                 freqs, trv, first)
+    f3, m3 = _bad(x, T["x_after_single"])
+    record(double_img_bad_frac=f1, double_img_max=m1, double_txt_bad_frac=f2, single_bad_frac=f3, single_max=m3)
+    assert f1 < 2e-3 and f2 < 2e-3 and f3 < 2e-3 and max(m1, m2, m3) < 0.13
+    # and the t2v path of the same weights differs (the replacement is not a no-op)
+    img_t2v, _ = infer.infer_double_block(weights.double_blocks[0], T["img"].cuda().clone(), T["txt"].cuda().clone(), T["vec"].cuda(), cu, Li + Lt, freqs)
+    assert not torch.equal(img_t2v[:first], img[:first]) and _bad(img_t2v[first:], img[first:])[0] < 5e-2

@@ -210,3 +210,22 @@ def test_vae_encoder_oracle_matches_reference_fixture(golden_dir):
     T, _ = _load(os.path.join(golden_dir, "wan_vae_encode_small.safetensors"))
     out = V.vae_encode(V.synth_vae_encoder_weights(0), T["video"])
     assert torch.equal(out, T["mu"])
+
+
+def test_hunyuan_i2v_token_replace_oracle_matches_reference_fixture(golden_dir):
+    """oracle/hunyuan_oracle.py with token_replace_vec / first_frame_tokens vs the REAL HunyuanTransformerInfer i2v path, bit for bit."""
+    from oracle import hunyuan_oracle as HO
+
+    torch.set_num_threads(8)
+    T, meta = _load(os.path.join(golden_dir, "hunyuan_blocks_i2v_small.safetensors"))
+    hidden, mlp, heads, first = int(meta["hidden"]), int(meta["mlp"]), int(meta["heads"]), int(meta["first_frame_tokens"])
+    W = HO.synth_weights(1, 1, hidden, mlp, seed=int(meta["weights_seed"]))
+    L_img, L_txt = T["img"].shape[0], T["txt"].shape[0]
+    cu = [0, L_img + int(meta["txt_valid"]), L_img + L_txt]
+    freqs = (T["cos"], T["sin"])
+    img1, txt1 = HO.infer_double_block(W, 0, T["img"].clone(), T["txt"].clone(), T["vec"], cu, freqs, heads, token_replace_vec=T["token_replace_vec"],
+                                       first_frame_tokens=first)
+    assert torch.equal(img1, T["img_after_double"]) and torch.equal(txt1, T["txt_after_double"])
+    x2 = HO.infer_single_block(W, 0, torch.cat((img1, txt1)), T["vec"], L_txt, cu, freqs, heads, hidden, token_replace_vec=T["token_replace_vec"],
+                               first_frame_tokens=first)
+    assert torch.equal(x2, T["x_after_single"])
