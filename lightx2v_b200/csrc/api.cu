@@ -69,7 +69,7 @@ int b200_num_sms(void) { return b200::num_sms(); }
 int64_t b200_launch_count(void) { return b200::launch_count(); }
 int b200_set_option(const char* name, int value) { return b200::set_option(name, value); }
 int b200_get_option(const char* name) {
-  static const char* const names[b200::OPT_COUNT] = {"conv_halo", "halo_base_offset", "conv_narrow", "conv_t96"};
+  static const char* const names[b200::OPT_COUNT] = {"conv_halo", "halo_base_offset", "conv_narrow"};
   for (int i = 0; name && i < b200::OPT_COUNT; ++i)
     if (strcmp(name, names[i]) == 0) return b200::get_option(i);
   return -1;

@@ -361,250 +361,6 @@ conv3d_igemm_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_const
   }
 }
 
-// =====================================================================================================================
-// Transposed tiles for cout = 96 (the 96-channel 720 x 1280 stage: 35 % of the Wan decode).
-//
-// With the voxels as M and the 96 output channels as N, a 128 x 96 x 16 MMA reads (128 + 96) x 32 B of shared-memory operands per 48
-// tensor clocks = 149 B/clk, against the ~90 B/clk the tensor core's operand path sustains (GEMM / FMHA tiles): the round-2 ncu captures
-// show 45-50 % tensor pipe whatever the L2 traffic (per-tap tiles: lts 57 %, halo tiles: 27 %).  Here the roles are swapped,
-//     D^T[128 (96 valid), 256 voxels] = W[128, K] * X[256 voxels, K]^T,
-// i.e. the weights are the M operand (rows 96..127 lie outside the weight matrix and are zero-filled by the TMA unit) and 256 voxels
-// (two 32 x 4 boxes) the N operand: (128 + 256) x 32 B per 128 clocks = 96 B/clk, the GEMM's ratio, at 75 % useful rows.  The accumulator
-// comes out channel-major (TMEM lane = output channel, column = voxel); the epilogue transposes it through shared memory (2-byte stores
-// into the same 128B-swizzled staging layout the TMA store of the other tiles uses).
-// K pipeline: slots of 48 KB, one per 64-channel sub-stage (W 16 KB + X 32 KB); the 32-channel remainder of cin = 96 uses half a slot.
-// =====================================================================================================================
-constexpr int T96_SLOT_BYTES = 48 * 1024;
-constexpr int T96_SLOTS = 4;
-constexpr int T96_SMEM_BYTES = T96_SLOTS * T96_SLOT_BYTES + 2 * CONV_STAGING_BYTES + 1024 + 256;
-static_assert(T96_SMEM_BYTES <= 232448, "shared memory budget exceeded");
-
-template <int MODE>
-__global__ void __launch_bounds__(CONV_THREADS, 1)
-conv3d_t96_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmIn2,
-                  const __grid_constant__ CUtensorMap tmW2, const __grid_constant__ CUtensorMap tmOut, const ConvParams p) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* sStage = smem + T96_SLOTS * T96_SLOT_BYTES;      // 2 x 16 KB: channels 0..63 / 64..95 of one 128-voxel sub-tile
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sStage + 2 * CONV_STAGING_BYTES);
-  uint64_t* full_bar = bars;
-  uint64_t* empty_bar = bars + T96_SLOTS;
-  uint64_t* tmem_full_bar = bars + 2 * T96_SLOTS;
-  uint64_t* tmem_empty_bar = bars + 2 * T96_SLOTS + 2;
-  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(bars + 2 * T96_SLOTS + 4);
-
-  const int warp = threadIdx.x >> 5;
-  const int lane = threadIdx.x & 31;
-  const int tiles_per_frame = p.tiles_w * p.tiles_h;
-  const int num_tiles = p.T * tiles_per_frame;
-  // sub-stages per tap: WIDE cin / 64 (each 64 channels); MIXED96 (cin / 96) x [64, 32]
-  const int groups = MODE == CONV_WIDE ? p.cin / 64 : p.cin / 96;
-  const int subs_per_tap = MODE == CONV_WIDE ? groups : 2 * groups;
-  const int num_subs = p.ntaps * subs_per_tap;
-
-  if (warp == 0 && lane == 0) {
-    prefetch_tmap(&tmIn);
-    prefetch_tmap(&tmW);
-    prefetch_tmap(&tmOut);
-  }
-  if (warp == 1 && lane == 0) {
-    for (int i = 0; i < T96_SLOTS; ++i) {
-      mbar_init(&full_bar[i], 1);
-      mbar_init(&empty_bar[i], 1);
-    }
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(&tmem_full_bar[i], 1);
-      mbar_init(&tmem_empty_bar[i], 128);
-    }
-    fence_mbar_init();
-  }
-  if (warp == 2) tmem_alloc(tmem_base_slot, 512);
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_base_slot;
-
-  auto tile_coords = [&](int tile, int& t, int& h0, int& w0) {
-    t = tile / tiles_per_frame;
-    const int m = tile - t * tiles_per_frame;
-    h0 = (m / p.tiles_w) * (2 * CONV_BH);
-    w0 = (m % p.tiles_w) * CONV_BW;
-  };
-  // sub-stage index -> (tap, first channel, 64- or 32-channel kind)
-  auto sub_coords = [&](int sidx, int& tap, int& cc, bool& narrow) {
-    tap = sidx / subs_per_tap;
-    const int r = sidx - tap * subs_per_tap;
-    if constexpr (MODE == CONV_WIDE) {
-      cc = r * 64;
-      narrow = false;
-    } else {
-      cc = (r >> 1) * 96 + (r & 1) * 64;
-      narrow = (r & 1) != 0;
-    }
-  };
-
-  if (warp == 0) {
-    // ===================== TMA producer =====================
-    if (lane == 0) {
-      int slot = 0;
-      uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        int t, h0, w0;
-        tile_coords(tile, t, h0, w0);
-        for (int sidx = 0; sidx < num_subs; ++sidx) {
-          int tap, cc;
-          bool narrow;
-          sub_coords(sidx, tap, cc, narrow);
-          mbar_wait(&empty_bar[slot], phase ^ 1);
-          uint8_t* sW = smem + slot * T96_SLOT_BYTES;
-          uint8_t* sX = sW + 16 * 1024;
-          if (!narrow) {
-            mbar_arrive_expect_tx(&full_bar[slot], 48 * 1024);
-            tma_load_2d(sW, &tmW, &full_bar[slot], tap * p.cin + cc, 0);                    // box {64, 128 rows}: rows >= cout read as zero
-#pragma unroll
-            for (int ms = 0; ms < 2; ++ms)
-              tma_load_4d(sX + ms * 16 * 1024, &tmIn, &full_bar[slot], cc, w0 + p.dw[tap], h0 + ms * CONV_BH + p.dh[tap], t + p.dt[tap]);
-          } else {
-            mbar_arrive_expect_tx(&full_bar[slot], 24 * 1024);
-            tma_load_2d(sW, &tmW2, &full_bar[slot], tap * p.cin + cc, 0);                   // box {32, 128 rows}
-#pragma unroll
-            for (int ms = 0; ms < 2; ++ms)
-              tma_load_4d(sX + ms * 8 * 1024, &tmIn2, &full_bar[slot], cc, w0 + p.dw[tap], h0 + ms * CONV_BH + p.dh[tap], t + p.dt[tap]);
-          }
-          if (++slot == T96_SLOTS) {
-            slot = 0;
-            phase ^= 1;
-          }
-        }
-      }
-    }
-  } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    constexpr uint32_t idesc = make_idesc(FMT_BF16, FMT_BF16, 128, 256, 0, 0);
-    const uint32_t tb = __shfl_sync(0xffffffffu, tmem_base, 0);
-    const uint32_t s_lo0 = ((smem_u32(smem) & 0x3FFFF) >> 4) | (1u << 16);
-    int slot = 0;
-    uint32_t phase = 0;
-    int acc = 0;
-    uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
-      tc_fence_after();
-      const uint32_t d_tmem = tb + acc * 256;
-      for (int sidx = 0; sidx < num_subs; ++sidx) {
-        const bool narrow = MODE == CONV_MIXED96 && ((sidx % subs_per_tap) & 1);
-        mbar_wait(&full_bar[slot], phase);
-        tc_fence_after();
-        const uint32_t w_lo = s_lo0 + slot * (T96_SLOT_BYTES >> 4);
-        const uint32_t x_lo = w_lo + ((16 * 1024) >> 4);
-        if (!narrow) {
-#pragma unroll
-          for (int k = 0; k < 4; ++k) mma_f16_ss_w(d_tmem, w_lo + 2 * k, kDescHiSw128, x_lo + 2 * k, kDescHiSw128, idesc, (sidx | k) != 0 ? 1u : 0u);
-        } else {
-#pragma unroll
-          for (int k = 0; k < 2; ++k) mma_f16_ss_w(d_tmem, w_lo + 2 * k, kDescHiSw64, x_lo + 2 * k, kDescHiSw64, idesc, 1u);
-        }
-        tc_commit_w(&empty_bar[slot]);
-        if (++slot == T96_SLOTS) {
-          slot = 0;
-          phase ^= 1;
-        }
-      }
-      tc_commit_w(&tmem_full_bar[acc]);
-      acc ^= 1;
-      if (acc == 0) acc_phase ^= 1;
-    }
-  } else if (warp >= 4) {
-    // ===================== transposing epilogue =====================
-    const int ewarp = warp - 4;
-    const int ch = ewarp * 32 + lane;        // output channel owned by this thread (TMEM lane)
-    const int et = threadIdx.x - 128;
-    const bool ch_ok = ch < p.cout;
-    const float bias = (p.bias != nullptr && ch_ok) ? __bfloat162float(p.bias[ch]) : 0.f;
-    // staging: element (voxel v, channel c) of a 64-channel buffer -> v * 128 + (((c >> 3) ^ (v & 7)) << 4) + (c & 7) * 2
-    uint8_t* stg = sStage + (ch >> 6) * CONV_STAGING_BYTES;
-    const int c64 = ch & 63;
-    int acc = 0;
-    uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      int t, h0, w0;
-      tile_coords(tile, t, h0, w0);
-      mbar_wait(&tmem_full_bar[acc], acc_phase);
-      tc_fence_after();
-#pragma unroll 1
-      for (int ms = 0; ms < 2; ++ms) {
-        const int hs = h0 + ms * CONV_BH;
-        if (hs >= p.H) break;                                 // uniform
-        if (et == 0) tma_store_wait_read<0>();                // the previous sub-tile's stores have read the staging buffers
-        named_bar_sync(1, 128);
-        const uint32_t t_row = tmem_base + acc * 256 + ms * 128 + (uint32_t(ewarp * 32) << 16);
-#pragma unroll 1
-        for (int v0 = 0; v0 < 128; v0 += 32) {               // 32 voxels = one image row of the sub-tile
-          uint32_t v[32];
-          tmem_ld_x32(t_row + v0, v);
-          tmem_ld_wait();
-          if (ch_ok) {
-            const int hh = hs + v0 / CONV_BW;
-            const __nv_bfloat16* res = (p.residual != nullptr && hh < p.H)
-                                           ? p.residual + (long long)t * p.res_st + (long long)hh * p.res_sh + (long long)w0 * p.res_sw + ch
-                                           : nullptr;
-#pragma unroll
-            for (int i = 0; i < 32; ++i) {
-              float f = __uint_as_float(v[i]) + bias;
-              if (res != nullptr && w0 + i < p.W) f += __bfloat162float(res[(long long)i * p.res_sw]);
-              if (p.clamp_out) f = fminf(fmaxf(f, -1.0f), 1.0f);
-              const int vox = v0 + i;
-              *reinterpret_cast<__nv_bfloat16*>(stg + vox * 128 + (((c64 >> 3) ^ (vox & 7)) << 4) + (c64 & 7) * 2) = __float2bfloat16_rn(f);
-            }
-          }
-        }
-        fence_async_smem();
-        named_bar_sync(1, 128);
-        if (et == 0) {
-#pragma unroll
-          for (int half = 0; half < 2; ++half) {              // channels [0, 64) and [64, 128): the second box is clipped at cout by the tensor map
-            if (half * 64 < p.cout) {
-              asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(
-                               reinterpret_cast<uint64_t>(&tmOut)),
-                           "r"(smem_u32(sStage + half * CONV_STAGING_BYTES)), "r"(half * 64), "r"(w0), "r"(hs), "r"(t)
-                           : "memory");
-            }
-          }
-          tma_store_commit();
-        }
-      }
-      tc_fence_before();
-      mbar_arrive(&tmem_empty_bar[acc]);
-      acc ^= 1;
-      if (acc == 0) acc_phase ^= 1;
-    }
-    if (et == 0) tma_store_wait_all<0>();
-  }
-
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 2) {
-    tc_fence_after();
-    tmem_dealloc(tmem_base, 512);
-  }
-}
-
-template <int MODE>
-static int launch_conv_t96(const CUtensorMap& tmIn, const CUtensorMap& tmW, const CUtensorMap& tmIn2, const CUtensorMap& tmW2, const CUtensorMap& tmOut,
-                           const ConvParams& p, cudaStream_t stream) {
-  auto kern = conv3d_t96_kernel<MODE>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    B200_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, T96_SMEM_BYTES));
-    attr_set = true;
-  }
-  const long long num_tiles = (long long)p.T * p.tiles_w * p.tiles_h;
-  const int grid = (int)(num_tiles < num_sms() ? num_tiles : num_sms());
-  kern<<<grid, CONV_THREADS, T96_SMEM_BYTES, stream>>>(tmIn, tmW, tmIn2, tmW2, tmOut, p); note_launch();
-  B200_CHECK_CUDA(cudaGetLastError());
-  return B200_OK;
-}
-
 template <int BLOCK_N, int MODE>
 static int launch_conv(const CUtensorMap& tmIn, const CUtensorMap& tmW, const CUtensorMap& tmIn2, const CUtensorMap& tmW2, const CUtensorMap& tmOut,
                        const ConvParams& p, cudaStream_t stream) {
@@ -669,9 +425,6 @@ int conv3d_cl(const void* in, long long in_st, long long in_sh, long long in_sw,
   }
   if (get_option(OPT_CONV_NARROW) && block_n != 128 && block_n != 256) mode = CONV_NARROW;   // round-1 tiles (A/B measurements)
 
-  // cout = 96 with 128-byte-row K chunks: the transposed tiles (weights as the M operand, 256 voxels as N; option "conv_t96", default on)
-  const bool t96 = get_option(OPT_CONV_T96) && cout == 96 && (mode == CONV_WIDE || mode == CONV_MIXED96);
-
   const int kc = mode == CONV_NARROW ? 32 : 64;
   const CUtensorMapSwizzle swz = mode == CONV_NARROW ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B;
   CUtensorMap tmIn, tmW, tmIn2, tmW2, tmOut;
@@ -690,11 +443,11 @@ int conv3d_cl(const void* in, long long in_st, long long in_sh, long long in_sw,
   {
     uint64_t dims[2] = {(uint64_t)ntaps * cin, (uint64_t)cout};
     uint64_t strides[1] = {(uint64_t)ntaps * cin * 2};
-    uint32_t box[2] = {(uint32_t)kc, (uint32_t)(t96 ? 128 : block_n)};      // transposed tiles: 128 weight rows (the last 32 outside the matrix: zeros)
+    uint32_t box[2] = {(uint32_t)kc, (uint32_t)block_n};
     if ((rc = encode_tmap(&tmW, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, wt, dims, strides, box, swz))) return rc;
     tmW2 = tmW;
     if (mode == CONV_MIXED96) {
-      uint32_t box2[2] = {32, (uint32_t)(t96 ? 128 : block_n)};
+      uint32_t box2[2] = {32, (uint32_t)block_n};
       if ((rc = encode_tmap(&tmW2, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, wt, dims, strides, box2, CU_TENSOR_MAP_SWIZZLE_64B))) return rc;
     }
   }
@@ -730,11 +483,6 @@ int conv3d_cl(const void* in, long long in_st, long long in_sh, long long in_sw,
   p.res_sh = res_sh;
   p.res_sw = res_sw;
   p.clamp_out = clamp_out;
-  if (t96) {
-    p.num_n_blocks = 1;
-    return mode == CONV_WIDE ? launch_conv_t96<CONV_WIDE>(tmIn, tmW, tmIn2, tmW2, tmOut, p, stream)
-                             : launch_conv_t96<CONV_MIXED96>(tmIn, tmW, tmIn2, tmW2, tmOut, p, stream);
-  }
 #define B200_CONV_CASE(BN, MD) \
   if (block_n == BN && mode == MD) return launch_conv<BN, MD>(tmIn, tmW, tmIn2, tmW2, tmOut, p, stream)
   B200_CONV_CASE(256, CONV_WIDE);

@@ -35,12 +35,9 @@ int num_sms() {
 #ifndef B200_CONV_HALO_DEFAULT
 #define B200_CONV_HALO_DEFAULT 1     // conv3d_halo.cu: verified on hardware in round 2 (profiles/r02_probe_rowshift.txt, r02_halo_parity.txt)
 #endif
-static const char* const kOptNames[OPT_COUNT] = {"conv_halo", "halo_base_offset", "conv_narrow", "conv_t96"};
-static const char* const kOptEnv[OPT_COUNT] = {"B200_CONV_HALO", "B200_HALO_BASE_OFFSET", "B200_CONV_NARROW", "B200_CONV_T96"};
-#ifndef B200_CONV_T96_DEFAULT
-#define B200_CONV_T96_DEFAULT 0      // transposed cout = 96 tiles: off until verified on hardware
-#endif
-static const int kOptDefault[OPT_COUNT] = {B200_CONV_HALO_DEFAULT, 0, 0, B200_CONV_T96_DEFAULT};   // halo_base_offset 0: the tensor core swizzles by absolute address bits (probe)
+static const char* const kOptNames[OPT_COUNT] = {"conv_halo", "halo_base_offset", "conv_narrow"};
+static const char* const kOptEnv[OPT_COUNT] = {"B200_CONV_HALO", "B200_HALO_BASE_OFFSET", "B200_CONV_NARROW"};
+static const int kOptDefault[OPT_COUNT] = {B200_CONV_HALO_DEFAULT, 0, 0};   // halo_base_offset 0: the tensor core swizzles by absolute address bits (probe)
 static std::atomic<int> g_opts[OPT_COUNT];
 static std::once_flag g_opts_once;
 
@@ -61,7 +58,7 @@ int set_option(const char* name, int value) {
       g_opts[i].store(value);
       return B200_OK;
     }
-  set_last_error("b200_set_option: unknown option '%s' (conv_halo, halo_base_offset, conv_narrow, conv_t96)", name ? name : "(null)");
+  set_last_error("b200_set_option: unknown option '%s' (conv_halo, halo_base_offset, conv_narrow)", name ? name : "(null)");
   return B200_ERR_INVALID;
 }
 

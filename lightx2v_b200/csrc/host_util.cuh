@@ -39,7 +39,7 @@ int num_sms();
 
 // Runtime options (b200_set_option): A/B switches for measurements and tests.  Initial values come from the environment
 // (B200_CONV_HALO, B200_HALO_BASE_OFFSET, B200_CONV_NARROW) the first time an option is read.
-enum Option : int { OPT_CONV_HALO = 0, OPT_HALO_BASE_OFFSET = 1, OPT_CONV_NARROW = 2, OPT_CONV_T96 = 3, OPT_COUNT = 4 };
+enum Option : int { OPT_CONV_HALO = 0, OPT_HALO_BASE_OFFSET = 1, OPT_CONV_NARROW = 2, OPT_COUNT = 3 };
 int get_option(int opt);
 int set_option(const char* name, int value);
 
