@@ -262,6 +262,13 @@ int b200_cl_to_video(const void* in, float* out, int64_t voxels, int CP, int64_t
  * addressing the tensor core honours (the precondition for taking a convolution's dw taps as row-shifted views of one halo tile). */
 int b200_debug_umma_rowshift(const void* A, const void* B, float* D, int k_elems, int r0, int mode, b200_stream_t stream);
 
+/* Hardware probe (debug; no reference counterpart, not on any product path): clocks per SS-mode tcgen05.mma (M = 128, K = 16, bf16, operands
+ * resident in shared memory, no TMA, no epilogue) at width n, rotating over n_acc TMEM accumulators, from `issuers` (1 | 2) warps, cycling
+ * through a_tiles (1..4) A tiles, with `writers` (0..4) warps streaming shared-memory stores beside it.  out: uint64 [3 * grid] -
+ * [2 * cta + issuer] clocks for iters x 4 MMAs, [2 * grid + cta] 512-byte store instructions retired by the writers.  tools/probe_umma_rate.py
+ * prints the table DESIGN.md section 4 quotes as the per-shape floor of the conv / GEMM tiles. */
+int b200_debug_umma_rate(int n, int iters, int n_acc, int issuers, int writers, int a_tiles, int grid, unsigned long long* out, b200_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

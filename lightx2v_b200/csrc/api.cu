@@ -59,6 +59,7 @@ int rms_rope_heads(void* x0, long long ld0, const void* w0, void* x1, long long 
 int ln_rope_heads64(void* x0, long long ld0, const void* w0, const void* b0, void* x1, long long ld1, const void* w1, const void* b1, long long rows,
                     int H, float eps, const void* cos_sin, long long rope_start, cudaStream_t stream);
 int debug_umma_rowshift(const void* A, const void* B, float* D, int k_elems, int r0, int mode, cudaStream_t stream);
+int debug_umma_rate(int n, int iters, int n_acc, int issuers, int writers, int a_tiles, int grid, unsigned long long* out, cudaStream_t stream);
 }  // namespace b200
 
 extern "C" {
@@ -214,6 +215,10 @@ int b200_ln_rope_heads64(void* x0, int64_t ld0, const void* w0, const void* b0, 
 
 int b200_debug_umma_rowshift(const void* A, const void* B, float* D, int k_elems, int r0, int mode, b200_stream_t stream) {
   return b200::debug_umma_rowshift(A, B, D, k_elems, r0, mode, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int b200_debug_umma_rate(int n, int iters, int n_acc, int issuers, int writers, int a_tiles, int grid, unsigned long long* out, b200_stream_t stream) {
+  return b200::debug_umma_rate(n, iters, n_acc, issuers, writers, a_tiles, grid, out, reinterpret_cast<cudaStream_t>(stream));
 }
 
 }  // extern "C"

@@ -114,12 +114,18 @@ conv3d_igemm_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_const
     prefetch_tmap(&tmOut);
   }
   if (warp == 1 && lane == 0) {
+    // With two sub-tiles the MMAs are issued by TWO warps (warp 1: sub-tile 0, warp 3: sub-tile 1): one elected lane needs ~17 SASS
+    // instructions (ELECT / R2UR / VOTEU / address adds) per UTCHMMA, ~100 clocks, while a 128 x 96 x 16 MMA occupies the tensor pipe for 48 -
+    // round 2's ncu source view shows the single issuing warp permanently busy, the producer blocked on free slots and the tensor pipe at
+    // 45-50 % for every N = 96 formulation (8 % at N = 16), independent of L2 traffic.  Each issuer commits its own MMAs, so the
+    // slot-release and accumulator-ready barriers expect one arrival per issuer.
+    constexpr int kIssuers = Cfg::kMSub == 2 ? 2 : 1;
     for (int i = 0; i < CONV_STAGES; ++i) {
       mbar_init(&full_bar[i], 1);
-      mbar_init(&empty_bar[i], 1);
+      mbar_init(&empty_bar[i], kIssuers);
     }
     for (int i = 0; i < 2; ++i) {
-      mbar_init(&tmem_full_bar[i], 1);
+      mbar_init(&tmem_full_bar[i], kIssuers);
       mbar_init(&tmem_empty_bar[i], 128);
     }
     fence_mbar_init();
@@ -188,8 +194,10 @@ conv3d_igemm_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_const
         }
       }
     }
-  } else if (warp == 1) {
-    // ===================== MMA issuer (whole warp, warp-uniform control flow) =====================
+  } else if (warp == 1 || (warp == 3 && Cfg::kMSub == 2)) {
+    // ===================== MMA issuers (whole warp, warp-uniform control flow): warp 1 -> sub-tile 0, warp 3 -> sub-tile 1 =====================
+    const int ms_begin = (Cfg::kMSub == 2 && warp == 3) ? 1 : 0;
+    const int ms_end = Cfg::kMSub == 2 ? ms_begin + 1 : 1;
     constexpr uint32_t idesc = make_idesc(FMT_BF16, FMT_BF16, CONV_BLOCK_M, BLOCK_N, 0, 0);
     const uint32_t tb = __shfl_sync(0xffffffffu, tmem_base, 0);
     const uint32_t s_lo0 = ((smem_u32(smem) & 0x3FFFF) >> 4) | (1u << 16);
@@ -211,8 +219,7 @@ conv3d_igemm_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_const
 #pragma unroll
           for (int c = 0; c < 3; ++c) {
             if (c < nch) {
-#pragma unroll
-              for (int ms = 0; ms < Cfg::kMSub; ++ms) {
+              for (int ms = ms_begin; ms < ms_end; ++ms) {
 #pragma unroll
                 for (int k = 0; k < 2; ++k) {   // K=16 MMAs per chunk: +32 B inside the swizzled row
                   const uint32_t accum = (ks | c | k) != 0 ? 1u : 0u;
@@ -223,8 +230,7 @@ conv3d_igemm_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_const
             }
           }
         } else {
-#pragma unroll
-          for (int ms = 0; ms < Cfg::kMSub; ++ms) {
+          for (int ms = ms_begin; ms < ms_end; ++ms) {
 #pragma unroll
             for (int k = 0; k < 4; ++k)
               mma_f16_ss_w(d_tmem + ms * BLOCK_N, a_lo + ms * (A64 >> 4) + 2 * k, kDescHiSw128, b_lo + 2 * k, kDescHiSw128, idesc, (ks | k) != 0 ? 1u : 0u);

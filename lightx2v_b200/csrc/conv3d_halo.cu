@@ -18,8 +18,9 @@
 // Work per pipeline slot (N = 96): A halo 68 KB feeds 9 taps x 2 rows x 4 K-steps = 72 MMAs (3456 tensor clocks); the nine 12 KB weight
 // tiles stream through their own ring.  Bytes per tensor clock: 51 (conv3d.cu MIXED96: 115), TMA rows per clock: 0.41 (1.22).
 //
-// Same warp roles as conv3d.cu plus a second producer: warp 0 loads halo tiles, warp 3 loads weight tiles (independent rings, so a
-// stalled weight slot never delays the next halo prefetch), warp 1 issues tcgen05.mma, warp 2 owns TMEM, warps 4-7 run the epilogue.
+// Warp roles: warp 0 loads halo tiles, warp 2 (after allocating TMEM) loads weight tiles - independent rings, so a stalled weight slot
+// never delays the next halo prefetch -, warps 1 and 3 issue tcgen05.mma for output row 0 / row 1 (two issuers: one elected lane needs
+// ~100 clocks of ELECT / R2UR / address instructions per UTCHMMA, see conv3d.cu), warps 4-7 run the epilogue.
 #include "host_util.cuh"
 #include "ptx.cuh"
 
@@ -97,14 +98,14 @@ conv3d_halo_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_consta
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < HALO_A_SLOTS; ++i) {
       mbar_init(&a_full[i], 1);
-      mbar_init(&a_empty[i], 1);
+      mbar_init(&a_empty[i], 2);          // one commit per MMA-issuing warp
     }
     for (int i = 0; i < Cfg::kBSlots; ++i) {
       mbar_init(&b_full[i], 1);
-      mbar_init(&b_empty[i], 1);
+      mbar_init(&b_empty[i], 2);
     }
     for (int i = 0; i < 2; ++i) {
-      mbar_init(&tmem_full_bar[i], 1);
+      mbar_init(&tmem_full_bar[i], 2);
       mbar_init(&tmem_empty_bar[i], 128);
     }
     fence_mbar_init();
@@ -146,8 +147,8 @@ conv3d_halo_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_consta
         }
       }
     }
-  } else if (warp == 3) {
-    // ===================== weight producer =====================
+  } else if (warp == 2) {
+    // ===================== weight producer (the TMEM-allocating warp) =====================
     if (lane == 0) {
       int slot = 0;
       uint32_t phase = 0;
@@ -168,8 +169,9 @@ conv3d_halo_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_consta
         }
       }
     }
-  } else if (warp == 1) {
-    // ===================== MMA issuer (whole warp, warp-uniform control flow) =====================
+  } else if (warp == 1 || warp == 3) {
+    // ===================== MMA issuers (whole warp, warp-uniform control flow): warp 1 -> output row 0, warp 3 -> output row 1 =====================
+    const int ms = warp == 3 ? 1 : 0;
     constexpr uint32_t idesc = make_idesc(FMT_BF16, FMT_BF16, 128, BLOCK_N, 0, 0);
     const uint32_t tb = __shfl_sync(0xffffffffu, tmem_base, 0);
     const uint32_t a_base = smem_u32(sA), b_base = smem_u32(sB);
@@ -193,8 +195,7 @@ conv3d_halo_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_consta
           mbar_wait(&b_full[bslot], bphase);
           tc_fence_after();
           const uint32_t b_lo = desc_lo_kmajor(b_base + bslot * Cfg::kBSlotBytes);
-#pragma unroll
-          for (int ms = 0; ms < 2; ++ms) {
+          {
             const uint32_t row = (uint32_t)(ms + dh) * HALO_W + dw;
             const uint32_t a_lo = desc_lo_kmajor(a_tile + row * 128);
             const uint32_t a_hi = kDescHiSw128 | (p.base_offset_mode ? ((row & 7u) << 17) : 0u);
@@ -365,14 +366,19 @@ int conv3d_cl_halo(const void* in, long long in_st, long long in_sh, long long i
   const int bo_mode = get_option(OPT_HALO_BASE_OFFSET);
   if (!get_option(OPT_CONV_HALO) || ntaps != 27 || W < 512) return 1;
   if (!(cin % 64 == 0 || cin % 64 == 32) || cin < 64) return 1;
-  // Measured on B200 (profiles/r02_conv_halo_ab.txt, r02_halo{96,192}_ncu_summary.txt): the halo tile halves the L2 traffic of every
-  // shape (lts throughput 57 % -> 27 % at N = 96), but only the 192-wide tiles were bound by it (1366 -> 1545 TFLOP/s, 77 % tensor pipe).
-  // At N = 96 / 16 the tensor core is limited by its shared-memory operand reads - (128 + N) x 32 B per 128 x N x 16 MMA = 149 B/clk at
-  // N = 96 against the ~90 B/clk the GEMM and FMHA tiles sustain - so those shapes stay on conv3d.cu's tiles (same speed, fewer
-  // resources; the 96 -> 16 head is faster there).  "conv_halo" = 2 forces the halo tiles for every eligible width (A/B runs, tests).
+  // Measured on B200 (profiles/r02_umma_rate_probe.txt, r02_conv_two_issuers.txt, r02_conv_halo_ab.txt):
+  //  * an SS-mode 128 x N x 16 MMA costs max(N / 2, (4096 + 32 N) / 128) clocks - the tensor core reads its operands from shared memory
+  //    at exactly 128 B/clk - so N = 96 tops out at 85.6 % of the pipe, N = 16 at 20 %; neither a second issuing warp nor concurrent
+  //    shared-memory stores move that floor;
+  //  * every im2col tile of conv3d.cu sits at ~64 B/clk/SM of TMA ingest (N = 96: 67.6 KB per 12 MMAs; 128 x 192: 40 KB per 4; 256 x 128:
+  //    48 KB per 8), i.e. the L2 -> SM path, not the tensor pipe, bounds them at 45-68 %;
+  //  * the halo tile cuts the ingest ~4x and leaves the MMA warp issue-bound (86 % of its samples in ELECT / R2UR / address code), which
+  //    the second issuing warp relieves: 192 -> 192 1349 -> 1560 TFLOP/s (93 % of the measured cuBLAS burst peak), 96 -> 96 975 -> 1105,
+  //    192 -> 96 1214 -> 1301.  The 96 -> 16 head stays on conv3d.cu's tiles (209 vs 193 TFLOP/s: at N = 16 the floor is the A read and
+  //    the halo's per-tap barrier traffic costs more than its ingest saves).  "conv_halo" = 2 also forces N = 16 (A/B runs, tests).
   int block_n;
   if (cout % 192 == 0) block_n = 192;
-  else if (get_option(OPT_CONV_HALO) >= 2 && cout % 96 == 0) block_n = 96;
+  else if (cout % 96 == 0) block_n = 96;
   else if (get_option(OPT_CONV_HALO) >= 2 && cout == 16) block_n = 16;
   else return 1;
   // taps must be the full 3 x 3 x 3 stencil in (temporal, dh, dw) order with dh, dw in {-1, 0, 1}

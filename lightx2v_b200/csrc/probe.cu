@@ -91,4 +91,92 @@ int debug_umma_rowshift(const void* A, const void* B, float* D, int k_elems, int
   return B200_OK;
 }
 
+// ---------------------------------------------------------------------------------------------------------------------------------
+// UMMA issue-rate probe: how many clocks does one SS-mode tcgen05.mma (M = 128, K = 16, bf16, both operands K-major SW128 in shared
+// memory) cost at a given N when NOTHING else limits it - no TMA, no epilogue, operands resident?  This is the floor every conv / GEMM
+// tile shape in this library is measured against.  Knobs: number of TMEM accumulators the MMAs rotate over (a chain
+// of MMAs into ONE accumulator is dependent), one or two issuing warps, how many distinct A tiles are cycled through, and `writers` warps
+// that stream 16-byte shared-memory stores next to the MMAs (the bank traffic a TMA producer would add).
+//   out[2 * cta + issuer] = clocks for `iters` x 4 MMAs (issue of the first to completion of the last); out[2 * grid + cta] = 512-byte
+//   store instructions the writer warps retired in that time.
+__global__ void __launch_bounds__(256, 1)
+umma_rate_probe_kernel(int n, int iters, int n_acc, int issuers, int writers, int a_tiles, unsigned long long* __restrict__ out) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sA = smem;                                   // 4 tiles x 16 KB
+  uint8_t* sB = smem + 64 * 1024;                       // 256 rows x 128 B
+  uint8_t* sW = smem + 96 * 1024;                       // 16 KB writer scratch
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 112 * 1024);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2);
+  volatile int* stop = reinterpret_cast<volatile int*>(bars + 3);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // finite, non-trivial bf16 operand bits (exponent field 0x3f / 0xbf: |x| in [1, 2)), so the datapath toggles like real data
+  for (int i = threadIdx.x; i < 96 * 1024 / 4; i += 256) {
+    const uint32_t h = (uint32_t)i * 2654435761u;
+    reinterpret_cast<uint32_t*>(smem)[i] = (h & 0x807f807fu) | 0x3f803f80u;
+  }
+  if (threadIdx.x == 0) {
+    mbar_init(&bars[0], 1);
+    mbar_init(&bars[1], 1);
+    *stop = 0;
+    fence_mbar_init();
+  }
+  fence_async_smem();
+  if (warp == 2) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  if (warp < issuers) {
+    const uint32_t idesc = make_idesc(FMT_BF16, FMT_BF16, 128, (uint32_t)n, 0, 0);
+    const uint32_t a0 = desc_lo_kmajor(smem_u32(sA)), b_lo = desc_lo_kmajor(smem_u32(sB));
+    const uint32_t d0 = tmem_base + (uint32_t)(warp * n_acc * n);
+    const long long t0 = clock64();
+    int acc = 0, at = 0;
+    for (int it = 0; it < iters; ++it) {
+      const uint32_t a_lo = a0 + (uint32_t)at * (16384u >> 4);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) mma_f16_ss_w(d0 + (uint32_t)(acc * n), a_lo + 2 * k, kDescHiSw128, b_lo + 2 * k, kDescHiSw128, idesc, it >= n_acc || k ? 1u : 0u);
+      if (++acc == n_acc) acc = 0;
+      if (++at == a_tiles) at = 0;
+    }
+    tc_commit_w(&bars[warp]);
+    mbar_wait(&bars[warp], 0);
+    const long long t1 = clock64();
+    if (lane == 0) {
+      out[2 * blockIdx.x + warp] = (unsigned long long)(t1 - t0);
+      if (warp == 0) *stop = 1;
+    }
+  } else if (warp >= 4 && warp < 4 + writers) {
+    unsigned long long cnt = 0;
+    uint4* dst = reinterpret_cast<uint4*>(sW) + (warp - 4) * 256 + lane;
+    const uint4 v = make_uint4(lane, warp, 1, 2);
+    while (!*stop) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(smem_u32(dst + j * 32)), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+      cnt += 8;
+    }
+    if (lane == 0) atomicAdd(&out[2 * gridDim.x + blockIdx.x], cnt);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+int debug_umma_rate(int n, int iters, int n_acc, int issuers, int writers, int a_tiles, int grid, unsigned long long* out, cudaStream_t stream) {
+  B200_CHECK_ARG(out && n >= 16 && n <= 256 && n % 16 == 0 && iters > 0 && n_acc >= 1 && issuers >= 1 && issuers <= 2 && writers >= 0 && writers <= 4 &&
+                     a_tiles >= 1 && a_tiles <= 4 && grid >= 1 && issuers * n_acc * n <= 512,
+                 "b200_debug_umma_rate: bad arguments");
+  const int smem_bytes = 114 * 1024;
+  B200_CHECK_CUDA(cudaFuncSetAttribute(umma_rate_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+  B200_CHECK_CUDA(cudaMemsetAsync(out, 0, sizeof(unsigned long long) * 3 * grid, stream));
+  umma_rate_probe_kernel<<<grid, 256, smem_bytes, stream>>>(n, iters, n_acc, issuers, writers, a_tiles, out);
+  note_launch();
+  B200_CHECK_CUDA(cudaGetLastError());
+  return B200_OK;
+}
+
 }  // namespace b200

@@ -37,6 +37,7 @@ SIGNATURES = {
     "b200_rms_rope_heads": (_i32, [_ptr, _i64, _ptr, _ptr, _i64, _ptr, _i64, _i32, _f32, _ptr, _i64, _ptr]),
     "b200_ln_rope_heads64": (_i32, [_ptr, _i64, _ptr, _ptr, _ptr, _i64, _ptr, _ptr, _i64, _i32, _f32, _ptr, _i64, _ptr]),
     "b200_debug_umma_rowshift": (_i32, [_ptr, _ptr, _ptr, _i32, _i32, _i32, _ptr]),
+    "b200_debug_umma_rate": (_i32, [_i32, _i32, _i32, _i32, _i32, _i32, _i32, _ptr, _ptr]),
     "b200_rms_rope_scatter": (_i32, [_ptr, _i64, _ptr, _ptr, _i64, _i32, _f32, _ptr, _i64, _ptr, _i32, _i32, _i64, _ptr]),
     "b200_fmha_fwd_d128_scatter": (_i32, [_ptr, _i64, _ptr, _i64, _ptr, _i64, _ptr, _i32, _i64, _i64, _i32, _i64, _i64, _i32, _f32, _ptr]),
     "b200_conv3d_cl": (_i32, [_ptr, _i64, _i64, _i64, _ptr, _ptr, _ptr, _i64, _i64, _i64, _ptr, _i64, _i64, _i64, _i32, _i32, _i32, _i32, _i32,

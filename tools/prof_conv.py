@@ -11,10 +11,14 @@ from lightx2v_b200.host.wan_vae import _Conv  # noqa: E402
 C, T, H, W = (int(v) for v in sys.argv[1:5])
 cout = int(sys.argv[5]) if len(sys.argv) > 5 else C
 g = torch.Generator(device="cuda").manual_seed(0)
-x = torch.randn(T, H, W, C, generator=g, device="cuda").to(torch.bfloat16)
+pitch = int(os.environ.get("PITCH", "0"))        # channel pitch of the activation tensors in memory (0: dense); e.g. 128 for the 96-channel stage
+if pitch:
+    x = torch.randn(T, H, W, pitch, generator=g, device="cuda").to(torch.bfloat16)[..., :C]
+else:
+    x = torch.randn(T, H, W, C, generator=g, device="cuda").to(torch.bfloat16)
 w = torch.randn(cout, C, 3, 3, 3, generator=g, device="cuda") / (C * 27) ** 0.5
 conv = _Conv(w, torch.zeros(cout), "cuda")
-out = torch.empty(T, H, W, conv.cout, dtype=torch.bfloat16, device="cuda")
+out = torch.empty(T, H, W, pitch if pitch else conv.cout, dtype=torch.bfloat16, device="cuda")[..., :conv.cout]
 for _ in range(3):
     conv(x, out=out)
 torch.cuda.synchronize()
@@ -27,4 +31,4 @@ e.record()
 torch.cuda.synchronize()
 ms = s.elapsed_time(e) / n
 fl = 2.0 * T * H * W * 27 * C * cout
-print(f"conv {C}->{cout} [{T},{H},{W}] mode env B200_CONV_NARROW={os.environ.get('B200_CONV_NARROW', '0')}: {ms:.3f} ms, {fl / ms / 1e9:.1f} TFLOP/s")
+print(f"pitch {pitch} conv {C}->{cout} [{T},{H},{W}] mode env B200_CONV_NARROW={os.environ.get('B200_CONV_NARROW', '0')}: {ms:.3f} ms, {fl / ms / 1e9:.1f} TFLOP/s")
