@@ -174,7 +174,7 @@ conv3d_halo_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_consta
     const int ms = warp == 3 ? 1 : 0;
     constexpr uint32_t idesc = make_idesc(FMT_BF16, FMT_BF16, 128, BLOCK_N, 0, 0);
     const uint32_t tb = __shfl_sync(0xffffffffu, tmem_base, 0);
-    const uint32_t a_base = smem_u32(sA), b_base = smem_u32(sB);
+    const uint32_t a_base = smem_u32(sA), b_lo0 = desc_lo_kmajor(smem_u32(sB));
     int aslot = 0, bslot = 0;
     uint32_t aphase = 0, bphase = 0;
     int acc = 0;
@@ -188,22 +188,22 @@ conv3d_halo_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_consta
         const int ksteps = (ch == p.nchunks - 1) ? p.ksteps_last : 4;
         mbar_wait(&a_full[aslot], aphase);
         tc_fence_after();
-        const uint32_t a_tile = a_base + aslot * HALO_A_BYTES;
-#pragma unroll 1
+        // descriptor of this issuer's output row at tap (dh, dw) = (-1, -1); tap (dh, dw) starts (dh * HALO_W + dw) rows = that many
+        // 128-byte units further on (the low word counts 16-byte units).  The 9 taps are unrolled so the offsets - and base_offset =
+        // row % 8 = dw, as HALO_W % 8 == 0 - are immediates: the issue loop is what bounds this kernel (see HaloCfg).
+        const uint32_t a_row0 = desc_lo_kmajor(a_base + aslot * HALO_A_BYTES + (uint32_t)ms * HALO_W * 128);
+        const bool full_chunk = ksteps == 4;
+#pragma unroll
         for (int sp = 0; sp < 9; ++sp) {
           const int dh = sp / 3, dw = sp - dh * 3;                // 0..2 (= offset + 1)
           mbar_wait(&b_full[bslot], bphase);
           tc_fence_after();
-          const uint32_t b_lo = desc_lo_kmajor(b_base + bslot * Cfg::kBSlotBytes);
-          {
-            const uint32_t row = (uint32_t)(ms + dh) * HALO_W + dw;
-            const uint32_t a_lo = desc_lo_kmajor(a_tile + row * 128);
-            const uint32_t a_hi = kDescHiSw128 | (p.base_offset_mode ? ((row & 7u) << 17) : 0u);
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              if (k < ksteps) mma_f16_ss_w(d_tmem + ms * BLOCK_N, a_lo + 2 * k, a_hi, b_lo + 2 * k, kDescHiSw128, idesc, (s | sp | k) != 0 ? 1u : 0u);
-            }
-          }
+          const uint32_t b_lo = b_lo0 + (uint32_t)bslot * (Cfg::kBSlotBytes >> 4);
+          const uint32_t a_lo = a_row0 + (uint32_t)(dh * HALO_W + dw) * 8;
+          const uint32_t a_hi = kDescHiSw128 | (p.base_offset_mode ? ((uint32_t)dw << 17) : 0u);
+          const uint32_t accumulate = sp != 0 ? 1u : (s != 0 ? 1u : 0u);
+          if (full_chunk) mma_f16_ss_w4(d_tmem + ms * BLOCK_N, a_lo, a_hi, b_lo, kDescHiSw128, idesc, accumulate);
+          else mma_f16_ss_w2(d_tmem + ms * BLOCK_N, a_lo, a_hi, b_lo, kDescHiSw128, idesc, accumulate);
           tc_commit_w(&b_empty[bslot]);
           if (++bslot == Cfg::kBSlots) {
             bslot = 0;

@@ -164,33 +164,33 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       const uint32_t q_lo = desc_lo_kmajor(smem_u32(sQ));
       const uint32_t kv_addr = smem_u32(sKV);
 
+      // MMAs are issued in runs of four K-steps (one 64-wide swizzled panel) under one election (mma_f16_ss_w4 / mma_f16_ts_w4): with
+      // one election per MMA this warp spent 74 % of its time in ELECT / R2UR / VOTEU code - 558 instructions per KV iteration for
+      // 32 MMAs (round-2 ncu source view) - and paced the tensor pipe.
       auto issue_qk = [&](int t, int kstage) {
         const uint32_t a = q_lo + t * (FMHA_TILE_BYTES >> 4);
         const uint32_t b = desc_lo_kmajor(kv_addr + kstage * FMHA_TILE_BYTES);
         const uint32_t d = t ? tS1 : tS0;
 #pragma unroll
-        for (int ks = 0; ks < kKSteps; ++ks) {  // head dim in steps of 16; 4 steps per 64-wide panel
-          const uint32_t off = ((ks >> 2) * FMHA_PANEL_BYTES + (ks & 3) * 32) >> 4;
-          mma_f16_ss_w(d, a + off, kDescHiSw128, b + off, kDescHiSw128, idesc_qk, ks != 0 ? 1u : 0u);
+        for (int pn = 0; pn < kKSteps / 4; ++pn) {  // head dim in steps of 16; 4 steps (32 B apart) per 64-wide panel
+          const uint32_t off = (pn * FMHA_PANEL_BYTES) >> 4;
+          mma_f16_ss_w4(d, a + off, kDescHiSw128, b + off, kDescHiSw128, idesc_qk, pn != 0 ? 1u : 0u);
         }
       };
-      // kv = 128 in steps of 16 rows (16 x 128 B = 2048 B); P: 8 columns per step; ks in [ks0, ks1)
-      auto issue_pv_range = [&](int t, int vstage, uint32_t accumulate, int ks0, int ks1) {
+      // kv = 128 in steps of 16 rows (16 x 128 B = 2048 B); P: 8 columns per step; half 0 = steps 0..3, half 1 = steps 4..7
+      auto issue_pv_half = [&](int t, int vstage, uint32_t accumulate, int half) {
         const uint32_t b = desc_lo_mnmajor(kv_addr + vstage * FMHA_TILE_BYTES, FMHA_PANEL_BYTES);
         const uint32_t d = t ? tO1 : tO0;
         const uint32_t a = t ? tS1 : tS0;
-#pragma unroll
-        for (int ks = 0; ks < 8; ++ks) {
-          if (ks >= ks0 && ks < ks1) mma_f16_ts_w(d, a + ks * 8, b + ks * (2048 >> 4), kDescHiSw128, idesc_pv, ks != 0 ? 1u : accumulate);
-        }
+        mma_f16_ts_w4(d, a + half * 32, b + half * (4 * 2048 >> 4), kDescHiSw128, idesc_pv, half ? 1u : accumulate);
       };
       auto issue_pv = [&](int t, int vstage, uint32_t accumulate, uint32_t parity) {
         mbar_wait(&p_full[2 * t], parity);
         tc_fence_after();
-        issue_pv_range(t, vstage, accumulate, 0, 4);
+        issue_pv_half(t, vstage, accumulate, 0);
         mbar_wait(&p_full[2 * t + 1], parity);
         tc_fence_after();
-        issue_pv_range(t, vstage, accumulate, 4, 8);
+        issue_pv_half(t, vstage, accumulate, 1);
       };
 
       int stage = 0;        // ring position of the next tile to consume

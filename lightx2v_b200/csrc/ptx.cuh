@@ -279,6 +279,45 @@ __device__ __forceinline__ void mma_f16_ss_w(uint32_t d_tmem, uint32_t a_lo, uin
       "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// A run of 4 (or 2) MMAs over consecutive K-steps of one swizzled 64-element chunk (descriptor start + 32 B per step) under ONE
+// elect.sync: per MMA the single-MMA wrapper above costs ~22 SASS instructions in the issuing warp (ELECT, two VOTEU, five R2UR, moves,
+// and - when guarded by `if (k < ksteps)` - a BSSY / BSYNC pair), ~100 clocks, more than a 128 x 96 x 16 MMA's 56-clock floor
+// (profiles/r02_umma_rate_probe.txt, r02_halo96_v2 source view).  The first MMA takes the accumulate flag, the others accumulate.
+#define B200_MMA_STEP(off)                                                  \
+  "add.u32 al, %1, " #off ";\n\t"                                           \
+  "add.u32 bl, %3, " #off ";\n\t"                                           \
+  "mov.b64 da, {al, %2};\n\t"                                               \
+  "mov.b64 db, {bl, %4};\n\t"                                               \
+  "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, t;\n\t"
+// an explicit branch around the run: ptxas then knows exactly one lane executes it and moves each operand to a uniform register once
+// (plain R2UR + UIADD3 per step) instead of re-broadcasting every operand of every MMA under the election predicate
+#define B200_MMA_HEAD                                                       \
+  "{\n\t"                                                                   \
+  ".reg .pred p, e, t;\n\t"                                                 \
+  ".reg .b64 da, db;\n\t"                                                   \
+  ".reg .b32 al, bl;\n\t"                                                   \
+  "elect.sync _|e, 0xffffffff;\n\t"                                         \
+  "@!e bra MMA_RUN_DONE;\n\t"                                               \
+  "setp.ne.b32 p, %6, 0;\n\t"                                               \
+  "setp.eq.b32 t, 0, 0;\n\t"                                                \
+  "mov.b64 da, {%1, %2};\n\t"                                               \
+  "mov.b64 db, {%3, %4};\n\t"                                               \
+  "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t"
+#define B200_MMA_TAIL "MMA_RUN_DONE:\n\t}\n"
+__device__ __forceinline__ void mma_f16_ss_w4(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi, uint32_t idesc,
+                                              uint32_t accumulate) {
+  asm volatile(B200_MMA_HEAD B200_MMA_STEP(2) B200_MMA_STEP(4) B200_MMA_STEP(6) B200_MMA_TAIL ::"r"(d_tmem), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi),
+               "r"(idesc), "r"(accumulate)
+               : "memory");
+}
+__device__ __forceinline__ void mma_f16_ss_w2(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi, uint32_t idesc,
+                                              uint32_t accumulate) {
+  asm volatile(B200_MMA_HEAD B200_MMA_STEP(2) B200_MMA_TAIL ::"r"(d_tmem), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+               : "memory");
+}
+#undef B200_MMA_STEP
+#undef B200_MMA_HEAD
+#undef B200_MMA_TAIL
 __device__ __forceinline__ void mma_f8_ss_w(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
                                             uint32_t idesc, uint32_t accumulate) {
   asm volatile(
@@ -341,6 +380,38 @@ __device__ __forceinline__ void mma_f16_ts_w(uint32_t d_tmem, uint32_t a_tmem, u
       "setp.ne.b32 p, %5, 0;\n\t"
       "mov.b64 db, {%2, %3};\n\t"
       "@e tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], db, %4, p;\n\t"
+      "}\n" ::"r"(d_tmem),
+      "r"(a_tmem), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// Four TS-mode MMAs (A = P in TMEM, 8 packed columns per 16-row K-step; B = V MN-major, 2048 B per K-step) under one election with an
+// explicit branch - see mma_f16_ss_w4.
+__device__ __forceinline__ void mma_f16_ts_w4(uint32_t d_tmem, uint32_t a_tmem, uint32_t b_lo, uint32_t b_hi, uint32_t idesc,
+                                              uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p, e, t;\n\t"
+      ".reg .b64 db;\n\t"
+      ".reg .b32 at, bl;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "@!e bra MMA_TS_RUN_DONE;\n\t"
+      "setp.ne.b32 p, %5, 0;\n\t"
+      "setp.eq.b32 t, 0, 0;\n\t"
+      "mov.b64 db, {%2, %3};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], db, %4, p;\n\t"
+      "add.u32 at, %1, 8;\n\t"
+      "add.u32 bl, %2, 128;\n\t"
+      "mov.b64 db, {bl, %3};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [at], db, %4, t;\n\t"
+      "add.u32 at, %1, 16;\n\t"
+      "add.u32 bl, %2, 256;\n\t"
+      "mov.b64 db, {bl, %3};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [at], db, %4, t;\n\t"
+      "add.u32 at, %1, 24;\n\t"
+      "add.u32 bl, %2, 384;\n\t"
+      "mov.b64 db, {bl, %3};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [at], db, %4, t;\n\t"
+      "MMA_TS_RUN_DONE:\n\t"
       "}\n" ::"r"(d_tmem),
       "r"(a_tmem), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
       : "memory");
