@@ -374,12 +374,14 @@ int conv3d_cl_halo(const void* in, long long in_st, long long in_sh, long long i
   //    48 KB per 8), i.e. the L2 -> SM path, not the tensor pipe, bounds them at 45-68 %;
   //  * the halo tile cuts the ingest ~4x and leaves the MMA warp issue-bound (86 % of its samples in ELECT / R2UR / address code), which
   //    the second issuing warp relieves: 192 -> 192 1349 -> 1560 TFLOP/s (93 % of the measured cuBLAS burst peak), 96 -> 96 975 -> 1105,
-  //    192 -> 96 1214 -> 1301.  The 96 -> 16 head stays on conv3d.cu's tiles (209 vs 193 TFLOP/s: at N = 16 the floor is the A read and
-  //    the halo's per-tap barrier traffic costs more than its ingest saves).  "conv_halo" = 2 also forces N = 16 (A/B runs, tests).
+  //    192 -> 96 1214 -> 1301;
+  //  * issuing each (tap, chunk)'s K-steps as ONE run under one election (mma_f16_ss_w4 / _w2: ~7 instead of ~22 SASS instructions per
+  //    MMA) lifts them again - 96 -> 96 1261, 192 -> 96 1487, 192 -> 192 1571 TFLOP/s - and makes the halo tiles the faster choice for
+  //    the 96 -> 16 head too (302 vs 209 TFLOP/s; its floor is the 39-clock A read).  profiles/r02_mma_runs_perf.txt.
   int block_n;
   if (cout % 192 == 0) block_n = 192;
   else if (cout % 96 == 0) block_n = 96;
-  else if (get_option(OPT_CONV_HALO) >= 2 && cout == 16) block_n = 16;
+  else if (cout == 16) block_n = 16;
   else return 1;
   // taps must be the full 3 x 3 x 3 stencil in (temporal, dh, dw) order with dh, dw in {-1, 0, 1}
   for (int kt = 0; kt < 3; ++kt)

@@ -150,6 +150,6 @@ def test_i2v_token_replace_blocks_vs_reference_fixture(golden_dir, record):
     f3, m3 = _bad(x, T["x_after_single"])
     record(double_img_bad_frac=f1, double_img_max=m1, double_txt_bad_frac=f2, single_bad_frac=f3, single_max=m3)
     assert f1 < 2e-3 and f2 < 2e-3 and f3 < 2e-3 and max(m1, m2, m3) < 0.13
-    # and the t2v path of the same weights differs (the replacement is not a no-op)
+    # and the t2v path of the same weights differs (the replacement is not a no-op; the later rows change too, through attention)
     img_t2v, _ = infer.infer_double_block(weights.double_blocks[0], T["img"].cuda().clone(), T["txt"].cuda().clone(), T["vec"].cuda(), cu, Li + Lt, freqs)
-    assert not torch.equal(img_t2v[:first], img[:first]) and _bad(img_t2v[first:], img[first:])[0] < 5e-2
+    assert _bad(img_t2v[:first], T["img_after_double"][:first])[0] > 0.1
