@@ -214,15 +214,18 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               tmem_cp_32x128b_w(tb + Cfg::kSfbCol + (BLOCK_N / 32) * k + 4 * t, sfb_lo + t * (2048 >> 4) + k * (512 >> 4), kDescHiSfNoSwz);
           }
         }
+        // one K-block = four MMAs, +32 bytes along K inside the 128B swizzle row = +2 in the (addr >> 4) field per step; the bf16 / fp8 runs are
+        // issued under one election (ptx.cuh: ~7 instead of ~22 SASS instructions per MMA in this warp)
+        static_assert(GEMM_BLOCK_K / GEMM_UMMA_K == 4, "MMA runs are four K-steps");
+        if constexpr (kF4) {
 #pragma unroll
-        for (int k = 0; k < GEMM_BLOCK_K / GEMM_UMMA_K; ++k) {
-          // +32 bytes along K inside the 128B swizzle row = +2 in the (addr >> 4) field
-          const uint32_t accum = (kb | k) != 0 ? 1u : 0u;
-          if constexpr (kF4)
+          for (int k = 0; k < 4; ++k)
             mma_f4_bs_w(d_tmem, a_lo + 2 * k, kDescHiSw128, b_lo + 2 * k, kDescHiSw128, idesc, tb + Cfg::kSfaCol + 4 * k,
-                        tb + Cfg::kSfbCol + (BLOCK_N / 32) * k, accum);
-          else if constexpr (kFp8) mma_f8_ss_w(d_tmem, a_lo + 2 * k, kDescHiSw128, b_lo + 2 * k, kDescHiSw128, idesc, accum);
-          else mma_f16_ss_w(d_tmem, a_lo + 2 * k, kDescHiSw128, b_lo + 2 * k, kDescHiSw128, idesc, accum);
+                        tb + Cfg::kSfbCol + (BLOCK_N / 32) * k, (kb | k) != 0 ? 1u : 0u);
+        } else if constexpr (kFp8) {
+          mma_f8_ss_w4(d_tmem, a_lo, kDescHiSw128, b_lo, kDescHiSw128, idesc, kb != 0 ? 1u : 0u);
+        } else {
+          mma_f16_ss_w4(d_tmem, a_lo, kDescHiSw128, b_lo, kDescHiSw128, idesc, kb != 0 ? 1u : 0u);
         }
         tc_commit_w(&empty_bar[stage]);  // frees the smem slot once these MMAs have read it
         if (++stage == kStages) {

@@ -283,15 +283,15 @@ __device__ __forceinline__ void mma_f16_ss_w(uint32_t d_tmem, uint32_t a_lo, uin
 // elect.sync: per MMA the single-MMA wrapper above costs ~22 SASS instructions in the issuing warp (ELECT, two VOTEU, five R2UR, moves,
 // and - when guarded by `if (k < ksteps)` - a BSSY / BSYNC pair), ~100 clocks, more than a 128 x 96 x 16 MMA's 56-clock floor
 // (profiles/r02_umma_rate_probe.txt, r02_halo96_v2 source view).  The first MMA takes the accumulate flag, the others accumulate.
-#define B200_MMA_STEP(off)                                                  \
+#define B200_MMA_STEP(kind, off)                                                \
   "add.u32 al, %1, " #off ";\n\t"                                           \
   "add.u32 bl, %3, " #off ";\n\t"                                           \
   "mov.b64 da, {al, %2};\n\t"                                               \
   "mov.b64 db, {bl, %4};\n\t"                                               \
-  "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, t;\n\t"
+  "tcgen05.mma.cta_group::1.kind::" kind " [%0], da, db, %5, t;\n\t"
 // an explicit branch around the run: ptxas then knows exactly one lane executes it and moves each operand to a uniform register once
 // (plain R2UR + UIADD3 per step) instead of re-broadcasting every operand of every MMA under the election predicate
-#define B200_MMA_HEAD                                                       \
+#define B200_MMA_HEAD(kind)                                                 \
   "{\n\t"                                                                   \
   ".reg .pred p, e, t;\n\t"                                                 \
   ".reg .b64 da, db;\n\t"                                                   \
@@ -302,17 +302,24 @@ __device__ __forceinline__ void mma_f16_ss_w(uint32_t d_tmem, uint32_t a_lo, uin
   "setp.eq.b32 t, 0, 0;\n\t"                                                \
   "mov.b64 da, {%1, %2};\n\t"                                               \
   "mov.b64 db, {%3, %4};\n\t"                                               \
-  "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t"
+  "tcgen05.mma.cta_group::1.kind::" kind " [%0], da, db, %5, p;\n\t"
 #define B200_MMA_TAIL "MMA_RUN_DONE:\n\t}\n"
 __device__ __forceinline__ void mma_f16_ss_w4(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi, uint32_t idesc,
                                               uint32_t accumulate) {
-  asm volatile(B200_MMA_HEAD B200_MMA_STEP(2) B200_MMA_STEP(4) B200_MMA_STEP(6) B200_MMA_TAIL ::"r"(d_tmem), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi),
+  asm volatile(B200_MMA_HEAD("f16") B200_MMA_STEP("f16", 2) B200_MMA_STEP("f16", 4) B200_MMA_STEP("f16", 6) B200_MMA_TAIL ::"r"(d_tmem), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi),
                "r"(idesc), "r"(accumulate)
                : "memory");
 }
 __device__ __forceinline__ void mma_f16_ss_w2(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi, uint32_t idesc,
                                               uint32_t accumulate) {
-  asm volatile(B200_MMA_HEAD B200_MMA_STEP(2) B200_MMA_TAIL ::"r"(d_tmem), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+  asm volatile(B200_MMA_HEAD("f16") B200_MMA_STEP("f16", 2) B200_MMA_TAIL ::"r"(d_tmem), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+               : "memory");
+}
+// fp8 (e4m3 x e4m3, K = 32 per MMA: the same 32-byte K-step inside the 128-byte swizzle row)
+__device__ __forceinline__ void mma_f8_ss_w4(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi, uint32_t idesc,
+                                             uint32_t accumulate) {
+  asm volatile(B200_MMA_HEAD("f8f6f4") B200_MMA_STEP("f8f6f4", 2) B200_MMA_STEP("f8f6f4", 4) B200_MMA_STEP("f8f6f4", 6) B200_MMA_TAIL ::"r"(d_tmem),
+               "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
                : "memory");
 }
 #undef B200_MMA_STEP
