@@ -654,6 +654,7 @@ def vae_decode_bench(cfg, dev, with_reference=True):
     from oracle import vae_oracle as V           # synthetic weights + (optional) the reference decode loop as GPU baseline
     C, Fr, Hh, Ww = cfg["target_shape"]
     Wd = V.synth_vae_weights(0)
+    resident = torch.cuda.memory_allocated()     # what the denoiser legs still hold in this process (weights, workspaces): not the decoder's
     dec = WanVAEDecoderB200(Wd, device=dev)
     g = torch.Generator(device=dev).manual_seed(3)
     zs = torch.randn(C, Fr, Hh, Ww, generator=g, device=dev)
@@ -672,7 +673,8 @@ def vae_decode_bench(cfg, dev, with_reference=True):
         torch.cuda.synchronize()
         ms = s.elapsed_time(e) / n
         res.update(value=round(mpix / (ms * 1e-3), 1), ms=round(ms, 1), effective_tflops=round(639.3 / (ms * 1e-3), 1),   # the reference algorithm's 639.3 TFLOP / time
-                   peak_mem_gb=round(torch.cuda.max_memory_allocated() / 2**30, 1))
+                   peak_mem_gb=round((torch.cuda.max_memory_allocated() - resident) / 2**30, 1),   # decoder weights + latent + activations + output
+                   resident_other_gb=round(resident / 2**30, 1))
         del img
     except Exception as ex:  # noqa
         res["error"] = str(ex)[:300]
