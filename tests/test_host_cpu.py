@@ -167,6 +167,40 @@ def test_unipc_scheduler_matches_reference_fixture(golden_dir):
         assert torch.allclose(sch.latents, ref, rtol=1e-5, atol=1e-5), (i, (sch.latents - ref).abs().max())
 
 
+def test_device_resident_scheduler_matches_the_eager_one_and_the_reference_fixture(golden_dir):
+    """host/wan_graph.py:WanSchedulerDevice (coefficient table + static in-place state, the scheduler the per-step CUDA graphs capture) vs
+    the eager WanScheduler and the REAL reference scheduler's fixture, step for step on the CPU: same latents bit for bit against the eager
+    class (every step kind occurs: first, second, steady state, last), fixture tolerance as in the test above."""
+    from safetensors import safe_open
+
+    from lightx2v_b200.host.wan_graph import WanSchedulerDevice
+    from lightx2v_b200.host.wan_scheduler import WanScheduler
+
+    with safe_open(os.path.join(golden_dir, "wan_scheduler_unipc.safetensors"), framework="pt") as f:
+        T = {k: f.get_tensor(k) for k in f.keys()}
+    cfg = dict(infer_steps=20, sample_shift=5.0, seed=42, target_shape=(16, 3, 8, 8), patch_size=(1, 2, 2))
+    eager, dev = WanScheduler(cfg, device="cpu"), WanSchedulerDevice(cfg, device="cpu")
+    eager.prepare()
+    dev.prepare()
+    assert torch.equal(dev.s_lat, T["latents_0"]) and dev.table.shape == (20, 12) and len(set(dev.kinds)) >= 3
+    g = torch.Generator().manual_seed(7)
+    for i in range(20):
+        eager.step_pre(i)
+        dev.load_step(i)
+        dev.step_pre()
+        assert torch.equal(dev.latents, eager.latents), i
+        # the fixture holds the reference's first 8 steps; later steps use fresh noise predictions
+        pred = T[f"noise_pred_{i}"] if i < 8 else torch.randn(eager.latents.shape, generator=g)
+        eager.noise_pred = pred
+        dev.noise_pred = pred.clone()
+        eager.step_post()
+        dev.step_post()
+        assert torch.equal(dev.latents, eager.latents), (i, dev.kind(i), (dev.latents - eager.latents).abs().max())
+        if i < 8:
+            assert torch.allclose(dev.latents, T[f"latents_post_{i}"], rtol=1e-5, atol=1e-5)
+    assert dev.kind(0) == (0, 1) and dev.kind(19)[1] == 1          # first step: no corrector, order 1; last step: predictor order 1
+
+
 def test_vae_dist_strip_bounds_match_reference_rules():
     """WanVAE.decode_dist (vae.py:883-922): 160 latent columns over 8 ranks -> 20-column chunks, 1-column halo, 160-pixel crops."""
     from lightx2v_b200.host.wan_vae import WanVAEDecoderB200 as D
