@@ -270,8 +270,10 @@ class WanModel:
             is_cond, cond_src, uncond_src, group = self.cfg_parallel
             mine = self._forward(inputs, is_cond).contiguous()
             world = dist.get_world_size(group)
-            both = torch.empty((world,) + tuple(mine.shape), dtype=mine.dtype, device=mine.device)
+            # output = the inputs concatenated along dim 0 (the layout every backend accepts; gloo rejects the stacked form)
+            both = torch.empty((world * mine.shape[0],) + tuple(mine.shape[1:]), dtype=mine.dtype, device=mine.device)
             dist.all_gather_into_tensor(both, mine, group=group)
+            both = both.view((world,) + tuple(mine.shape))
             cond, uncond = both[cond_src], both[uncond_src]
             self.scheduler.noise_pred = uncond + self.config["sample_guide_scale"] * (cond - uncond)
             return

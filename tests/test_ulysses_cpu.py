@@ -130,3 +130,46 @@ def test_hunyuan_ulysses_matches_joint_attention_world2():
         for r in range(world):
             ok, err = results[r]
             assert ok, (r, err)
+
+
+def _cfg_worker(rank, world, port, results):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from lightx2v_b200.host import ulysses as U
+        from lightx2v_b200.host.wan_model import WanModel
+
+        class Sched:
+            noise_pred = None
+
+        model = object.__new__(WanModel)
+        model.config = dict(enable_cfg=True, sample_guide_scale=5.0)
+        model.scheduler, model.cfg_parallel, model.pre_process, model.post_process = Sched(), None, None, None
+        calls = []
+
+        def forward(inputs, is_cond):                    # stands for the whole block stack: a function of the branch only
+            calls.append(is_cond)
+            g = torch.Generator().manual_seed(1 if is_cond else 2)
+            return torch.randn(16, 3, 8, 8, generator=g)
+
+        model._forward = forward
+        WanModel.infer(model, {})                        # serial CFG: cond then uncond on this rank
+        serial = model.scheduler.noise_pred.clone()
+        assert calls == [True, False]
+        del calls[:]
+        mode = U.parallelize_wan_cfg(model, 3 * 8 * 8, attention_fn=_oracle_attn, sp="nccl")
+        WanModel.infer(model, {})
+        results[rank] = (mode, list(calls), torch.equal(model.scheduler.noise_pred, serial))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_cfg_parallel_world2_runs_one_branch_per_rank_and_equals_serial_cfg():
+    """parallelize_wan_cfg on two ranks: rank 0 runs only the conditional forward, rank 1 only the unconditional one, the predictions are
+    exchanged and both ranks hold `uncond + g (cond - uncond)` bit-identical to the serial evaluation (wan/model.py:203-218)."""
+    world = 2
+    with mp.Manager() as m:
+        results = m.dict()
+        mp.spawn(_cfg_worker, args=(world, _free_port(), results), nprocs=world, join=True)
+        assert results[0] == ("cfg2", [True], True) and results[1] == ("cfg2", [False], True), dict(results)
