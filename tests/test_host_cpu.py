@@ -399,3 +399,35 @@ def test_weight_cache_is_rebuilt_when_the_weights_change():
     assert infer._cache(sa) is not c2
     infer.clear_weight_caches()
     assert not infer._caches
+
+
+def test_install_into_the_real_reference_registries_and_uninstall():
+    """registry.install_into_lightx2v() against the REAL LightX2V registries (vendored copy / build container; CPU shims of
+    oracle/ref_loader.py): the B200 keys appear, the two hard-coded norm keys are overridden, the reference's own weight tree then
+    builds B200 op objects from a stock config, and uninstall puts the reference's norm classes back."""
+    from oracle import ref_loader
+
+    if not ref_loader.import_reference():
+        pytest.skip("reference package not available here")
+    from lightx2v.utils import registry_factory as rf
+
+    from lightx2v_b200.host import ops, registry
+
+    ref_rms, ref_ln = rf.RMS_WEIGHT_REGISTER["sgl-kernel"], rf.LN_WEIGHT_REGISTER["Default"]
+    assert ref_rms is not ops.RMSWeightB200 and ref_ln is not ops.LNWeightB200
+    try:
+        assert registry.install_into_lightx2v() is True
+        assert rf.MM_WEIGHT_REGISTER[registry.MM_KEY] is ops.MMWeightB200 and rf.ATTN_WEIGHT_REGISTER[registry.ATTN_KEY] is ops.FmhaWeightB200
+        assert rf.MM_WEIGHT_REGISTER[ops.FP8_MM_KEY] is ops.MMWeightFp8B200 and rf.MM_WEIGHT_REGISTER[ops.NVFP4_MM_KEY] is ops.MMWeightNvfp4B200
+        assert rf.RMS_WEIGHT_REGISTER["sgl-kernel"] is ops.RMSWeightB200 and rf.LN_WEIGHT_REGISTER["Default"] is ops.LNWeightB200
+        assert registry.install_into_lightx2v() is True                      # idempotent: no "already exists"
+        # the reference's OWN weight tree, driven by a stock config that names the B200 keys
+        from lightx2v.models.networks.wan.weights.transformer_weights import WanTransformerWeights
+
+        cfg = ref_loader.ref_config(dim=128, num_heads=1, ffn_dim=256, num_layers=1, mm_type=registry.MM_KEY, attn_type=registry.ATTN_KEY)
+        tree = WanTransformerWeights(cfg)
+        kinds = {type(m).__name__ for blk in tree.blocks for phase in blk.compute_phases for m in phase._modules.values()}
+        assert {"MMWeightB200", "FmhaWeightB200", "RMSWeightB200"} <= kinds, kinds
+    finally:
+        registry.uninstall_from_lightx2v()
+    assert rf.RMS_WEIGHT_REGISTER["sgl-kernel"] is ref_rms and rf.LN_WEIGHT_REGISTER["Default"] is ref_ln
