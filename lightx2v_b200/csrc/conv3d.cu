@@ -114,11 +114,11 @@ conv3d_igemm_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_const
     prefetch_tmap(&tmOut);
   }
   if (warp == 1 && lane == 0) {
-    // With two sub-tiles the MMAs are issued by TWO warps (warp 1: sub-tile 0, warp 3: sub-tile 1): one elected lane needs ~17 SASS
-    // instructions (ELECT / R2UR / VOTEU / address adds) per UTCHMMA, ~100 clocks, while a 128 x 96 x 16 MMA occupies the tensor pipe for 48 -
-    // round 2's ncu source view shows the single issuing warp permanently busy, the producer blocked on free slots and the tensor pipe at
-    // 45-50 % for every N = 96 formulation (8 % at N = 16), independent of L2 traffic.  Each issuer commits its own MMAs, so the
-    // slot-release and accumulator-ready barriers expect one arrival per issuer.
+    // With two sub-tiles the MMAs are issued by TWO warps (warp 1: sub-tile 0, warp 3: sub-tile 1), each committing its own MMAs, so the
+    // slot-release and accumulator-ready barriers expect one arrival per issuer.  Measured (profiles/r02_conv_two_issuers.txt): one elected
+    // lane spends ~17-22 SASS instructions (ELECT / R2UR / VOTEU / address adds) per UTCHMMA, but these per-tap tiles are bound by the TMA
+    // ingest (~64 B/clk/SM, DESIGN.md section 4 law 2), not by the issue rate: the second issuer is neutral here (975 vs 979 TFLOP/s at
+    // 96 -> 96) and is what lifts the halo-staged tiles of conv3d_halo.cu, which share this warp layout.
     constexpr int kIssuers = Cfg::kMSub == 2 ? 2 : 1;
     for (int i = 0; i < CONV_STAGES; ++i) {
       mbar_init(&full_bar[i], 1);
