@@ -30,9 +30,9 @@ constexpr int CONV_STAGING_BYTES = CONV_BLOCK_M * 64 * 2;        // 16 KB (64 ou
 // (96 / 192 output channels) a 128-voxel tile gives only ~290 tensor cycles per pipeline stage, far below the TMA round trip;
 // two sub-tiles double the MMA work per byte of weight traffic and per barrier.
 //
-// K-chunk geometries.  The TMA unit retires ~0.75 box rows per clock per SM whatever their width (round 2: the 128-byte-row GEMM
-// tiles and the 64-byte-row tiles below stall at the same rows / clock), so a stage should be made of 128-byte rows wherever the
-// channel count allows:
+// K-chunk geometries.  These per-tap tiles are bound by the TMA ingest into the SM (law 2): ~64 B/clk/SM with
+// 128-byte box rows, and measurably less with 64-byte rows (A/B at the decoder's shapes: profiles/r02_conv_tiles_ab.txt, +7 % at 96 -> 96,
+// +28 % at 192 -> 192), so a stage should be made of 128-byte rows wherever the channel count allows:
 //   CONV_WIDE    64-channel chunks (128-byte rows, SWIZZLE_128B), one per stage, four stages: cin % 64 == 0 (192 / 384 channels of the
 //                Wan decoder, 128 / 256 / 512 of the HunyuanVideo decoder);
 //   CONV_MIXED96 cin % 96 == 0 but not % 64 (the 96-channel stage of the Wan decoder): a stage is one 96-channel group of one tap,
