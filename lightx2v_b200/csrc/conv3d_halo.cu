@@ -1,5 +1,5 @@
-// Halo-staged implicit-GEMM 3x3x3 convolution for the wide stages of the Wan VAE (W >= 512: the 96-channel 720 x 1280 and 192-channel
-// 360 x 640 stages, 62 % of the decode in round 1).
+// Halo-staged implicit-GEMM 3x3x3 convolution for the wide stages of the Wan VAE (W >= 512: the 96-channel 720 x 1280 stage incl. its
+// 16-wide head, and the 192-channel 360 x 640 stage - 62 % of the decode).
 //
 // Why: conv3d.cu fetches the A operand of EVERY tap separately (a TMA box shifted by the tap offset), i.e. each input voxel crosses
 // L2 -> shared memory 27 times per output tile; ncu (profiles/r01_misc_kernels_ncu_summary.txt, profiles/r02_*conv*) shows those tiles at
@@ -15,12 +15,14 @@
 // shifts 0..8) is read correctly with base_offset = 0 - the tensor core, like the TMA unit, derives the swizzle phase from ABSOLUTE
 // shared-memory address bits - and incorrectly with base_offset = row % 8.  So a row-shifted view is just "start address + rows * 128".
 //
-// Work per pipeline slot (N = 96): A halo 68 KB feeds 9 taps x 2 rows x 4 K-steps = 72 MMAs (3456 tensor clocks); the nine 12 KB weight
-// tiles stream through their own ring.  Bytes per tensor clock: 51 (conv3d.cu MIXED96: 115), TMA rows per clock: 0.41 (1.22).
+// Work per pipeline slot (N = 96): A halo 68 KB feeds 9 taps x 2 rows x 4 K-steps = 72 MMAs; the nine 12 KB weight tiles stream through
+// their own ring: 2.5 KB of TMA ingest per MMA against 5.6 KB for conv3d.cu's MIXED96 tiles, which sit at the ~64 B/clk/SM ingest ceiling
+// (law 2).  With the ingest out of the way the MMA warp's issue rate became the limit, hence the two issuing warps
+// and the runs of four MMAs under one election below (law 3); what remains at N = 96 is the operand-read floor of law 1 (56 clocks per MMA).
 //
 // Warp roles: warp 0 loads halo tiles, warp 2 (after allocating TMEM) loads weight tiles - independent rings, so a stalled weight slot
-// never delays the next halo prefetch -, warps 1 and 3 issue tcgen05.mma for output row 0 / row 1 (two issuers: one elected lane needs
-// ~100 clocks of ELECT / R2UR / address instructions per UTCHMMA, see conv3d.cu), warps 4-7 run the epilogue.
+// never delays the next halo prefetch -, warps 1 and 3 issue tcgen05.mma for output row 0 / row 1 (two issuers, each issuing a tap's K-steps as one run:
+// ptx.cuh mma_f16_ss_w4 / _w2), warps 4-7 run the epilogue.
 #include "host_util.cuh"
 #include "ptx.cuh"
 
@@ -190,7 +192,7 @@ conv3d_halo_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_consta
         tc_fence_after();
         // descriptor of this issuer's output row at tap (dh, dw) = (-1, -1); tap (dh, dw) starts (dh * HALO_W + dw) rows = that many
         // 128-byte units further on (the low word counts 16-byte units).  The 9 taps are unrolled so the offsets - and base_offset =
-        // row % 8 = dw, as HALO_W % 8 == 0 - are immediates: the issue loop is what bounds this kernel (see HaloCfg).
+        // row % 8 = dw, as HALO_W % 8 == 0 - are immediates: the issue loop is what bounded this kernel (file header).
         const uint32_t a_row0 = desc_lo_kmajor(a_base + aslot * HALO_A_BYTES + (uint32_t)ms * HALO_W * 128);
         const bool full_chunk = ksteps == 4;
 #pragma unroll
