@@ -261,9 +261,11 @@ __device__ __forceinline__ void mma_f8_ss(uint32_t d_tmem, uint64_t a_desc, uint
       : "memory");
 }
 
-// Warp-collective issue forms: called by ALL 32 lanes of a converged warp with warp-uniform operands (so ptxas keeps
-// descriptors in uniform registers and UTCHMMA issues without R2UR round trips); one elected lane executes the MMA.
-// Descriptors are passed as (lo, hi) 32-bit halves.
+// Warp-collective issue forms: called by ALL 32 lanes of a converged warp with warp-uniform operands; one elected lane executes the
+// MMA.  Descriptors are passed as (lo, hi) 32-bit halves.  Measured cost in the issuing warp (round-2 ncu source views): the
+// single-MMA forms below compile to ELECT + two VOTEU + five predicated R2UR.BROADCAST + moves, 17-22 SASS instructions per UTCHMMA (a
+// divergent `if (lane == 0)` around a plain MMA was ~100); the run forms further down (mma_f16_ss_w4 / _w2, mma_f8_ss_w4,
+// mma_f16_ts_w4) are what the hot loops use.
 __device__ __forceinline__ void mma_f16_ss_w(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
                                              uint32_t idesc, uint32_t accumulate) {
   asm volatile(
